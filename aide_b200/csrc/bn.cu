@@ -1,0 +1,436 @@
+// bn.cu -- BatchNorm2d (+ReLU, +MaxPool2d(2,2), +concat-slot write) forward and backward.
+//
+// All kernels are HBM-bound streaming kernels over NHWC fp32 data: 128-bit loads/stores, 4 channels
+// per thread, channel index fastest across threadIdx.x so that a warp reads contiguous 512 B.
+// Reductions are two-stage and fixed-order (per-block partial rows -> fp64 column reduction), so
+// results are bit-reproducible run to run (no float atomics).
+#include "common.cuh"
+
+namespace aide {
+
+// ------------------------------------------------------------------ column reduction of partial rows
+// out[j] = sum_r partial[r*ld + j]  for j < cols, accumulated in fp64 in fixed order.
+// block = (32 columns, 8 row lanes)
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int ld, int cols,
+                                   float* __restrict__ out) {
+  __shared__ double sm[8][33];
+  int j = blockIdx.x * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (j < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) acc += (double)partial[(size_t)r * ld + j];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    out[j] = (float)t;
+  }
+}
+
+int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* out, cudaStream_t st) {
+  reduce_rows_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, rows, ld, cols, out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward statistics finalize
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                   int training, float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0;
+  if (training && c < C) {
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      a += (double)partial[((size_t)r * 2 + 0) * C + c];
+      b += (double)partial[((size_t)r * 2 + 1) * C + c];
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  float mean, var;
+  if (training) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sa += s1[k][threadIdx.x];
+      sb += s2[k][threadIdx.x];
+    }
+    double m = sa / count;
+    double v = sb / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (rmean) {
+      double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rmean[c];
+    var = rvar[c];
+  }
+  float rstd = 1.0f / sqrtf(var + eps);
+  float sc = gamma[c] * rstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - mean * sc;
+  if (mean_rstd) {
+    mean_rstd[c] = mean;
+    mean_rstd[C + c] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------ forward apply
+__device__ __forceinline__ float4 bn_relu4(float4 z, float4 sc, float4 sh) {
+  return make_float4(fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), fmaxf(fmaf(z.y, sc.y, sh.y), 0.f),
+                     fmaxf(fmaf(z.z, sc.z, sh.z), 0.f), fmaxf(fmaf(z.w, sc.w, sh.w), 0.f));
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+template <int FMT, bool POOL>
+__global__ void bn_relu_apply_kernel(const float* __restrict__ z, int N, int H, int W, int C,
+                                     const float* __restrict__ scale_shift, View dst, View pa, View pb) {
+  const int C4 = C >> 2;
+  if constexpr (!POOL) {
+    size_t total = (size_t)N * H * W * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      int c = (int)(i % C4) * 4;
+      size_t pix = i / C4;
+      float4 sc = __ldg(reinterpret_cast<const float4*>(scale_shift + c));
+      float4 sh = __ldg(reinterpret_cast<const float4*>(scale_shift + C + c));
+      float4 v = *reinterpret_cast<const float4*>(z + pix * C + c);
+      st4<FMT>(dst.p0, dst.p1, pix * dst.ctot + dst.coff + c, bn_relu4(v, sc, sh));
+    }
+  } else {
+    const int Hh = H >> 1, Wh = W >> 1;
+    size_t total = (size_t)N * Hh * Wh * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      int c = (int)(i % C4) * 4;
+      size_t win = i / C4;
+      int wx = (int)(win % Wh);
+      int hy = (int)((win / Wh) % Hh);
+      int n = (int)(win / ((size_t)Wh * Hh));
+      float4 sc = __ldg(reinterpret_cast<const float4*>(scale_shift + c));
+      float4 sh = __ldg(reinterpret_cast<const float4*>(scale_shift + C + c));
+      size_t p00 = ((size_t)n * H + 2 * hy) * W + 2 * wx;
+      size_t p01 = p00 + 1, p10 = p00 + W, p11 = p10 + 1;
+      float4 y00 = bn_relu4(*reinterpret_cast<const float4*>(z + p00 * C + c), sc, sh);
+      float4 y01 = bn_relu4(*reinterpret_cast<const float4*>(z + p01 * C + c), sc, sh);
+      float4 y10 = bn_relu4(*reinterpret_cast<const float4*>(z + p10 * C + c), sc, sh);
+      float4 y11 = bn_relu4(*reinterpret_cast<const float4*>(z + p11 * C + c), sc, sh);
+      if (dst.p0) {
+        st4<FMT>(dst.p0, dst.p1, p00 * dst.ctot + dst.coff + c, y00);
+        st4<FMT>(dst.p0, dst.p1, p01 * dst.ctot + dst.coff + c, y01);
+        st4<FMT>(dst.p0, dst.p1, p10 * dst.ctot + dst.coff + c, y10);
+        st4<FMT>(dst.p0, dst.p1, p11 * dst.ctot + dst.coff + c, y11);
+      }
+      float4 m = max4(max4(y00, y01), max4(y10, y11));
+      if (pa.p0) st4<FMT>(pa.p0, pa.p1, win * pa.ctot + pa.coff + c, m);
+      if (pb.p0) st4<FMT>(pb.p0, pb.p1, win * pb.ctot + pb.coff + c, m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward stage 1
+struct BwdSrcs {
+  const float* dptr[3];
+  int dctot[3], dcoff[3], nd;
+  const float* pptr[3];
+  int pctot[3], pcoff[3], np;
+};
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// first-max-wins selection mask for one channel of a 2x2 window (scan order 00,01,10,11; strict >)
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  int k = 0;
+  float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  return k;
+}
+
+// blockDim = (cx, ty); grid = (rows, cgroups).  Each thread owns 4 channels and walks 2x2 windows
+// (WINDOW: needed when pooled sources exist) or single pixels (any H, W).
+template <bool WINDOW>
+__global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ scale_shift,
+                                          const float* __restrict__ mean_rstd, int N, int H, int W, int C,
+                                          BwdSrcs s, float* __restrict__ g, float* __restrict__ partial) {
+  extern __shared__ float smem[];  // [ty][cx*8]
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const bool cvalid = c < C;
+  constexpr int KP = WINDOW ? 4 : 1;
+  const int Hh = WINDOW ? (H >> 1) : H, Wh = WINDOW ? (W >> 1) : W;
+  const size_t nwin = (size_t)N * Hh * Wh;
+  float sg[4] = {0, 0, 0, 0}, sgx[4] = {0, 0, 0, 0};
+  if (cvalid) {
+    const float4 sc = *reinterpret_cast<const float4*>(scale_shift + c);
+    const float4 sh = *reinterpret_cast<const float4*>(scale_shift + C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean_rstd + c);
+    const float4 rs = *reinterpret_cast<const float4*>(mean_rstd + C + c);
+    for (size_t win = (size_t)blockIdx.x * blockDim.y + threadIdx.y; win < nwin;
+         win += (size_t)gridDim.x * blockDim.y) {
+      size_t p[KP];
+      if constexpr (WINDOW) {
+        int wx = (int)(win % Wh);
+        int hy = (int)((win / Wh) % Hh);
+        int n = (int)(win / ((size_t)Wh * Hh));
+        p[0] = ((size_t)n * H + 2 * hy) * W + 2 * wx;
+        p[1] = p[0] + 1;
+        p[2] = p[0] + W;
+        p[3] = p[2] + 1;
+      } else {
+        p[0] = win;
+      }
+      float4 zz[KP], yy[KP], gg[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        zz[k] = *reinterpret_cast<const float4*>(z + p[k] * C + c);
+        yy[k] = bn_relu4(zz[k], sc, sh);
+        gg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int d = 0; d < s.nd; ++d) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          gg[k] = add4(gg[k], *reinterpret_cast<const float4*>(s.dptr[d] + p[k] * s.dctot[d] + s.dcoff[d] + c));
+      }
+      if constexpr (WINDOW) {
+        float4 pg = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int d = 0; d < s.np; ++d)
+          pg = add4(pg, *reinterpret_cast<const float4*>(s.pptr[d] + win * s.pctot[d] + s.pcoff[d] + c));
+        int kx = argmax4(yy[0].x, yy[1].x, yy[2].x, yy[3].x);
+        int ky = argmax4(yy[0].y, yy[1].y, yy[2].y, yy[3].y);
+        int kz = argmax4(yy[0].z, yy[1].z, yy[2].z, yy[3].z);
+        int kw = argmax4(yy[0].w, yy[1].w, yy[2].w, yy[3].w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (kx == k) gg[k].x += pg.x;
+          if (ky == k) gg[k].y += pg.y;
+          if (kz == k) gg[k].z += pg.z;
+          if (kw == k) gg[k].w += pg.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        float4 o;
+        o.x = yy[k].x > 0.f ? gg[k].x : 0.f;
+        o.y = yy[k].y > 0.f ? gg[k].y : 0.f;
+        o.z = yy[k].z > 0.f ? gg[k].z : 0.f;
+        o.w = yy[k].w > 0.f ? gg[k].w : 0.f;
+        *reinterpret_cast<float4*>(g + p[k] * C + c) = o;
+        sg[0] += o.x; sg[1] += o.y; sg[2] += o.z; sg[3] += o.w;
+        sgx[0] += o.x * ((zz[k].x - mu.x) * rs.x);
+        sgx[1] += o.y * ((zz[k].y - mu.y) * rs.y);
+        sgx[2] += o.z * ((zz[k].z - mu.z) * rs.z);
+        sgx[3] += o.w * ((zz[k].w - mu.w) * rs.w);
+      }
+    }
+  }
+  // block reduction over threadIdx.y (fixed order)
+  float* row = smem + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    row[k] = sg[k];
+    row[4 + k] = sgx[k];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && cvalid) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < (int)blockDim.y; ++t) {
+      const float* r = smem + ((size_t)t * blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += r[k];
+    }
+    float* out = partial + (size_t)blockIdx.x * 2 * C;
+    *reinterpret_cast<float4*>(out + c) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(out + C + c) = make_float4(a[4], a[5], a[6], a[7]);
+  }
+}
+
+// ------------------------------------------------------------------ backward stage 2
+template <int FMT>
+__global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z,
+                                         const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ sums /*[2][C]: sum g, sum g*xhat*/, float inv_count,
+                                         size_t npix, int C, void* dz0, void* dz1, float* __restrict__ partial2) {
+  extern __shared__ float smem[];  // [ty][cx*4]
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const bool cvalid = c < C;
+  float sd[4] = {0, 0, 0, 0};
+  if (cvalid) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean_rstd + c);
+    const float4 rs = *reinterpret_cast<const float4*>(mean_rstd + C + c);
+    const float4 ga = make_float4(gamma[c], gamma[c + 1], gamma[c + 2], gamma[c + 3]);
+    const float4 s1 = *reinterpret_cast<const float4*>(sums + c);
+    const float4 s2 = *reinterpret_cast<const float4*>(sums + C + c);
+    const float4 k0 = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+    const float4 m1 = make_float4(s1.x * inv_count, s1.y * inv_count, s1.z * inv_count, s1.w * inv_count);
+    const float4 m2 = make_float4(s2.x * inv_count, s2.y * inv_count, s2.z * inv_count, s2.w * inv_count);
+    for (size_t p = (size_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += (size_t)gridDim.x * blockDim.y) {
+      float4 gv = *reinterpret_cast<const float4*>(g + p * C + c);
+      float4 zv = *reinterpret_cast<const float4*>(z + p * C + c);
+      float4 d;
+      d.x = k0.x * (gv.x - m1.x - ((zv.x - mu.x) * rs.x) * m2.x);
+      d.y = k0.y * (gv.y - m1.y - ((zv.y - mu.y) * rs.y) * m2.y);
+      d.z = k0.z * (gv.z - m1.z - ((zv.z - mu.z) * rs.z) * m2.z);
+      d.w = k0.w * (gv.w - m1.w - ((zv.w - mu.w) * rs.w) * m2.w);
+      st4<FMT>(dz0, dz1, p * C + c, d);
+      sd[0] += d.x; sd[1] += d.y; sd[2] += d.z; sd[3] += d.w;
+    }
+  }
+  float* row = smem + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) row[k] = sd[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && cvalid) {
+    float a[4] = {0, 0, 0, 0};
+    for (int t = 0; t < (int)blockDim.y; ++t) {
+      const float* r = smem + ((size_t)t * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += r[k];
+    }
+    *reinterpret_cast<float4*>(partial2 + (size_t)blockIdx.x * C + c) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+}
+
+// shared geometry for the two backward kernels
+struct BwdGeom {
+  int cx, ty, cgroups, rows;
+};
+static BwdGeom bwd_geom(int N, int H, int W, int C) {
+  BwdGeom gm;
+  int c4 = C / 4;
+  gm.cx = c4 < 64 ? c4 : 64;
+  gm.ty = 256 / gm.cx;
+  if (gm.ty < 1) gm.ty = 1;
+  gm.cgroups = ceil_div(c4, gm.cx);
+  long long nwin = ((long long)N * H * W + 3) / 4;
+  long long want = (nwin + gm.ty * 4 - 1) / (gm.ty * 4);  // >= 4 windows per thread
+  long long cap = (long long)kNumSMs * 8 / gm.cgroups;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  gm.rows = (int)want;
+  return gm;
+}
+
+}  // namespace aide
+
+using namespace aide;
+
+extern "C" int aide_bn_finalize(const float* stat_partial, int rows, int C, double count, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum,
+                                float eps, int training, float* scale_shift, float* mean_rstd, void* stream) {
+  AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift, "bn_finalize: bad arguments");
+  AIDE_REQUIRE(training ? (stat_partial && rows > 0 && count > 0) : (running_mean && running_var),
+               "bn_finalize: missing statistics input");
+  dim3 block(32, 8), grid(ceil_div(C, 32));
+  bn_finalize_kernel<<<grid, block, 0, as_stream(stream)>>>(stat_partial, rows, C, count, gamma, beta,
+                                                            running_mean, running_var, momentum, eps, training,
+                                                            scale_shift, mean_rstd);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, int C, const float* scale_shift,
+                                  void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff, void* poolA_p0,
+                                  void* poolA_p1, int poolA_ctot, int poolA_coff, void* poolB_p0, void* poolB_p1,
+                                  int poolB_ctot, int poolB_coff, void* stream) {
+  AIDE_REQUIRE(z && scale_shift && C % 4 == 0 && N > 0, "bn_relu_apply: bad arguments (C %% 4 must be 0)");
+  const bool pool = poolA_p0 || poolB_p0;
+  AIDE_REQUIRE(pool || dst_p0, "bn_relu_apply: no destination");
+  AIDE_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "bn_relu_apply: pooling needs even H, W");
+  AIDE_REQUIRE((dst_coff % 4 == 0) && (dst_ctot % 4 == 0) && (poolA_coff % 4 == 0) && (poolB_coff % 4 == 0),
+               "bn_relu_apply: channel offsets must be multiples of 4");
+  View dst{dst_p0, dst_p1, dst_ctot, dst_coff}, pa{poolA_p0, poolA_p1, poolA_ctot, poolA_coff},
+      pb{poolB_p0, poolB_p1, poolB_ctot, poolB_coff};
+  size_t total = (size_t)N * H * W * (C / 4) / (pool ? 4 : 1);
+  int blocks = (int)((total + 255) / 256);
+  int cap = kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (pool) {
+    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, true><<<blocks, 256, 0, as_stream(stream)>>>(
+                               z, N, H, W, C, scale_shift, dst, pa, pb)));
+  } else {
+    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, false><<<blocks, 256, 0, as_stream(stream)>>>(
+                               z, N, H, W, C, scale_shift, dst, pa, pb)));
+  }
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_bn_bwd_rows(int N, int H, int W, int C) { return bwd_geom(N, H, W, C).rows; }
+
+extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift, const float* mean_rstd, int N,
+                                       int H, int W, int C, const float* const* direct_ptr, const int* direct_ctot,
+                                       const int* direct_coff, int n_direct, const float* const* pool_ptr,
+                                       const int* pool_ctot, const int* pool_coff, int n_pool, float* g,
+                                       float* partial, void* stream) {
+  AIDE_REQUIRE(z && scale_shift && mean_rstd && g && partial, "bn_relu_bwd_reduce: null argument");
+  AIDE_REQUIRE(C % 4 == 0, "bn_relu_bwd_reduce: need C%%4==0");
+  AIDE_REQUIRE(n_pool == 0 || (H % 2 == 0 && W % 2 == 0), "bn_relu_bwd_reduce: pooled sources need even H,W");
+  AIDE_REQUIRE(n_direct >= 0 && n_direct <= 3 && n_pool >= 0 && n_pool <= 3 && n_direct + n_pool > 0,
+               "bn_relu_bwd_reduce: up to 3 direct and 3 pooled gradient sources supported (at least one)");
+  BwdSrcs s{};
+  s.nd = n_direct;
+  s.np = n_pool;
+  for (int i = 0; i < n_direct; ++i) {
+    s.dptr[i] = direct_ptr[i];
+    s.dctot[i] = direct_ctot[i];
+    s.dcoff[i] = direct_coff[i];
+    AIDE_REQUIRE(s.dptr[i] && s.dctot[i] % 4 == 0 && s.dcoff[i] % 4 == 0, "bn_relu_bwd_reduce: bad direct source");
+  }
+  for (int i = 0; i < n_pool; ++i) {
+    s.pptr[i] = pool_ptr[i];
+    s.pctot[i] = pool_ctot[i];
+    s.pcoff[i] = pool_coff[i];
+    AIDE_REQUIRE(s.pptr[i] && s.pctot[i] % 4 == 0 && s.pcoff[i] % 4 == 0, "bn_relu_bwd_reduce: bad pooled source");
+  }
+  BwdGeom gm = bwd_geom(N, H, W, C);
+  dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
+  size_t smem = (size_t)gm.cx * gm.ty * 8 * sizeof(float);
+  if (n_pool > 0)
+    bn_relu_bwd_reduce_kernel<true><<<grid, block, smem, as_stream(stream)>>>(z, scale_shift, mean_rstd, N, H, W, C,
+                                                                              s, g, partial);
+  else
+    bn_relu_bwd_reduce_kernel<false><<<grid, block, smem, as_stream(stream)>>>(z, scale_shift, mean_rstd, N, H, W, C,
+                                                                               s, g, partial);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd,
+                                      const float* gamma, const float* partial, int rows, int N, int H, int W, int C,
+                                      void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
+                                      float* partial2, void* stream) {
+  AIDE_REQUIRE(g && z && mean_rstd && gamma && partial && dz_p0 && dgamma && dbeta && partial2,
+               "bn_relu_bwd_apply: null argument");
+  AIDE_REQUIRE(dbeta + C == dgamma, "bn_relu_bwd_apply: dbeta/dgamma must be adjacent ([2][C] buffer: dbeta, dgamma)");
+  BwdGeom gm = bwd_geom(N, H, W, C);
+  AIDE_REQUIRE(rows == gm.rows, "bn_relu_bwd_apply: rows mismatch (%d vs %d)", rows, gm.rows);
+  cudaStream_t st = as_stream(stream);
+  // sums[0..C) = sum g (= dbeta), sums[C..2C) = sum g*xhat (= dgamma)
+  reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
+  AIDE_CHECK_LAUNCH();
+  size_t npix = (size_t)N * H * W;
+  dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
+  size_t smem = (size_t)gm.cx * gm.ty * 4 * sizeof(float);
+  float inv = (float)(1.0 / (double)npix);
+  AIDE_DISPATCH_FMT(fmt, (bn_relu_bwd_apply_kernel<FMT><<<grid, block, smem, st>>>(
+                             g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2)));
+  AIDE_CHECK_LAUNCH();
+  if (dbias_conv) {
+    reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(partial2, rows, C, C, dbias_conv);
+    AIDE_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -1,0 +1,145 @@
+// common.cuh -- shared helpers for libaide_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/aide_b200.h"
+
+namespace aide {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define AIDE_CUDA(expr)                                                          \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return ::aide::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+#define AIDE_CHECK_LAUNCH() AIDE_CUDA(cudaGetLastError())
+#define AIDE_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::aide::set_error(__VA_ARGS__);           \
+      return 1;                                 \
+    }                                           \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ operand-format views
+struct View {
+  void* p0;
+  void* p1;
+  int ctot;
+  int coff;
+};
+struct CView {
+  const void* p0;
+  const void* p1;
+  int ctot;
+  int coff;
+};
+
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Load/store 4 consecutive channels (c % 4 == 0, view channel offsets are multiples of 4).
+template <int FMT>
+__device__ __forceinline__ float4 ld4(const void* p0, const void* p1, size_t e) {
+  if constexpr (FMT == AIDE_FMT_F32) {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p0) + e);
+  } else if constexpr (FMT == AIDE_FMT_TF32X2) {
+    float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p0) + e);
+    float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p1) + e);
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  } else {
+    uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p0) + e);
+    __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void st4(void* p0, void* p1, size_t e, float4 v) {
+  if constexpr (FMT == AIDE_FMT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p0) + e) = v;
+  } else if constexpr (FMT == AIDE_FMT_TF32X2) {
+    float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+    float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p0) + e) = h;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p1) + e) = l;
+  } else {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo);
+    r.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p0) + e) = r;
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ float ld1(const void* p0, const void* p1, size_t e) {
+  if constexpr (FMT == AIDE_FMT_F32) {
+    return reinterpret_cast<const float*>(p0)[e];
+  } else if constexpr (FMT == AIDE_FMT_TF32X2) {
+    return reinterpret_cast<const float*>(p0)[e] + reinterpret_cast<const float*>(p1)[e];
+  } else {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p0)[e]);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void st1(void* p0, void* p1, size_t e, float v) {
+  if constexpr (FMT == AIDE_FMT_F32) {
+    reinterpret_cast<float*>(p0)[e] = v;
+  } else if constexpr (FMT == AIDE_FMT_TF32X2) {
+    float h = tf32_rn(v);
+    reinterpret_cast<float*>(p0)[e] = h;
+    reinterpret_cast<float*>(p1)[e] = v - h;
+  } else {
+    reinterpret_cast<__nv_bfloat16*>(p0)[e] = __float2bfloat16_rn(v);
+  }
+}
+
+inline int fmt_elem_bytes(int fmt) { return fmt == AIDE_FMT_BF16 ? 2 : 4; }
+inline bool fmt_valid(int fmt) { return fmt >= 0 && fmt <= 2; }
+
+// dispatch a templated launcher on the runtime format
+#define AIDE_DISPATCH_FMT(fmt, ...)                                   \
+  switch (fmt) {                                                      \
+    case AIDE_FMT_F32: { constexpr int FMT = AIDE_FMT_F32; __VA_ARGS__; break; }       \
+    case AIDE_FMT_TF32X2: { constexpr int FMT = AIDE_FMT_TF32X2; __VA_ARGS__; break; } \
+    case AIDE_FMT_BF16: { constexpr int FMT = AIDE_FMT_BF16; __VA_ARGS__; break; }     \
+    default: ::aide::set_error("bad operand format %d", fmt); return 1;                 \
+  }
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// out[j] = sum_r partial[r*ld + j] (j < cols), fp64 accumulation in fixed order (defined in bn.cu)
+int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* out, cudaStream_t st);
+
+// warp / block reductions ------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace aide

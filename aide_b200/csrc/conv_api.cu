@@ -1,0 +1,68 @@
+// conv_api.cu -- C-ABI entry points for conv3x3 forward/dgrad/wgrad: dispatch between the CUDA-core
+// exact path (AIDE_FMT_F32, and layers that do not fit an MMA shape) and the tcgen05 path.
+#include "common.cuh"
+
+namespace aide {
+int simt_stat_rows(int N, int H, int W);
+int simt_conv3x3(const float* x, int x_ctot, int x_coff, int cin, const float* w, const float* bias, float* z,
+                 int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial, cudaStream_t st);
+size_t simt_wgrad_workspace_bytes(int cin, int cout, int N, int H, int W);
+int simt_wgrad(const float* x, int x_ctot, int x_coff, int cin, const float* dz, int cout, int N, int H, int W,
+               float* ws, size_t ws_bytes, float* dw, cudaStream_t st);
+int tc_stat_rows(int N, int H, int W);
+bool tc_shape_ok(int fmt, int cin, int cout);
+int tc_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
+               const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
+               cudaStream_t st);
+size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
+int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
+             int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st);
+bool tma_available();
+}  // namespace aide
+
+using namespace aide;
+
+extern "C" int aide_has_tma(void) { return tma_available() ? 1 : 0; }
+
+extern "C" int aide_conv3x3_stat_rows(int fmt, int N, int H, int W) {
+  return fmt == AIDE_FMT_F32 ? simt_stat_rows(N, H, W) : tc_stat_rows(N, H, W);
+}
+
+extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                                const void* w_p0, const void* w_p1, const float* bias, float* z, int z_ctot,
+                                int z_coff, int cout, int N, int H, int W, float* stat_partial, void* stream) {
+  AIDE_REQUIRE(x_p0 && w_p0 && z && cin > 0 && cout > 0 && N > 0 && H > 0 && W > 0, "conv3x3_fwd: bad arguments");
+  AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot && z_coff >= 0 && z_coff + cout <= z_ctot,
+               "conv3x3_fwd: channel view out of range");
+  if (fmt == AIDE_FMT_F32)
+    return simt_conv3x3(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin,
+                        reinterpret_cast<const float*>(w_p0), bias, z, z_ctot, z_coff, cout, N, H, W, stat_partial,
+                        as_stream(stream));
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16, "conv3x3_fwd: bad operand format %d", fmt);
+  AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout),
+               "conv3x3_fwd: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0 (got %d -> %d); use AIDE_FMT_F32",
+               cin, cout);
+  AIDE_REQUIRE(z_ctot % 4 == 0 && z_coff % 4 == 0, "conv3x3_fwd: output view must be 16-byte aligned");
+  return tc_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
+                    stat_partial, as_stream(stream));
+}
+
+extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W) {
+  if (fmt == AIDE_FMT_F32) return simt_wgrad_workspace_bytes(cin, cout, N, H, W);
+  if (!tc_shape_ok(fmt, cin, cout)) return 0;
+  return tc_wgrad_workspace_bytes(fmt, cin, cout, N, H, W);
+}
+
+extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                                  const void* dz_p0, const void* dz_p1, int cout, int N, int H, int W, void* workspace,
+                                  size_t workspace_bytes, float* dw_oihw, void* stream) {
+  AIDE_REQUIRE(x_p0 && dz_p0 && dw_oihw && workspace, "conv3x3_wgrad: null argument");
+  AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot, "conv3x3_wgrad: channel view out of range");
+  if (fmt == AIDE_FMT_F32)
+    return simt_wgrad(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin, reinterpret_cast<const float*>(dz_p0),
+                      cout, N, H, W, reinterpret_cast<float*>(workspace), workspace_bytes, dw_oihw, as_stream(stream));
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16, "conv3x3_wgrad: bad operand format %d", fmt);
+  AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout), "conv3x3_wgrad: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0");
+  return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes,
+                  dw_oihw, as_stream(stream));
+}

@@ -1,0 +1,161 @@
+// head.cu -- last_conv1: 1x1 convolution C -> K (+bias), forward and backward
+// (reference: models_twomodalinputs/fuseunet.py:41,89; models_singlemodalinput/UNet.py:150,164).
+// K is tiny (num_classes = 2), so this is an HBM-bound per-pixel dot product on CUDA cores:
+// reads the NHWC activation once (128-bit loads), writes NCHW fp32 logits.
+#include "common.cuh"
+
+namespace aide {
+
+constexpr int kMaxK = 8;
+
+// LP lanes cooperate on one pixel (LP = power of two <= 32); 32/LP pixels per warp per iteration.
+template <int FMT>
+__global__ void conv1x1_fwd_kernel(CView x, int C, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ out, int K, size_t npix, int HW, int LP) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LP, l = lane % LP, PW = 32 / LP;
+  const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int C4 = C >> 2;
+  for (size_t base = warp * PW; base < npix; base += nwarps * PW) {
+    size_t pix = base + sub;
+    bool valid = pix < npix;
+    float acc[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
+    if (valid) {
+      for (int c4 = l; c4 < C4; c4 += LP) {
+        float4 v = ld4<FMT>(x.p0, x.p1, pix * x.ctot + x.coff + c4 * 4);
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+          if (k < K) {
+            float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + c4 * 4));
+            acc[k] += v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      if (k < K) {
+        for (int o = LP >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+    }
+    if (valid && l == 0) {
+      size_t n = pix / HW, hw = pix % HW;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) out[(n * K + k) * HW + hw] = acc[k] + (bias ? bias[k] : 0.f);
+    }
+  }
+}
+
+// blockDim = (cx, ty), grid = (rows, cgroups); each thread owns 4 channels.
+template <int FMT>
+__global__ void conv1x1_bwd_kernel(CView x, int C, const float* __restrict__ w, const float* __restrict__ dl, int K,
+                                   size_t npix, int HW, float* __restrict__ dx, float* __restrict__ partial) {
+  extern __shared__ float smem[];  // [ty][cx][K*4 + K]
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const bool cvalid = c < C;
+  const int stride = K * 4 + K;
+  float aw[kMaxK][4], ab[kMaxK];
+  float4 wv[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    aw[k][0] = aw[k][1] = aw[k][2] = aw[k][3] = 0.f;
+    ab[k] = 0.f;
+    wv[k] = (cvalid && k < K) ? *reinterpret_cast<const float4*>(w + (size_t)k * C + c) : make_float4(0, 0, 0, 0);
+  }
+  if (cvalid) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += (size_t)gridDim.x * blockDim.y) {
+      size_t n = p / HW, hw = p % HW;
+      float4 xv = ld4<FMT>(x.p0, x.p1, p * x.ctot + x.coff + c);
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) {
+        if (k < K) {
+          float g = __ldg(dl + (n * K + k) * HW + hw);
+          d.x += g * wv[k].x; d.y += g * wv[k].y; d.z += g * wv[k].z; d.w += g * wv[k].w;
+          aw[k][0] += g * xv.x; aw[k][1] += g * xv.y; aw[k][2] += g * xv.z; aw[k][3] += g * xv.w;
+          ab[k] += g;
+        }
+      }
+      *reinterpret_cast<float4*>(dx + p * C + c) = d;
+    }
+  }
+  float* row = smem + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * stride;
+  for (int k = 0; k < K; ++k) {
+    row[k * 4 + 0] = aw[k][0]; row[k * 4 + 1] = aw[k][1]; row[k * 4 + 2] = aw[k][2]; row[k * 4 + 3] = aw[k][3];
+    row[K * 4 + k] = ab[k];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && cvalid) {
+    float* out = partial + (size_t)blockIdx.x * ((size_t)K * C + K);
+    for (int j = 0; j < stride; ++j) {
+      float a = 0.f;
+      for (int t = 0; t < (int)blockDim.y; ++t) a += smem[((size_t)t * blockDim.x + threadIdx.x) * stride + j];
+      if (j < K * 4) out[(size_t)(j >> 2) * C + c + (j & 3)] = a;
+      else if (c == 0) out[(size_t)K * C + (j - K * 4)] = a;
+    }
+  }
+}
+
+struct HeadGeom { int cx, ty, cgroups, rows; };
+static HeadGeom head_geom(int N, int H, int W, int C) {
+  HeadGeom g;
+  int c4 = C / 4;
+  g.cx = c4 < 64 ? c4 : 64;
+  g.ty = 256 / g.cx;
+  g.cgroups = ceil_div(c4, g.cx);
+  long long npix = (long long)N * H * W;
+  long long want = (npix + g.ty * 8 - 1) / (g.ty * 8);
+  long long cap = (long long)kNumSMs * 4 / g.cgroups;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  g.rows = (int)want;
+  return g;
+}
+
+}  // namespace aide
+
+using namespace aide;
+
+extern "C" int aide_conv1x1_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int C,
+                                const float* w, const float* bias, float* logits_nchw, int K, int N, int H, int W,
+                                void* stream) {
+  AIDE_REQUIRE(x_p0 && w && logits_nchw && C % 4 == 0 && x_coff % 4 == 0 && K >= 1 && K <= kMaxK,
+               "conv1x1_fwd: bad arguments (C%%4==0, 1<=K<=%d)", kMaxK);
+  CView x{x_p0, x_p1, x_ctot, x_coff};
+  int LP = 1;
+  while (LP < C / 4 && LP < 32) LP <<= 1;
+  size_t npix = (size_t)N * H * W;
+  size_t warps = (npix + (32 / LP) - 1) / (32 / LP);
+  int blocks = (int)((warps + 7) / 8);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks < 1) blocks = 1;
+  AIDE_DISPATCH_FMT(fmt, (conv1x1_fwd_kernel<FMT><<<blocks, 256, 0, as_stream(stream)>>>(x, C, w, bias, logits_nchw, K,
+                                                                                        npix, H * W, LP)));
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_conv1x1_bwd_rows(int N, int H, int W, int C) { return head_geom(N, H, W, C).rows; }
+
+extern "C" int aide_conv1x1_bwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int C,
+                                const float* w, const float* dlogits_nchw, int K, int N, int H, int W, float* dx,
+                                float* dw_db, float* partial, void* stream) {
+  AIDE_REQUIRE(x_p0 && w && dlogits_nchw && dx && dw_db && partial && C % 4 == 0 && x_coff % 4 == 0 && K >= 1 &&
+                   K <= kMaxK,
+               "conv1x1_bwd: bad arguments");
+  CView x{x_p0, x_p1, x_ctot, x_coff};
+  HeadGeom g = head_geom(N, H, W, C);
+  dim3 block(g.cx, g.ty), grid(g.rows, g.cgroups);
+  size_t smem = (size_t)g.cx * g.ty * (K * 5) * sizeof(float);
+  size_t npix = (size_t)N * H * W;
+  AIDE_DISPATCH_FMT(fmt, (conv1x1_bwd_kernel<FMT><<<grid, block, smem, as_stream(stream)>>>(
+                             x, C, w, dlogits_nchw, K, npix, H * W, dx, partial)));
+  AIDE_CHECK_LAUNCH();
+  int ld = K * C + K;
+  return launch_reduce_rows(partial, g.rows, ld, ld, dw_db, as_stream(stream));
+}

@@ -1,0 +1,115 @@
+// layout.cu -- module-boundary layout changes and weight preparation.
+//   NCHW fp32 <-> NHWC operand-format views; OIHW fp32 -> [Cout][9][Cin] / [Cin][9][Cout] planes.
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace aide {
+
+// ------------------------------------------------------------------ error plumbing (one TU owns it)
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return 2;
+}
+
+// ------------------------------------------------------------------ NCHW -> NHWC
+// Tile transpose through shared memory: block handles 32 pixels x 32 channels of one image.
+template <int FMT>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* p0, void* p1, int ctot, int coff,
+                                    int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p_base = blockIdx.x * 32, c_base = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c_base + i, p = p_base + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p_base + i, c = c_base + threadIdx.x;
+    if (c < C && p < HW) st1<FMT>(p0, p1, ((size_t)n * HW + p) * ctot + coff + c, tile[threadIdx.x][i]);
+  }
+}
+
+template <int FMT>
+__global__ void nhwc_to_nchw_kernel(const void* p0, const void* p1, int ctot, int coff, float* __restrict__ dst,
+                                    int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p_base = blockIdx.x * 32, c_base = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p_base + i, c = c_base + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? ld1<FMT>(p0, p1, ((size_t)n * HW + p) * ctot + coff + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c_base + i, p = p_base + threadIdx.x;
+    if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ weight prep
+// one thread per (co, ci, tap) element; writes both layouts.
+template <int FMT>
+__global__ void weight_prep_kernel(const float* __restrict__ w, int cout, int cin, void* f0, void* f1, void* d0,
+                                   void* d1) {
+  size_t total = (size_t)cout * cin * 9;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    // iterate in the fwd layout order so the fwd store is coalesced: i = (co*9 + tap)*cin + ci
+    int ci = (int)(i % cin);
+    int tap = (int)((i / cin) % 9);
+    int co = (int)(i / ((size_t)cin * 9));
+    float v = w[((size_t)co * cin + ci) * 9 + tap];
+    if (f0) st1<FMT>(f0, f1, i, v);
+    if (d0) st1<FMT>(d0, d1, ((size_t)ci * 9 + (8 - tap)) * cout + co, v);
+  }
+}
+
+}  // namespace aide
+
+using namespace aide;
+
+extern "C" const char* aide_last_error(void) { return g_err; }
+extern "C" int aide_version(void) { return 100; }
+
+extern "C" int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                                 int N, int C, int H, int W, void* stream) {
+  AIDE_REQUIRE(src && dst_p0 && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+  AIDE_REQUIRE(fmt != AIDE_FMT_TF32X2 || dst_p1, "nchw_to_nhwc: TF32X2 needs two planes");
+  dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), N), block(32, 8);
+  AIDE_DISPATCH_FMT(fmt, (nchw_to_nhwc_kernel<FMT><<<grid, block, 0, as_stream(stream)>>>(
+                             src, dst_p0, dst_p1, dst_ctot, dst_coff, C, H * W)));
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_nhwc_to_nchw(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,
+                                 float* dst, int N, int C, int H, int W, void* stream) {
+  AIDE_REQUIRE(src_p0 && dst && N > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad arguments");
+  dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), N), block(32, 8);
+  AIDE_DISPATCH_FMT(fmt, (nhwc_to_nchw_kernel<FMT><<<grid, block, 0, as_stream(stream)>>>(
+                             src_p0, src_p1, src_ctot, src_coff, dst, C, H * W)));
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin, void* fwd_p0, void* fwd_p1,
+                                void* dgrad_p0, void* dgrad_p1, void* stream) {
+  AIDE_REQUIRE(w_oihw && cout > 0 && cin > 0 && (fwd_p0 || dgrad_p0), "weight_prep: bad arguments");
+  AIDE_REQUIRE(fmt != AIDE_FMT_TF32X2 || ((!fwd_p0 || fwd_p1) && (!dgrad_p0 || dgrad_p1)),
+               "weight_prep: TF32X2 needs two planes");
+  size_t total = (size_t)cout * cin * 9;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  AIDE_DISPATCH_FMT(fmt, (weight_prep_kernel<FMT><<<blocks, 256, 0, as_stream(stream)>>>(
+                             w_oihw, cout, cin, fwd_p0, fwd_p1, dgrad_p0, dgrad_p1)));
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}

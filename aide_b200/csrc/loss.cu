@@ -1,0 +1,303 @@
+// loss.cu -- fused per-image CE + Dice (+ weighted-MSE consistency) reductions, their closed-form
+// backward, pseudo-label generation and the small-loss (co-teaching) selection.
+//
+// Reference: utils/loss2d.py:5-13,35-61,87-154 (CrossEntropyLoss2d, DiceLoss, MulticlassDiceLoss,
+// MulticlassMSELoss, CEMDiceLoss, CEMDiceLossImage), utils/metrics2d.py:8-29 (Dice_fn),
+// train_files/trainchaos_proposed_30cases1labeled.py:274-292 (pseudo label), :303-321 (selection).
+//
+// With two classes everything is a function of d = z1 - z0 and s = softmax(z)[1]:
+//   ce  = softplus(z_other - z_t) * wc[t]              dce/dd   = wc[t] * (s - t)
+//   dice_n = 1 - (2 I + sm)/(S + T + sm)               ddice/ds = -(2 t D - (2 I + sm)) / D^2,  D = S+T+sm
+//   mse = wm * ((1-s-q0)^2 + (s-q1)^2)                 dmse/ds  = 2 wm ((s-q1) - (1-s-q0))
+//   ds/dd = s (1 - s);   dL/dz1 = +dL/dd,  dL/dz0 = -dL/dd.
+// The sums are accumulated in fp64 (one pass, fixed-order two-stage reduction) so per-image losses
+// match the fp32 reference to ~1e-7 and the small-loss ordering is reproducible.
+#include "common.cuh"
+
+namespace aide {
+
+constexpr int kLossThreads = 256;
+constexpr int kPixPerBlock = 4096;
+
+__device__ __forceinline__ void softmax2(float z0, float z1, float& s0, float& s1) {
+  float m = fmaxf(z0, z1);
+  float e0 = expf(z0 - m), e1 = expf(z1 - m);
+  float inv = 1.0f / (e0 + e1);
+  s0 = e0 * inv;
+  s1 = e1 * inv;
+}
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+__global__ void loss_sums_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
+                                 const float* __restrict__ q, const float* __restrict__ wm, int HW, float wc0,
+                                 float wc1, int ignore_index, float thr, double* __restrict__ scratch) {
+  const int n = blockIdx.y;
+  const float* z0p = logits + (size_t)n * 2 * HW;
+  const float* z1p = z0p + HW;
+  const int64_t* tp = targets + (size_t)n * HW;
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int p_end = min(HW, (int)(blockIdx.x + 1) * kPixPerBlock);
+  for (int p = blockIdx.x * kPixPerBlock + threadIdx.x; p < p_end; p += kLossThreads) {
+    float z0 = z0p[p], z1 = z1p[p];
+    long long t = tp[p];
+    float s0, s1;
+    softmax2(z0, z1, s0, s1);
+    float tf = (float)t;
+    if (t != ignore_index) {
+      float w = t == 1 ? wc1 : wc0;
+      float ce = softplusf(t == 1 ? z0 - z1 : z1 - z0);
+      a[0] += (double)(ce * w);
+      a[1] += (double)w;
+    }
+    a[2] += (double)(s1 * tf);
+    a[3] += (double)s1;
+    a[4] += (double)tf;
+    if (s1 >= thr) {
+      a[5] += (double)tf;
+      a[6] += 1.0;
+    }
+    if (q) {
+      float q0 = q[(size_t)n * 2 * HW + p], q1 = q[(size_t)n * 2 * HW + HW + p];
+      float w = wm ? wm[(size_t)n * HW + p] : 1.f;
+      float e0 = s0 - q0, e1 = s1 - q1;
+      a[7] += (double)(w * (e0 * e0)) + (double)(w * (e1 * e1));
+    }
+  }
+  __shared__ double sm[kLossThreads / 32][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double v = warp_sum(a[k]);
+    if (lane == 0) sm[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int w = 0; w < kLossThreads / 32; ++w) t += sm[w][threadIdx.x];
+    scratch[((size_t)n * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = t;
+  }
+}
+
+__global__ void loss_sums_finalize_kernel(const double* __restrict__ scratch, int blocks, double* __restrict__ sums) {
+  int n = blockIdx.x, k = threadIdx.x;
+  if (k >= 8) return;
+  double t = 0.0;
+  for (int b = 0; b < blocks; ++b) t += scratch[((size_t)n * blocks + b) * 8 + k];
+  sums[(size_t)n * 8 + k] = t;
+}
+
+__global__ void loss_image_finalize_kernel(const double* __restrict__ sums, int N, double hw, float w_ce, float w_dice,
+                                           float smooth, float* __restrict__ loss_img, float* __restrict__ dice_img,
+                                           float* __restrict__ dice_fn_out) {
+  // single block; N <= 1024
+  __shared__ float dsum[1024];
+  int n = threadIdx.x;
+  float dfn = 0.f;
+  if (n < N) {
+    const double* s = sums + (size_t)n * 8;
+    float ce = (float)(s[0] / hw);
+    float I = (float)s[2], S = (float)s[3], T = (float)s[4];
+    float dice = 1.0f - (2.0f * I + smooth) / (S + T + smooth);
+    if (loss_img) loss_img[n] = ce * w_ce + dice * w_dice;
+    if (dice_img) dice_img[n] = dice;
+    // Dice_fn (metrics2d.py:14-28): thresholded prediction, empty-target rule
+    float pi = (float)s[5], ps = (float)s[6];
+    if (T == 0.f) dfn = (ps == 0.f) ? 1.f : 0.f;
+    else dfn = (2.f * pi) / (ps + T);
+  }
+  dsum[threadIdx.x] = dfn;
+  __syncthreads();
+  if (threadIdx.x == 0 && dice_fn_out) {
+    float t = 0.f;
+    for (int i = 0; i < N; ++i) t += dsum[i];
+    *dice_fn_out = t;
+  }
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
+                                const float* __restrict__ q, const float* __restrict__ wm,
+                                const double* __restrict__ sums, const float* __restrict__ a_ce,
+                                const float* __restrict__ a_dice, const float* __restrict__ a_mse, int HW, float wc0,
+                                float wc1, int ignore_index, float smooth, float* __restrict__ dlogits) {
+  const int n = blockIdx.y;
+  const float ace = a_ce ? a_ce[n] : 0.f, adi = a_dice ? a_dice[n] : 0.f, ams = (a_mse && q) ? a_mse[n] : 0.f;
+  const double* s = sums + (size_t)n * 8;
+  const float I = (float)s[2], D = (float)s[3] + (float)s[4] + smooth;
+  const float invD2 = 1.0f / (D * D), num = 2.0f * I + smooth;
+  const size_t base = (size_t)n * 2 * HW;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    float z0 = logits[base + p], z1 = logits[base + HW + p];
+    long long t = targets[(size_t)n * HW + p];
+    float s0, s1;
+    softmax2(z0, z1, s0, s1);
+    float tf = (float)t;
+    float gd = 0.f;  // dL/dd
+    if (ace != 0.f && t != ignore_index) gd += ace * (t == 1 ? wc1 : wc0) * (s1 - tf);
+    float gs = 0.f;  // dL/ds1 (through the softmax)
+    if (adi != 0.f) gs += adi * (-(2.0f * tf * D - num) * invD2);
+    if (ams != 0.f) {
+      float q0 = q[base + p], q1 = q[base + HW + p];
+      float w = wm ? wm[(size_t)n * HW + p] : 1.f;
+      gs += ams * 2.0f * w * ((s1 - q1) - (s0 - q0));
+    }
+    gd += gs * (s1 * s0);
+    dlogits[base + p] = -gd;
+    dlogits[base + HW + p] = gd;
+  }
+}
+
+struct AugPtrs {
+  const float* p[8];
+};
+__global__ void pseudo_label_kernel(AugPtrs aug, int n_aug, int HW, size_t total, float expo, float* __restrict__ q,
+                                    float* __restrict__ wm) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t n = i / HW, p = i % HW;
+    size_t base = n * 2 * HW + p;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < n_aug; ++k) {
+      float s0, s1;
+      softmax2(aug.p[k][base], aug.p[k][base + HW], s0, s1);
+      a0 += s0;
+      a1 += s1;
+    }
+    float inv = 1.0f / (float)n_aug;
+    a0 = a0 / (float)n_aug;
+    a1 = a1 / (float)n_aug;
+    (void)inv;
+    float m0 = expo == 1.0f ? a0 : powf(a0, expo), m1 = expo == 1.0f ? a1 : powf(a1, expo);
+    float sum = m0 + m1;
+    float q0 = m0 / sum, q1 = m1 / sum;
+    q[base] = q0;
+    q[base + HW] = q1;
+    wm[n * HW + p] = 1.0f - 4.0f * q0 * q1;
+  }
+}
+
+// single block, N <= 1024 threads
+__global__ void coteach_select_kernel(const float* __restrict__ pre_other, const float* __restrict__ loss_img,
+                                      const double* __restrict__ sums, int N, double hw, int n_clean, float rate,
+                                      float seg_w, float cor_w, float w_ce, float w_dice, int64_t* __restrict__ idx,
+                                      float* __restrict__ a_ce, float* __restrict__ a_dice, float* __restrict__ a_mse,
+                                      float* __restrict__ loss_out) {
+  __shared__ float v[1024];
+  __shared__ int order[1024];
+  const int i = threadIdx.x;
+  if (i < N) v[i] = pre_other[i];
+  __syncthreads();
+  int rank = 0;
+  if (i < N) {
+    float mine = v[i];
+    for (int j = 0; j < N; ++j) {
+      float o = v[j];
+      rank += (o < mine) || (o == mine && j < i);  // stable ascending
+    }
+    order[rank] = i;
+  }
+  __syncthreads();
+  const int n_rest = N - n_clean;
+  if (i < N) {
+    idx[i] = order[i];
+    bool clean = rank < n_clean;
+    // loss = seg_w * (mean_clean L + (1-rate) mean_rest L) + cor_w * rate * sum_rest(mse) / (n_rest*2*HW)
+    float cseg = clean ? seg_w / (float)n_clean : (n_rest > 0 ? seg_w * (1.0f - rate) / (float)n_rest : 0.f);
+    a_ce[i] = cseg * w_ce / (float)hw;
+    a_dice[i] = cseg * w_dice;
+    a_mse[i] = (!clean && n_rest > 0) ? cor_w * rate / (float)((double)n_rest * 2.0 * hw) : 0.f;
+  }
+  __syncthreads();
+  if (i == 0 && loss_out) {
+    // fixed-order scalar assembly following the reference expression order
+    float seg1 = 0.f, seg2 = 0.f;
+    double mse = 0.0;
+    for (int r = 0; r < N; ++r) {
+      int k = order[r];
+      if (r < n_clean) seg1 += loss_img[k];
+      else {
+        seg2 += loss_img[k];
+        mse += sums[(size_t)k * 8 + 7];
+      }
+    }
+    seg1 = seg1 / (float)n_clean;
+    float cor = 0.f;
+    if (n_rest > 0) {
+      seg2 = seg2 / (float)n_rest;
+      cor = (float)(mse / ((double)n_rest * 2.0 * hw));
+    }
+    *loss_out = seg_w * (seg1 + (1.0f - rate) * seg2) + cor_w * rate * cor;
+  }
+}
+
+}  // namespace aide
+
+using namespace aide;
+
+extern "C" int aide_loss_blocks(int H, int W) { return ceil_div((long long)H * W, kPixPerBlock); }
+
+extern "C" int aide_loss_sums(const float* logits, const int64_t* targets, const float* q, const float* wm, int N,
+                              int H, int W, float wc0, float wc1, int ignore_index, float threshold, double* sums,
+                              double* scratch, void* stream) {
+  AIDE_REQUIRE(logits && targets && sums && scratch && N > 0 && H > 0 && W > 0, "loss_sums: bad arguments");
+  int blocks = aide_loss_blocks(H, W);
+  loss_sums_kernel<<<dim3(blocks, N), kLossThreads, 0, as_stream(stream)>>>(logits, targets, q, wm, H * W, wc0, wc1,
+                                                                            ignore_index, threshold, scratch);
+  AIDE_CHECK_LAUNCH();
+  loss_sums_finalize_kernel<<<N, 32, 0, as_stream(stream)>>>(scratch, blocks, sums);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_loss_image_finalize(const double* sums, int N, int H, int W, float w_ce, float w_dice,
+                                        float smooth, float* loss_img, float* dice_img, float* dice_fn_out,
+                                        void* stream) {
+  AIDE_REQUIRE(sums && N > 0 && N <= 1024, "loss_image_finalize: bad arguments (N <= 1024)");
+  int threads = ((N + 31) / 32) * 32;
+  loss_image_finalize_kernel<<<1, threads, 0, as_stream(stream)>>>(sums, N, (double)H * W, w_ce, w_dice, smooth,
+                                                                   loss_img, dice_img, dice_fn_out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_loss_bwd(const float* logits, const int64_t* targets, const float* q, const float* wm,
+                             const double* sums, const float* a_ce, const float* a_dice, const float* a_mse, int N,
+                             int H, int W, float wc0, float wc1, int ignore_index, float smooth, float* dlogits,
+                             void* stream) {
+  AIDE_REQUIRE(logits && targets && sums && dlogits && N > 0, "loss_bwd: bad arguments");
+  int HW = H * W;
+  int bx = ceil_div(HW, 256 * 4);
+  if (bx < 1) bx = 1;
+  loss_bwd_kernel<<<dim3(bx, N), 256, 0, as_stream(stream)>>>(logits, targets, q, wm, sums, a_ce, a_dice, a_mse, HW,
+                                                              wc0, wc1, ignore_index, smooth, dlogits);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo, float* q,
+                                 float* wm, void* stream) {
+  AIDE_REQUIRE(aug_logits && n_aug >= 1 && n_aug <= 8 && q && wm, "pseudo_label: 1..8 augmented logit tensors");
+  AugPtrs a{};
+  for (int i = 0; i < n_aug; ++i) {
+    AIDE_REQUIRE(aug_logits[i], "pseudo_label: null logits pointer");
+    a.p[i] = aug_logits[i];
+  }
+  size_t total = (size_t)N * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pseudo_label_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, n_aug, H * W, total, expo, q, wm);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_coteach_select(const float* pre_other, const float* loss_img, const double* sums, int N, int H,
+                                   int W, int n_clean, float rate, float seg_w, float cor_w, float w_ce, float w_dice,
+                                   int64_t* idx, float* a_ce, float* a_dice, float* a_mse, float* loss_out,
+                                   void* stream) {
+  AIDE_REQUIRE(pre_other && loss_img && sums && idx && a_ce && a_dice && a_mse, "coteach_select: null argument");
+  AIDE_REQUIRE(N >= 1 && N <= 1024 && n_clean >= 1 && n_clean <= N, "coteach_select: need 1 <= n_clean <= N <= 1024");
+  int threads = ((N + 31) / 32) * 32;
+  coteach_select_kernel<<<1, threads, 0, as_stream(stream)>>>(pre_other, loss_img, sums, N, (double)H * W, n_clean,
+                                                              rate, seg_w, cor_w, w_ce, w_dice, idx, a_ce, a_dice,
+                                                              a_mse, loss_out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}

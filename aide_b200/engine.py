@@ -1,0 +1,488 @@
+"""Host-side executor for the AIDE networks on libaide_b200 (sm_100a).
+
+A network (fuseunet / UNet, reference: models_twomodalinputs/fuseunet.py:43-91,
+models_singlemodalinput/UNet.py:152-165) is described once as a *plan*: a list of conv3x3+BN+ReLU
+units, bilinear upsamples and the 1x1 head operating on named NHWC buffers.  Channel concatenation
+(torch.cat in the reference) never copies: producers write into channel slices ("views") of the
+consumer's input buffer, 2x2 max-pool outputs are emitted by the producer's BN-apply kernel.
+
+Forward and backward are each a straight sequence of C-ABI calls on the current CUDA stream; there
+is no CPU compute and no fallback.  The backward plan is derived from the forward plan: the
+gradient of a unit's output is the sum of the consumers' dgrad slices (same resolution), max-pool
+routed slices (half resolution) and upsample-transposed gradients.
+
+PyTorch is used for device memory (one arena tensor per forward / backward), streams and autograd
+registration only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FMT_BF16, FMT_F32, FMT_TF32X2, call, lib
+
+MODES = {"exact": FMT_F32, "parity": FMT_TF32X2, "fast": FMT_BF16}
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def default_mode() -> str:
+    """Engine precision mode: 'parity' (3xTF32 tcgen05, fp32-equivalent; default), 'fast' (single-pass
+    BF16 tcgen05) or 'exact' (fp32 CUDA cores).  Opt-in via AIDE_B200_MODE."""
+    m = os.environ.get("AIDE_B200_MODE", "parity")
+    if m not in MODES:
+        raise ValueError(f"AIDE_B200_MODE must be one of {sorted(MODES)}, got {m!r}")
+    return m
+
+
+def _planes(fmt: int) -> int:
+    return 2 if fmt == FMT_TF32X2 else 1
+
+
+def _esize(fmt: int) -> int:
+    return 2 if fmt == FMT_BF16 else 4
+
+
+def _align(n: int, a: int = 1024) -> int:
+    return (n + a - 1) // a * a
+
+
+# ------------------------------------------------------------------------------------------------
+# plan description
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Unit:
+    """conv3x3(+bias) -> BatchNorm2d -> ReLU (netblocks.py:30-33 / :17-19)."""
+    name: str            # e.g. "modal1_downblock1.block.1" (for messages)
+    conv: str            # parameter prefix of the conv  (…conv1 / …bilinear_up.1)
+    bn: str              # parameter prefix of the BN    (…bn1   / …bilinear_up.2)
+    cin: int
+    cout: int
+    level: int           # resolution level: h = H >> level
+    src: Tuple[str, int]             # (buffer, channel offset) of the input view
+    dst: Optional[Tuple[str, int]]   # full-resolution destination view of y
+    pools: List[Tuple[str, int]] = field(default_factory=list)  # half-resolution destinations of maxpool(y)
+    first: bool = False              # input is a network input (fp32 NHWC, 3 channels): CUDA-core path
+
+
+@dataclass
+class Upsample:
+    src: str
+    dst: str
+    c: int
+    level: int           # level of the SOURCE (low resolution)
+
+
+@dataclass
+class Plan:
+    kind: str
+    n_inputs: int
+    num_classes: int
+    bufs: Dict[str, Tuple[int, int]]   # activation buffers: name -> (level, channels)
+    ops: list                          # forward order: ("input", i, buf) | Unit | Upsample | ("head", buf, cin)
+    units: List[Unit]
+
+
+def _block(ops, units, prefix, cin, cout, level, src, dst, pools, mid_buf, bufs, first=False):
+    """basic_block = two units; the first writes `mid_buf`, the second writes dst/pools."""
+    bufs[mid_buf] = (level, cout)
+    u1 = Unit(prefix + ".1", prefix + ".conv1", prefix + ".bn1", cin, cout, level, src, (mid_buf, 0), [], first)
+    u2 = Unit(prefix + ".2", prefix + ".conv2", prefix + ".bn2", cout, cout, level, (mid_buf, 0), dst, pools)
+    ops += [u1, u2]
+    units += [u1, u2]
+
+
+def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes: int):
+    """Four UNet_basic_up_block (netblocks.py:137-147) + last_conv1.  Skip tensors already live in the
+    upper half of the cat buffers (cat((upsampled, skip)) -> channels [C, 2C))."""
+    x, cx = bottom, skips_c[0] * 2
+    for i, c in enumerate(skips_c, 1):            # c = 512, 256, 128, 64 ; level = 4 - i
+        lvl = 4 - i
+        up, cat, mid, out = f"up{i}", f"cat{i}", f"u{i}m", f"u{i}o"
+        bufs[up] = (lvl, cx)
+        bufs[out] = (lvl, c)
+        ops.append(Upsample(x, up, cx, lvl + 1))
+        u = Unit(f"up_block{i}.up", f"up_block{i}.bilinear_up.1", f"up_block{i}.bilinear_up.2", cx, c, lvl,
+                 (up, 0), (cat, 0), [])
+        ops.append(u)
+        units.append(u)
+        _block(ops, units, f"up_block{i}.block", 2 * c, c, lvl, (cat, 0), (out, 0), [], mid, bufs)
+        x, cx = out, c
+    ops.append(("head", x, cx))
+
+
+def plan_fuseunet(num_classes: int = 2) -> Plan:
+    """fuseunet.forward (fuseunet.py:43-91): modal-1 encoder consumes the fused concat, modal-2 is independent."""
+    bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3), "in1": (0, 3)}
+    ops: list = [("input", 0, "in0"), ("input", 1, "in1")]
+    units: List[Unit] = []
+    width = [32, 64, 128, 256, 512]
+    # fused tensors y1..y4 are the upper halves of cat4..cat1; y5 is its own buffer; p{l} = maxpool(y_l)
+    for lvl, c in enumerate(width):
+        fused = ("y5", 0) if lvl == 4 else (f"cat{4 - lvl}", 2 * c)     # cat width is 4c: [up 2c | skip 2c]
+        if lvl == 4:
+            bufs["y5"] = (4, 2 * c)
+        else:
+            bufs[f"cat{4 - lvl}"] = (lvl, 4 * c)
+            bufs[f"p{lvl + 1}"] = (lvl + 1, 2 * c)
+        pool_a = [] if lvl == 4 else [(f"p{lvl + 1}", 0)]
+        pool_b = [] if lvl == 4 else [(f"p{lvl + 1}", c)]
+        src_a = ("in0", 0) if lvl == 0 else (f"p{lvl}", 0)
+        cin_a = 3 if lvl == 0 else 2 * width[lvl - 1]
+        src_b = ("in1", 0) if lvl == 0 else (f"p{lvl}", width[lvl - 1])   # modal-2 = second half of the pooled concat
+        cin_b = 3 if lvl == 0 else width[lvl - 1]
+        _block(ops, units, f"modal1_downblock{lvl + 1}.block", cin_a, c, lvl, src_a, (fused[0], fused[1]), pool_a,
+               f"a{lvl + 1}m", bufs, first=lvl == 0)
+        _block(ops, units, f"modal2_downblock{lvl + 1}.block", cin_b, c, lvl, src_b, (fused[0], fused[1] + c), pool_b,
+               f"b{lvl + 1}m", bufs, first=lvl == 0)
+    _decoder(ops, units, bufs, "y5", [512, 256, 128, 64], num_classes)
+    return Plan("fuseunet", 2, num_classes, bufs, ops, units)
+
+
+def plan_unet(num_classes: int = 2) -> Plan:
+    """UNet.forward (UNet.py:152-165); max-pool inside down blocks 2..5 (UNet.py:117-121)."""
+    bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3)}
+    ops: list = [("input", 0, "in0")]
+    units: List[Unit] = []
+    width = [64, 128, 256, 512, 1024]
+    for lvl, c in enumerate(width):
+        if lvl == 4:
+            bufs["x5"] = (4, c)
+            dst = ("x5", 0)
+        else:
+            bufs[f"cat{4 - lvl}"] = (lvl, 2 * c)
+            bufs[f"p{lvl + 1}"] = (lvl + 1, c)
+            dst = (f"cat{4 - lvl}", c)
+        pools = [] if lvl == 4 else [(f"p{lvl + 1}", 0)]
+        src = ("in0", 0) if lvl == 0 else (f"p{lvl}", 0)
+        cin = 3 if lvl == 0 else width[lvl - 1]
+        _block(ops, units, f"down_block{lvl + 1}.block", cin, c, lvl, src, dst, pools, f"d{lvl + 1}m", bufs,
+               first=lvl == 0)
+    _decoder(ops, units, bufs, "x5", [512, 256, 128, 64], num_classes)
+    return Plan("unet", 1, num_classes, bufs, ops, units)
+
+
+# ------------------------------------------------------------------------------------------------
+# memory layout of one forward pass ("tape")
+# ------------------------------------------------------------------------------------------------
+class Layout:
+    """Byte offsets of every buffer of a plan for a given (N, H, W, fmt) inside one arena."""
+
+    def __init__(self, plan: Plan, N: int, H: int, W: int, fmt: int):
+        if H % 16 or W % 16:
+            raise ValueError(f"input height/width must be multiples of 16 (got {H}x{W}); the nets pool 4 times")
+        self.plan, self.N, self.H, self.W, self.fmt = plan, N, H, W, fmt
+        self.off: Dict[str, int] = {}
+        self.plane_stride: Dict[str, int] = {}
+        cur = 0
+        for name, (lvl, c) in plan.bufs.items():
+            h, w = H >> lvl, W >> lvl
+            f = FMT_F32 if name.startswith("in") else fmt
+            nbytes = _align(N * h * w * c * _esize(f))
+            self.off[name] = cur
+            self.plane_stride[name] = nbytes
+            cur += nbytes * _planes(f)
+        self.stat_rows: Dict[str, int] = {}
+        for u in plan.units:
+            h, w = H >> u.level, W >> u.level
+            ufmt = FMT_F32 if u.first else fmt
+            rows = lib.aide_conv3x3_stat_rows(ufmt, N, h, w)
+            self.stat_rows[u.name] = rows
+            self.off["z:" + u.name] = cur
+            cur += _align(N * h * w * u.cout * 4)
+            self.off["st:" + u.name] = cur
+            cur += _align(rows * 2 * u.cout * 4)
+            self.off["ss:" + u.name] = cur            # scale_shift [2][C] then mean_rstd [2][C]
+            cur += _align(4 * u.cout * 4)
+        self.total = cur
+
+    def buf_fmt(self, name: str) -> int:
+        return FMT_F32 if name.startswith("in") else self.fmt
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------
+# weights in operand format (re-derived when a parameter's version changes)
+# ------------------------------------------------------------------------------------------------
+class PreparedWeights:
+    """Operand-format copies of every conv3x3 weight: forward [Cout][9][Cin] and dgrad [Cin][9][Cout]
+    planes (aide_weight_prep).  One instance per parameter *version*; tapes hold a reference so a later
+    optimiser step cannot invalidate the weights a pending backward needs."""
+
+    def __init__(self, plan: Plan, params: Dict[str, torch.Tensor], fmt: int, need_dgrad: bool):
+        self.key = tuple((params[u.conv + ".weight"].data_ptr(), params[u.conv + ".weight"]._version)
+                         for u in plan.units)
+        self.has_dgrad = need_dgrad
+        dev = params[plan.units[0].conv + ".weight"].device
+        total = 0
+        self.off: Dict[str, Tuple[int, int, int]] = {}   # name -> (fwd offset, dgrad offset, plane stride)
+        for u in plan.units:
+            f = FMT_F32 if u.first else fmt
+            pb = _align(u.cout * 9 * u.cin * _esize(f), 256)
+            fwd = total
+            total += pb * _planes(f)
+            dg = -1
+            if need_dgrad and not u.first:
+                dg = total
+                total += pb * _planes(f)
+            self.off[u.name] = (fwd, dg, pb)
+        self.arena = torch.empty(total, dtype=torch.uint8, device=dev)
+        base = self.arena.data_ptr()
+        st = _stream()
+        for u in plan.units:
+            f = FMT_F32 if u.first else fmt
+            fwd, dg, pb = self.off[u.name]
+            two = _planes(f) == 2
+            w = params[u.conv + ".weight"]
+            call("aide_weight_prep", f, w.data_ptr(), u.cout, u.cin, base + fwd, base + fwd + pb if two else None,
+                 base + dg if dg >= 0 else None, base + dg + pb if (dg >= 0 and two) else None, st)
+
+    def fwd(self, u: Unit, fmt: int):
+        fwd, _, pb = self.off[u.name]
+        b = self.arena.data_ptr() + fwd
+        return b, (b + pb if _planes(FMT_F32 if u.first else fmt) == 2 else None)
+
+    def dgrad(self, u: Unit, fmt: int):
+        _, dg, pb = self.off[u.name]
+        b = self.arena.data_ptr() + dg
+        return b, (b + pb if _planes(fmt) == 2 else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# forward
+# ------------------------------------------------------------------------------------------------
+class Tape:
+    __slots__ = ("layout", "arena", "weights", "training", "inputs_shape")
+
+
+def _view(layout: Layout, base: int, name: str, coff: int):
+    """(p0, p1, ctot, coff) of a channel view of activation buffer `name`."""
+    lvl, c = layout.plan.bufs[name]
+    p0 = base + layout.off[name]
+    p1 = p0 + layout.plane_stride[name] if _planes(layout.buf_fmt(name)) == 2 else None
+    return p0, p1, c, coff
+
+
+def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], weights: PreparedWeights,
+                inputs: Sequence[torch.Tensor], training: bool, logits: torch.Tensor,
+                arena: torch.Tensor) -> None:
+    N, H, W, fmt = layout.N, layout.H, layout.W, layout.fmt
+    base = arena.data_ptr()
+    st = _stream()
+    for op in plan.ops:
+        if isinstance(op, tuple) and op[0] == "input":
+            _, i, name = op
+            p0, p1, ctot, _ = _view(layout, base, name, 0)
+            call("aide_nchw_to_nhwc", FMT_F32, inputs[i].data_ptr(), p0, None, ctot, 0, N, 3, H, W, st)
+        elif isinstance(op, Unit):
+            u = op
+            h, w = H >> u.level, W >> u.level
+            ufmt = FMT_F32 if u.first else fmt
+            x0, x1, xct, xco = _view(layout, base, u.src[0], u.src[1])
+            w0, w1 = weights.fwd(u, fmt)
+            z = base + layout.off["z:" + u.name]
+            stp = base + layout.off["st:" + u.name]
+            ss = base + layout.off["ss:" + u.name]
+            call("aide_conv3x3_fwd", ufmt, x0, x1, xct, xco, u.cin, w0, w1, params[u.conv + ".bias"].data_ptr(),
+                 z, u.cout, 0, u.cout, N, h, w, stp if training else None, st)
+            call("aide_bn_finalize", stp, layout.stat_rows[u.name], u.cout, float(N * h * w),
+                 params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
+                 params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
+                 BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + 2 * u.cout * 4, st)
+            d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
+            pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
+            pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
+            call("aide_bn_relu_apply", fmt, z, N, h, w, u.cout, ss, *d, *pa, *pb, st)
+        elif isinstance(op, Upsample):
+            h, w = H >> op.level, W >> op.level
+            s = _view(layout, base, op.src, 0)
+            d = _view(layout, base, op.dst, 0)
+            call("aide_upsample2x_fwd", fmt, *s, *d, N, h, w, op.c, st)
+        else:
+            _, name, cin = op
+            x0, x1, xct, xco = _view(layout, base, name, 0)
+            call("aide_conv1x1_fwd", fmt, x0, x1, xct, xco, cin, params["last_conv1.weight"].data_ptr(),
+                 params["last_conv1.bias"].data_ptr(), logits.data_ptr(), plan.num_classes, N, H, W, st)
+
+
+# ------------------------------------------------------------------------------------------------
+# backward
+# ------------------------------------------------------------------------------------------------
+class BackwardPlan:
+    """Gradient routing derived from the forward plan (who consumes which channel slice)."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        # consumers of each activation buffer: list of (kind, obj, coff, c)
+        cons: Dict[str, list] = {b: [] for b in plan.bufs}
+        for op in plan.ops:
+            if isinstance(op, Unit):
+                cons[op.src[0]].append(("unit", op, op.src[1], op.cin))
+            elif isinstance(op, Upsample):
+                cons[op.src].append(("ups", op, 0, op.c))
+            elif op[0] == "head":
+                cons[op[1]].append(("head", op, 0, op[2]))
+        self.sources: Dict[str, Tuple[list, list]] = {}
+        for u in plan.units:
+            direct, pooled = [], []
+            if u.dst:
+                direct = self._covering(cons[u.dst[0]], u.dst[1], u.cout, u)
+            for (pbuf, pco) in u.pools:
+                pooled += self._covering(cons[pbuf], pco, u.cout, u)
+            if not direct and not pooled:
+                raise RuntimeError(f"unit {u.name} has no consumer")
+            if len(direct) > 3 or len(pooled) > 3:
+                raise RuntimeError(f"unit {u.name}: too many gradient sources")
+            self.sources[u.name] = (direct, pooled)
+
+    @staticmethod
+    def _covering(consumers, coff, c, u):
+        out = []
+        for kind, obj, ccoff, cc in consumers:
+            if ccoff <= coff and coff + c <= ccoff + cc:
+                out.append((kind, obj, coff - ccoff, cc))       # (kind, consumer, offset inside its dX, its dX width)
+            elif not (coff + c <= ccoff or ccoff + cc <= coff):
+                raise RuntimeError(f"partial overlap between {u.name} output and a consumer view")
+        return out
+
+
+class GradLayout:
+    """Offsets (in floats) of every parameter gradient inside ONE flat fp32 buffer -- the unit of the
+    data-parallel all-reduce and of the fused Adam step.  BN beta/gamma gradients and the
+    head's weight/bias gradients are adjacent because the kernels emit them as one vector."""
+
+    def __init__(self, plan: Plan):
+        self.off: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        cur = 0
+
+        def add(name, shape):
+            nonlocal cur
+            n = 1
+            for d in shape:
+                n *= d
+            self.off[name] = (cur, tuple(shape))
+            cur += (n + 3) // 4 * 4
+
+        for u in plan.units:
+            add(u.conv + ".weight", (u.cout, u.cin, 3, 3))
+            add(u.conv + ".bias", (u.cout,))
+            add(u.bn + ".bias", (u.cout,))       # dbeta  } adjacent: written as one [2][C] vector
+            add(u.bn + ".weight", (u.cout,))     # dgamma }
+        head = next(op for op in plan.ops if isinstance(op, tuple) and op[0] == "head")
+        add("last_conv1.weight", (plan.num_classes, head[2], 1, 1))
+        self.off["last_conv1.bias"] = (self.off["last_conv1.weight"][0] + plan.num_classes * head[2],
+                                       (plan.num_classes,))
+        cur = self.off["last_conv1.bias"][0] + (plan.num_classes + 3) // 4 * 4
+        self.total = cur
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        o, shape = self.off[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return flat[o:o + n].view(shape)
+
+
+def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: Layout,
+                 params: Dict[str, torch.Tensor], weights: PreparedWeights, arena: torch.Tensor,
+                 dlogits: torch.Tensor, grad_flat: torch.Tensor) -> None:
+    """Writes every parameter gradient into `grad_flat` (fp32, laid out by `glayout`)."""
+    N, H, W, fmt = layout.N, layout.H, layout.W, layout.fmt
+    base = arena.data_ptr()
+    st = _stream()
+    gbase = grad_flat.data_ptr()
+
+    def gptr(name):
+        return gbase + glayout.off[name][0] * 4
+
+    # ---- backward arena: dX per unit / upsample / head, shared scratch for g, dz, partials, wgrad workspace
+    off: Dict[str, int] = {}
+    cur = 0
+
+    def reserve(key, nbytes):
+        nonlocal cur
+        off[key] = cur
+        cur += _align(nbytes)
+
+    max_g = max_dz = max_part = max_ws = 0
+    for u in plan.units:
+        h, w = H >> u.level, W >> u.level
+        ufmt = FMT_F32 if u.first else fmt
+        if not u.first:
+            reserve("dx:" + u.name, N * h * w * u.cin * 4)
+        max_g = max(max_g, N * h * w * u.cout * 4)
+        max_dz = max(max_dz, _align(N * h * w * u.cout * _esize(ufmt)) * _planes(ufmt))
+        max_part = max(max_part, lib.aide_bn_bwd_rows(N, h, w, u.cout) * 2 * u.cout * 4)
+        max_ws = max(max_ws, lib.aide_conv3x3_wgrad_workspace_bytes(ufmt, u.cin, u.cout, N, h, w))
+    for op in plan.ops:
+        if isinstance(op, Upsample):
+            reserve("dlo:" + op.dst, N * (H >> op.level) * (W >> op.level) * op.c * 4)
+        elif isinstance(op, tuple) and op[0] == "head":
+            reserve("dx:head", N * H * W * op[2] * 4)
+            hrows = lib.aide_conv1x1_bwd_rows(N, H, W, op[2])
+            reserve("headpart", hrows * (plan.num_classes * op[2] + plan.num_classes) * 4)
+    reserve("g", max_g)
+    reserve("dz", max_dz)
+    reserve("part", max_part)
+    reserve("part2", max_part)
+    reserve("ws", max_ws)
+    barena = torch.empty(cur, dtype=torch.uint8, device=arena.device)
+    bb = barena.data_ptr()
+
+    def src_ptr(kind, obj):
+        if kind == "unit":
+            return bb + off["dx:" + obj.name]
+        if kind == "ups":
+            return bb + off["dlo:" + obj.dst]
+        return bb + off["dx:head"]
+
+    for op in reversed(plan.ops):
+        if isinstance(op, tuple) and op[0] == "head":
+            _, name, cin = op
+            x0, x1, xct, xco = _view(layout, base, name, 0)
+            call("aide_conv1x1_bwd", fmt, x0, x1, xct, xco, cin, params["last_conv1.weight"].data_ptr(),
+                 dlogits.data_ptr(), plan.num_classes, N, H, W, bb + off["dx:head"], gptr("last_conv1.weight"),
+                 bb + off["headpart"], st)
+        elif isinstance(op, Upsample):
+            # the (single) consumer of op.dst is the up-conv unit; its dX is the high-resolution gradient
+            consumer = next(u for u in plan.units if u.src[0] == op.dst)
+            h, w = H >> op.level, W >> op.level
+            call("aide_upsample2x_bwd", bb + off["dx:" + consumer.name], consumer.cin, 0, bb + off["dlo:" + op.dst],
+                 N, h, w, op.c, st)
+        elif isinstance(op, Unit):
+            u = op
+            h, w = H >> u.level, W >> u.level
+            ufmt = FMT_F32 if u.first else fmt      # first-layer units: CUDA-core wgrad, no dgrad -> fp32 dz
+            direct, pooled = bplan.sources[u.name]
+            dptr = (C.c_void_p * 3)(*[src_ptr(k, o) for k, o, _, _ in direct])
+            dct = (C.c_int * 3)(*[cc for _, _, _, cc in direct])
+            dco = (C.c_int * 3)(*[co for _, _, co, _ in direct])
+            pptr = (C.c_void_p * 3)(*[src_ptr(k, o) for k, o, _, _ in pooled])
+            pct = (C.c_int * 3)(*[cc for _, _, _, cc in pooled])
+            pco = (C.c_int * 3)(*[co for _, _, co, _ in pooled])
+            z = base + layout.off["z:" + u.name]
+            ss = base + layout.off["ss:" + u.name]
+            mr = ss + 2 * u.cout * 4
+            g, part, part2 = bb + off["g"], bb + off["part"], bb + off["part2"]
+            call("aide_bn_relu_bwd_reduce", z, ss, mr, N, h, w, u.cout, dptr, dct, dco, len(direct),
+                 pptr, pct, pco, len(pooled), g, part, st)
+            rows = lib.aide_bn_bwd_rows(N, h, w, u.cout)
+            dz0 = bb + off["dz"]
+            dz1 = dz0 + _align(N * h * w * u.cout * _esize(ufmt)) if _planes(ufmt) == 2 else None
+            call("aide_bn_relu_bwd_apply", ufmt, g, z, mr, params[u.bn + ".weight"].data_ptr(), part, rows,
+                 N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"), gptr(u.conv + ".bias"),
+                 part2, st)
+            x0, x1, xct, xco = _view(layout, base, u.src[0], u.src[1])
+            call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, u.cout, N, h, w,
+                 bb + off["ws"], max_ws, gptr(u.conv + ".weight"), st)
+            if not u.first:
+                w0, w1 = weights.dgrad(u, fmt)
+                call("aide_conv3x3_fwd", fmt, dz0, dz1, u.cout, 0, u.cout, w0, w1, None,
+                     bb + off["dx:" + u.name], u.cin, 0, u.cin, N, h, w, None, st)

@@ -1,0 +1,225 @@
+"""Drop-in nn.Module surface of the reference networks, executed by the B200 engine.
+
+``fuseunet`` mirrors models_twomodalinputs/fuseunet.py:6-91 and ``UNet`` mirrors
+models_singlemodalinput/UNet.py:135-165: same constructor signatures, same module tree (hence the
+same ``state_dict()`` keys/shapes/order and -- because nn.Conv2d / nn.BatchNorm2d are instantiated
+in the reference's order -- the same random initialisation under the same torch seed), same
+``forward`` signatures.  The sub-modules only *hold* parameters and buffers; ``forward`` hands
+their storage to the CUDA engine (aide_b200.engine) through one autograd.Function per network.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+
+# -------------------------------------------------------------------------------------------------
+# parameter containers (names follow netblocks.py:9-33,128-147 and UNet.py:4-28,110-133)
+# -------------------------------------------------------------------------------------------------
+class basic_block(nn.Module):
+    def __init__(self, input_channel: int, output_channel: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_channel, output_channel, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(output_channel)
+        self.conv2 = nn.Conv2d(output_channel, output_channel, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(output_channel)
+        self.relu = nn.ReLU()
+
+
+def UNet_up_conv_bn_relu(input_channel: int, output_channel: int, learned_bilinear: bool = False) -> nn.Sequential:
+    if learned_bilinear:
+        raise NotImplementedError(
+            "learned_bilinear=True (ConvTranspose2d decoder, netblocks.py:11-14) is not built yet; no reference "
+            "script enables it (SURVEY.md section 0, item 2)")
+    return nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
+                         nn.Conv2d(input_channel, output_channel, kernel_size=3, padding=1),
+                         nn.BatchNorm2d(output_channel),
+                         nn.ReLU())
+
+
+class UNet_basic_down_block(nn.Module):
+    def __init__(self, input_channel: int, output_channel: int, down_size: Optional[bool] = None):
+        super().__init__()
+        self.block = basic_block(input_channel, output_channel)
+        if down_size is not None:                     # single-modal flavour (UNet.py:110-121)
+            self.max_pool = nn.MaxPool2d(2, 2)
+            self.down_size = down_size
+
+
+class UNet_basic_up_block(nn.Module):
+    def __init__(self, input_channel: int, prev_channel: int, output_channel: int, learned_bilinear: bool = False):
+        super().__init__()
+        self.bilinear_up = UNet_up_conv_bn_relu(input_channel, prev_channel, learned_bilinear)
+        self.block = basic_block(prev_channel * 2, output_channel)
+
+
+# -------------------------------------------------------------------------------------------------
+# autograd bridge
+# -------------------------------------------------------------------------------------------------
+class _NetFunction(torch.autograd.Function):
+    """logits = net(inputs).  Saved state is the engine's activation arena (the 'tape')."""
+
+    @staticmethod
+    def forward(ctx, net, n_in, *tensors):
+        inputs, params = tensors[:n_in], tensors[n_in:]
+        logits, tape = net._engine_forward(inputs, keep_tape=True)
+        ctx.net, ctx.tape, ctx.n_in, ctx.n_params = net, tape, n_in, len(params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.net._engine_backward(ctx.tape, dlogits)
+        return (None, None) + (None,) * ctx.n_in + tuple(grads)
+
+
+class _EngineNet(nn.Module):
+    """Shared host logic of fuseunet / UNet."""
+
+    _plan: E.Plan
+
+    def _engine_setup(self, plan: E.Plan, mode: Optional[str]):
+        self._plan = plan
+        self._bplan = E.BackwardPlan(plan)
+        self._glayout = E.GradLayout(plan)
+        self.engine_mode = mode or E.default_mode()
+        if self.engine_mode not in E.MODES:
+            raise ValueError(f"mode must be one of {sorted(E.MODES)}")
+        self._layouts: Dict[tuple, E.Layout] = {}
+        self._weights: Optional[E.PreparedWeights] = None
+        self._tensors: Optional[Dict[str, torch.Tensor]] = None
+        self._scratch: Optional[torch.Tensor] = None
+        self.last_grad_flat: Optional[torch.Tensor] = None
+
+    # ---- bookkeeping ---------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._tensors, self._weights, self._scratch = None, None, None
+        return out
+
+    def _named(self) -> Dict[str, torch.Tensor]:
+        if self._tensors is None:
+            t = dict(self.named_parameters())
+            t.update(dict(self.named_buffers()))
+            self._tensors = t
+        return self._tensors
+
+    def _param_order(self):
+        return [p for _, p in self.named_parameters()]
+
+    def _check_inputs(self, inputs):
+        x0 = inputs[0]
+        for x in inputs:
+            if not x.is_cuda:
+                raise RuntimeError("aide_b200 runs on CUDA only (there is no CPU fallback); move inputs to the GPU")
+            if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+                raise ValueError(f"expected fp32 [N,3,H,W] inputs, got {tuple(x.shape)} {x.dtype}")
+            if x.shape != x0.shape:
+                raise ValueError("both modalities must have the same shape")
+        p = next(self.parameters())
+        if p.device != x0.device:
+            raise RuntimeError(f"module is on {p.device}, inputs on {x0.device}")
+
+    # ---- engine calls --------------------------------------------------------------------------
+    def _engine_forward(self, inputs, keep_tape: bool):
+        plan = self._plan
+        fmt = E.MODES[self.engine_mode]
+        N, _, H, W = inputs[0].shape
+        key = (N, H, W, fmt)
+        layout = self._layouts.get(key)
+        if layout is None:
+            layout = self._layouts[key] = E.Layout(plan, N, H, W, fmt)
+        named = self._named()
+        training = self.training
+        wkey = tuple((named[u.conv + ".weight"].data_ptr(), named[u.conv + ".weight"]._version) for u in plan.units)
+        need_dgrad = keep_tape
+        if self._weights is None or self._weights.key != wkey or (need_dgrad and not self._weights.has_dgrad):
+            self._weights = E.PreparedWeights(plan, named, fmt, need_dgrad)
+        dev = inputs[0].device
+        if keep_tape:
+            arena = torch.empty(layout.total, dtype=torch.uint8, device=dev)
+        else:
+            if self._scratch is None or self._scratch.numel() < layout.total or self._scratch.device != dev:
+                self._scratch = torch.empty(layout.total, dtype=torch.uint8, device=dev)
+            arena = self._scratch
+        logits = torch.empty((N, plan.num_classes, H, W), dtype=torch.float32, device=dev)
+        xs = [x.detach().contiguous() for x in inputs]
+        E.run_forward(plan, layout, named, self._weights, xs, training, logits, arena)
+        if training:
+            torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], 1)
+        tape = None
+        if keep_tape:
+            tape = E.Tape()
+            tape.layout, tape.arena, tape.weights, tape.training = layout, arena, self._weights, training
+        return logits, tape
+
+    def _engine_backward(self, tape, dlogits):
+        if not tape.training:
+            raise NotImplementedError("backward through an eval-mode (running-statistics) BatchNorm forward is not "
+                                      "supported; the reference never does this")
+        named = self._named()
+        flat = torch.empty(self._glayout.total, dtype=torch.float32, device=dlogits.device)
+        E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
+                       dlogits.contiguous(), flat)
+        self.last_grad_flat = flat
+        return [self._glayout.view(flat, n) for n, _ in self.named_parameters()]
+
+    def _run(self, *inputs):
+        self._check_inputs(inputs)
+        params = self._param_order()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _NetFunction.apply(self, len(inputs), *inputs, *params)
+        logits, _ = self._engine_forward(inputs, keep_tape=False)
+        return logits
+
+
+# -------------------------------------------------------------------------------------------------
+# the two networks
+# -------------------------------------------------------------------------------------------------
+class fuseunet(_EngineNet):
+    """Two-encoder / one-decoder U-Net (models_twomodalinputs/fuseunet.py:6-91)."""
+
+    def __init__(self, num_classes=2, reduction=16, dilation=4, learned_bilinear=False, mode: Optional[str] = None):
+        super().__init__()
+        enc = [(3, 3, 32), (64, 32, 64), (128, 64, 128), (256, 128, 256), (512, 256, 512)]
+        for i, (c1, _, co) in enumerate(enc, 1):
+            setattr(self, f"modal1_downblock{i}", UNet_basic_down_block(c1, co))
+            if i < 5:
+                setattr(self, f"modal1_maxpool{i}", nn.MaxPool2d(kernel_size=2, stride=2))
+        for i, (_, c2, co) in enumerate(enc, 1):
+            setattr(self, f"modal2_downblock{i}", UNet_basic_down_block(c2, co))
+            if i < 5:
+                setattr(self, f"modal2_maxpool{i}", nn.MaxPool2d(kernel_size=2, stride=2))
+        self.up_block1 = UNet_basic_up_block(1024, 512, 512, learned_bilinear)
+        self.up_block2 = UNet_basic_up_block(512, 256, 256, learned_bilinear)
+        self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
+        self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
+        self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
+        self._engine_setup(E.plan_fuseunet(num_classes), mode)
+
+    def forward(self, modal1_inputs, modal2_inputs):
+        return self._run(modal1_inputs, modal2_inputs)
+
+
+class UNet(_EngineNet):
+    """Classic 5-level U-Net 3->64->...->1024 (models_singlemodalinput/UNet.py:135-165)."""
+
+    def __init__(self, num_classes=2, learned_bilinear=False, mode: Optional[str] = None):
+        super().__init__()
+        self.down_block1 = UNet_basic_down_block(3, 64, False)
+        self.down_block2 = UNet_basic_down_block(64, 128, True)
+        self.down_block3 = UNet_basic_down_block(128, 256, True)
+        self.down_block4 = UNet_basic_down_block(256, 512, True)
+        self.down_block5 = UNet_basic_down_block(512, 1024, True)
+        self.up_block1 = UNet_basic_up_block(1024, 512, 512, learned_bilinear)
+        self.up_block2 = UNet_basic_up_block(512, 256, 256, learned_bilinear)
+        self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
+        self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
+        self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
+        self._engine_setup(E.plan_unet(num_classes), mode)
+
+    def forward(self, x):
+        return self._run(x)

@@ -1,0 +1,73 @@
+"""Optimiser pieces ("next" row f1 of SURVEY.md section 8).
+
+FlatAdamAMSGrad = torch.optim.Adam(lr, amsgrad=True) (reference:
+train_files/trainchaos_proposed_30cases1labeled.py:231-232,323,325) applied by ONE kernel to flat fp32
+parameter / gradient / state buffers (aide_adam_amsgrad).  PolyLR mirrors utils/poly_lr_scheduler.py:31-51.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+from torch.optim.lr_scheduler import _LRScheduler
+
+from ._lib import call
+
+
+class FlatAdamAMSGrad:
+    """Keeps a flat copy-free view of the parameters: on construction the parameters are re-pointed into
+    one contiguous fp32 buffer (so ``module.parameters()`` keep working) and the three Adam states are
+    flat buffers of the same size.  ``step(grad_flat)`` consumes a flat gradient laid out in the same
+    parameter order (see flatten_grads) -- or the per-parameter ``.grad`` fields when called without."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.offsets, cur = [], 0
+        for p in self.params:
+            self.offsets.append(cur)
+            cur += (p.numel() + 3) // 4 * 4
+        dev = self.params[0].device
+        self.flat = torch.zeros(cur, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + p.numel()].view_as(p.data)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.vmax = torch.zeros_like(self.flat)
+        self.gbuf = torch.zeros_like(self.flat)
+
+    def flatten_grads(self) -> torch.Tensor:
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is not None:
+                self.gbuf[o:o + p.numel()].copy_(p.grad.reshape(-1))
+            else:
+                self.gbuf[o:o + p.numel()].zero_()
+        return self.gbuf
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self, grad_flat: torch.Tensor = None, grad_scale: float = 1.0):
+        g = self.flatten_grads() if grad_flat is None else grad_flat
+        if g.numel() != self.flat.numel():
+            raise ValueError("flat gradient does not match the flat parameter buffer")
+        self.t += 1
+        call("aide_adam_amsgrad", self.flat.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+             self.vmax.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t,
+             grad_scale, torch.cuda.current_stream().cuda_stream)
+        # the kernel wrote the parameters behind autograd's back: bump their version counters so that the
+        # engine re-derives its operand-format weight planes (PreparedWeights is keyed on _version)
+        torch.autograd.graph.increment_version(self.params)
+
+
+class PolyLR(_LRScheduler):
+    def __init__(self, optimizer, max_epoch, power=0.9, last_epoch=-1):
+        self.max_epoch, self.power = max_epoch, power
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        return [b * ((1.0 - float(self.last_epoch % self.max_epoch) / float(self.max_epoch)) ** self.power)
+                for b in self.base_lrs]

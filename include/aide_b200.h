@@ -1,0 +1,170 @@
+/* aide_b200.h -- C ABI of libaide_b200.so: the B200 (sm_100a) engine for the AIDE hot path.
+ *
+ * The reference (lich0031/AIDE) is pure Python/PyTorch and has no FFI of its own; each entry point
+ * below cites the reference code (file:line, relative to the reference tree) whose work it replaces.
+ * The Python host (aide_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; aide_last_error() returns a
+ *     thread-local description.  Nothing here allocates device memory: all buffers (including
+ *     workspaces, whose sizes are queried with the *_workspace_bytes / *_rows helpers) are owned
+ *     by the caller and passed as raw device pointers.  `stream` is a cudaStream_t.
+ *   - activations are NHWC ("pixel-major"): element (n,h,w,c) of a buffer with `ctot` channels
+ *     lives at ((n*H+h)*W+w)*ctot + c.  A *view* (p0,p1,ctot,coff) addresses channels
+ *     [coff, coff+C) of such a buffer -- this is how torch.cat (fuseunet.py:49-81,
+ *     netblocks.py:145) becomes zero-copy: producers write straight into their slice.
+ *   - `fmt` is the operand format of activation/weight planes:
+ *       AIDE_FMT_F32    one fp32 plane (CUDA-core exact path)
+ *       AIDE_FMT_TF32X2 two fp32 planes hi = rn_tf32(x), lo = x - hi ("parity mode": 3 tcgen05
+ *                       kind::tf32 MMAs hi*hi + hi*lo + lo*hi reproduce fp32 products)
+ *       AIDE_FMT_BF16   one bf16 plane ("fast mode": single kind::f16 MMA)
+ *     Raw convolution outputs (z), gradients w.r.t. activations and all reductions are fp32.
+ */
+#ifndef AIDE_B200_H_
+#define AIDE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AIDE_FMT_F32 = 0, AIDE_FMT_TF32X2 = 1, AIDE_FMT_BF16 = 2 };
+
+const char* aide_last_error(void);
+int aide_version(void);
+/* 1 if the tcgen05/TMA path can run (driver entry point for cuTensorMapEncodeTiled found). */
+int aide_has_tma(void);
+
+/* ---- layout / weight preparation -------------------------------------------------------------- */
+/* NCHW fp32 [N,C,H,W] (module boundary, fuseunet.py:43) -> NHWC view in operand format. */
+int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                      int N, int C, int H, int W, void* stream);
+/* NHWC view (operand format) -> NCHW fp32. */
+int aide_nhwc_to_nchw(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,
+                      float* dst, int N, int C, int H, int W, void* stream);
+/* nn.Conv2d weight OIHW fp32 [Cout,Cin,3,3] (netblocks.py:24,26,17) ->
+ *   fwd   planes [Cout][9][Cin]   (tap = ky*3+kx)            used by aide_conv3x3_fwd
+ *   dgrad planes [Cin][9][Cout]   (tap flipped: 8 - tap)     used by aide_conv3x3_fwd as dgrad
+ * either destination may be NULL. */
+int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
+                     void* fwd_p0, void* fwd_p1, void* dgrad_p0, void* dgrad_p1, void* stream);
+
+/* ---- conv3x3, stride 1, pad 1 (netblocks.py:24,26,17 -> ATen conv2d / cuDNN) -------------------- */
+/* z[n,h,w,co] = bias[co] + sum_{tap,ci} x[n,h+dy,w+dx,ci] * w[co][tap][ci].
+ * Also emits per-tile BatchNorm partial statistics (sum z, sum z^2 per channel) when stat_partial
+ * != NULL: layout [rows][2][cout] fp32 with rows = aide_conv3x3_stat_rows(...).
+ * The same entry point computes dgrad when given dgrad-prepared weights (bias = stats = NULL).
+ * F32 -> CUDA-core kernel; TF32X2/BF16 -> tcgen05 implicit GEMM fed by TMA (needs cin%32==0
+ * (TF32X2) or cin%32==0 (BF16), cout%32==0; other shapes -> error). */
+int aide_conv3x3_stat_rows(int fmt, int N, int H, int W);
+int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                     const void* w_p0, const void* w_p1, const float* bias,
+                     float* z, int z_ctot, int z_coff, int cout, int N, int H, int W,
+                     float* stat_partial, void* stream);
+/* dW[co,ci,ky,kx] = sum_{n,h,w} dz[n,h,w,co] * x[n,h+ky-1,w+kx-1,ci]  (ATen conv backward-filter).
+ * dz is a plain [N,H,W,cout] operand-format buffer.  Result written (not accumulated) as OIHW fp32. */
+size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
+int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                       const void* dz_p0, const void* dz_p1, int cout, int N, int H, int W,
+                       void* workspace, size_t workspace_bytes, float* dw_oihw, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, +MaxPool2d(2,2), +concat slot) (netblocks.py:25,27,28; fuseunet.py:13-31) */
+/* Reduce the conv's partial statistics in fixed order (fp64), then
+ *   training: mean/biased var -> scale,shift ; running_mean/var updated with momentum, unbiased var
+ *   eval    : scale,shift from running stats (stat_partial ignored)
+ * scale_shift: [2][C] fp32 (y = scale*z + shift); mean_rstd: [2][C] fp32 (saved for backward). */
+int aide_bn_finalize(const float* stat_partial, int rows, int C, double count,
+                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float momentum, float eps, int training,
+                     float* scale_shift, float* mean_rstd, void* stream);
+/* y = relu(scale*z+shift) written to `dst` (full resolution) and, when given, the 2x2 max-pooled y to
+ * up to two half-resolution views (the fused-encoder concat and the modal-2 branch, fuseunet.py:51-56). */
+int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, int C, const float* scale_shift,
+                       void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                       void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                       void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream);
+/* backward, stage 1: g = relu'(y) * (sum of upstream gradients).  Upstream sources (all fp32 NHWC):
+ * up to 3 same-resolution slices and up to 3 half-resolution slices routed through the max-pool
+ * arg-max (first maximum in window scan order wins, like ATen max_pool2d_with_indices).  y is
+ * recomputed from z.  Writes g [N,H,W,C] and per-block partial sums of (g, g*xhat): [rows][2][C],
+ * rows = aide_bn_bwd_rows(N,H,W,C). */
+int aide_bn_bwd_rows(int N, int H, int W, int C);
+int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift, const float* mean_rstd,
+                            int N, int H, int W, int C,
+                            const float* const* direct_ptr, const int* direct_ctot, const int* direct_coff, int n_direct,
+                            const float* const* pool_ptr, const int* pool_ctot, const int* pool_coff, int n_pool,
+                            float* g, float* partial, void* stream);
+/* backward, stage 2: sums = fixed-order reduction of `partial`; dgamma = sum g*xhat, dbeta = sum g,
+ * dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) stored in operand format [N,H,W,C];
+ * dbias_conv = sum dz (mathematically 0 under train-mode BN; kept for fidelity).
+ * partial2: scratch [rows][C] fp32 (rows as above). */
+int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd, const float* gamma,
+                           const float* partial, int rows, int N, int H, int W, int C,
+                           void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
+                           float* partial2, void* stream);
+
+/* ---- nn.Upsample(scale_factor=2, bilinear, align_corners=True) (netblocks.py:16) ---------------- */
+int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,
+                        void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                        int N, int h, int w, int C, void* stream);
+/* d_lo[N,h,w,C] (fp32) = transpose of the interpolation applied to d_hi view [N,2h,2w,*] (fp32). */
+int aide_upsample2x_bwd(const float* dhi, int dhi_ctot, int dhi_coff, float* dlo, int N, int h, int w, int C,
+                        void* stream);
+
+/* ---- last_conv1: 1x1 conv C -> K + bias (fuseunet.py:41,89; UNet.py:150,164) --------------------- */
+int aide_conv1x1_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int C,
+                     const float* w /*[K][C]*/, const float* bias, float* logits_nchw, int K,
+                     int N, int H, int W, void* stream);
+int aide_conv1x1_bwd_rows(int N, int H, int W, int C);
+int aide_conv1x1_bwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int C,
+                     const float* w, const float* dlogits_nchw, int K, int N, int H, int W,
+                     float* dx /*[N,H,W,C] fp32*/, float* dw_db /*[K*C] dW then [K] dbias*/,
+                     float* partial /*[rows][K*C+K]*/, void* stream);
+
+/* ---- losses (utils/loss2d.py, utils/metrics2d.py, train_files/trainchaos_proposed_*.py) --------- */
+/* One pass over logits [N,2,H,W] (NCHW fp32) + targets [N,H,W] int64 producing per image, in fp64:
+ *   sums[n][0]=sum ce*wc[t]  [1]=sum wc[t] (non-ignored)  [2]=sum s*t  [3]=sum s  [4]=sum t
+ *   [5]=#(s>=thr & t)  [6]=#(s>=thr)  [7]=sum wm*((1-s-q0)^2+(s-q1)^2)   (s = softmax prob of class 1)
+ * q (pseudo label [N,2,H,W]) / wm (weight map [N,1,H,W]) may be NULL (-> [7] = 0).
+ * Replaces CrossEntropyLoss2d (loss2d.py:5-13), DiceLoss (:35-61), MulticlassDiceLoss (:87-107),
+ * MulticlassMSELoss*weightmap (:109-117 + trainchaos_proposed_30cases1labeled.py:311-313) and the
+ * counting part of Dice_fn (metrics2d.py:8-29). */
+int aide_loss_sums(const float* logits, const int64_t* targets, const float* q, const float* wm,
+                   int N, int H, int W, float wc0, float wc1, int ignore_index, float threshold,
+                   double* sums /*[N][8]*/, double* scratch /*[N*aide_loss_blocks()][8]*/, void* stream);
+int aide_loss_blocks(int H, int W);
+/* per-image loss [N] fp32: w_ce * sums0/(H*W) + w_dice * (1 - (2*sums2+smooth)/(sums3+sums4+smooth))
+ * (CEMDiceLossImage.forward, loss2d.py:146-154); dice_fn_out (nullable): batch SUM of per-image
+ * Dice with the empty-target rule (metrics2d.py:19-24). */
+int aide_loss_image_finalize(const double* sums, int N, int H, int W, float w_ce, float w_dice, float smooth,
+                             float* loss_img, float* dice_img, float* dice_fn_out, void* stream);
+/* dL/dlogits for L = sum_n [ a_ce[n]*sum_hw ce*wc[t] + a_dice[n]*dice_n + a_mse[n]*sums7_n ]
+ * (closed form).  Any coefficient array may be NULL (= 0).  dlogits [N,2,H,W]. */
+int aide_loss_bwd(const float* logits, const int64_t* targets, const float* q, const float* wm,
+                  const double* sums, const float* a_ce, const float* a_dice, const float* a_mse,
+                  int N, int H, int W, float wc0, float wc1, int ignore_index, float smooth,
+                  float* dlogits, void* stream);
+/* softmax of n_aug logit tensors, mean, sharpen p^expo / sum, weight map 1-4*q0*q1
+ * (trainchaos_proposed_30cases1labeled.py:274-292,97-101). */
+int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo,
+                      float* q /*[N,2,H,W]*/, float* wm /*[N,1,H,W]*/, void* stream);
+/* Small-loss selection (trainchaos_proposed_30cases1labeled.py:305-321): ascending argsort of
+ * `pre_other` (the OTHER net's per-image loss) -> idx[N]; the first n_clean images are "clean".
+ * Emits this net's per-image coefficients and its scalar loss
+ *   loss = seg_w*(mean_clean L + (1-rate)*mean_rest L) + cor_w*rate*sum_rest(sums7)/(n_rest*2*H*W)
+ * with L = own per-image CE+Dice loss (loss_img).  a_* are the d loss / d(per-image term) weights
+ * consumed by aide_loss_bwd. */
+int aide_coteach_select(const float* pre_other, const float* loss_img, const double* sums, int N, int H, int W,
+                        int n_clean, float rate, float seg_w, float cor_w, float w_ce, float w_dice,
+                        int64_t* idx, float* a_ce, float* a_dice, float* a_mse, float* loss_out, void* stream);
+
+/* ---- optimiser ("next" row f1): torch.optim.Adam(amsgrad=True) on a flat fp32 buffer ------------- */
+int aide_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, size_t n,
+                      float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIDE_B200_H_ */

@@ -1,0 +1,307 @@
+"""GPU: every kernel of libaide_b200 against the same operator on the CPU (torch fp32 / the oracle),
+called through the C ABI (aide_b200.ops / aide_b200.losses are thin ctypes wrappers).
+
+Tolerances: 'exact' (fp32 CUDA cores) and 'parity' (3xTF32 tcgen05) must agree with fp32 to ~1e-5 of the
+tensor's max (fp32 summation-order noise); 'fast' (single-pass BF16) is only sanity-checked."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 2e-5, 1: 3e-5, 2: 3e-2}          # FMT_F32, FMT_TF32X2, FMT_BF16
+NAMES = {0: "exact", 1: "parity", 2: "fast"}
+
+
+def relmax(a, b):
+    return ((a.cpu().double() - b.cpu().double()).abs().max() / b.cpu().double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+CONV_SHAPES = [  # N, H, W, cin, cout
+    (2, 16, 16, 32, 32), (1, 32, 32, 64, 64), (2, 8, 8, 128, 256), (1, 20, 12, 64, 32),
+    (1, 2, 2, 512, 128), (1, 16, 128, 32, 64), (3, 24, 40, 96, 96), (1, 8, 8, 1024, 512),
+]
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3x3_forward_and_stats(dev, fmt, shape):
+    from aide_b200 import ops
+    N, H, W, cin, cout = shape
+    x, w, b = rnd(N, cin, H, W, seed=1), rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5), rnd(cout, seed=3)
+    ref = F.conv2d(x, w, b, padding=1)
+    a = ops.from_nchw(x.to(dev), fmt)
+    z, part = ops.conv3x3(a, w.to(dev), b.to(dev), stats=True)
+    torch.cuda.synchronize()
+    got = ops.nhwc_to_nchw(z)
+    assert relmax(got, ref) < TOL[fmt], NAMES[fmt]
+    s = part.sum(0).cpu()
+    assert relmax(s[0], got.cpu().sum((0, 2, 3))) < 1e-4
+    assert relmax(s[1], (got.cpu() ** 2).sum((0, 2, 3))) < 1e-4
+
+
+def test_conv3x3_first_layer_cin3(dev):
+    from aide_b200 import ops
+    x, w, b = rnd(2, 3, 32, 48, seed=1), rnd(32, 3, 3, 3, seed=2, scale=0.2), rnd(32, seed=3)
+    a = ops.from_nchw(x.to(dev), 0)
+    z, _ = ops.conv3x3(a, w.to(dev), b.to(dev))
+    assert relmax(ops.nhwc_to_nchw(z), F.conv2d(x, w, b, padding=1)) < 2e-5
+    dz = rnd(2, 32, 32, 48, seed=5)
+    dw = ops.conv3x3_wgrad(a, ops.from_nchw(dz.to(dev), 0))
+    ref = torch.nn.grad.conv2d_weight(x, w.shape, dz, padding=1)
+    assert relmax(dw, ref) < 3e-5
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3x3_dgrad_wgrad(dev, fmt, shape):
+    from aide_b200 import ops
+    N, H, W, cin, cout = shape
+    x, w, dz = rnd(N, cin, H, W, seed=4), rnd(cout, cin, 3, 3, seed=5, scale=(9 * cin) ** -0.5), rnd(N, cout, H, W, seed=6)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, w, dz, padding=1)
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dz, padding=1)
+    dza = ops.from_nchw(dz.to(dev), fmt)
+    dx = ops.nhwc_to_nchw(ops.conv3x3_dgrad(dza, w.to(dev)))
+    dw = ops.conv3x3_wgrad(ops.from_nchw(x.to(dev), fmt), dza)
+    torch.cuda.synchronize()
+    assert relmax(dx, ref_dx) < TOL[fmt], "dgrad " + NAMES[fmt]
+    assert relmax(dw, ref_dw) < TOL[fmt], "wgrad " + NAMES[fmt]
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_conv3x3_channel_views(dev, fmt):
+    """conv reading a channel slice of a wider buffer and writing... (zero-copy concat, fuseunet.py:49-55)."""
+    from aide_b200 import ops
+    x, w = rnd(2, 96, 16, 16, seed=7), rnd(64, 32, 3, 3, seed=8, scale=0.06)
+    a = ops.from_nchw(x.to(dev), fmt)
+    z, _ = ops.conv3x3(a, w.to(dev), None, cin=32, coff=64)
+    assert relmax(ops.nhwc_to_nchw(z), F.conv2d(x[:, 64:96], w, None, padding=1)) < TOL[fmt]
+    dz = rnd(2, 64, 16, 16, seed=9)
+    dw = ops.conv3x3_wgrad(a, ops.from_nchw(dz.to(dev), fmt), cin=32, coff=64)
+    assert relmax(dw, torch.nn.grad.conv2d_weight(x[:, 64:96], w.shape, dz, padding=1)) < TOL[fmt]
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_conv_adjoint_identity_full_size(dev, fmt):
+    """Size-independent property at a BASELINE-sized layer (B=4, 128x128, 128->64):
+    <conv(x,w), dz> == <x, dgrad(dz,w)> == <w, wgrad(x,dz)>."""
+    from aide_b200 import ops
+    N, H, W, cin, cout = 4, 128, 128, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, cin, H, W, device=dev, generator=g)
+    w = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * (9 * cin) ** -0.5
+    dz = torch.randn(N, cout, H, W, device=dev, generator=g)
+    xa, dza = ops.from_nchw(x, fmt), ops.from_nchw(dz, fmt)
+    z, _ = ops.conv3x3(xa, w, None)
+    a = (z.double() * dza.float().double()).sum().item()
+    b = (ops.conv3x3_dgrad(dza, w).double() * xa.float().double()).sum().item()
+    c = (ops.conv3x3_wgrad(xa, dza).double() * w.double()).sum().item()
+    tol = 1e-5 if fmt == 1 else 2e-2
+    scale = (z.double().norm() * dza.float().double().norm()).item()
+    assert abs(a - b) < tol * scale and abs(a - c) < tol * scale, (a, b, c)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_relu_pool_forward(dev, fmt, training):
+    from aide_b200 import ops
+    N, C, H, W = 3, 64, 12, 20
+    x, w = rnd(N, 32, H, W, seed=1), rnd(C, 32, 3, 3, seed=2, scale=0.1)
+    gamma, beta = rnd(C, seed=3).abs() + 0.5, rnd(C, seed=4)
+    rm, rv = rnd(C, seed=5) * 0.1, rnd(C, seed=6).abs() + 0.5
+    zr = F.conv2d(x, w, None, padding=1)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    yr = F.relu(F.batch_norm(zr, rm_ref, rv_ref, gamma, beta, training, 0.1, 1e-5))
+    a = ops.from_nchw(x.to(dev), 0)
+    z, part = ops.conv3x3(a, w.to(dev), None, stats=True)
+    rmd, rvd = rm.to(dev), rv.to(dev)
+    ss, mr = ops.bn_finalize(part, N * H * W, gamma.to(dev), beta.to(dev), rmd, rvd, training)
+    y, p = ops.bn_relu_apply(z, ss, fmt, pool=True)
+    tol = 5e-5 if fmt != 2 else 1e-2
+    assert relmax(ops.to_nchw(y), yr) < tol
+    assert relmax(ops.to_nchw(p), F.max_pool2d(yr, 2, 2)) < tol
+    assert relmax(rmd, rm_ref) < 1e-5 and relmax(rvd, rv_ref) < 1e-5
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_bn_relu_pool_backward(dev, fmt):
+    """g routing: one same-resolution source + two pooled sources (the modal-2 level-1 pattern)."""
+    from aide_b200 import ops
+    from aide_b200._lib import call, lib
+    import ctypes as C
+    N, Cc, H, W = 2, 32, 8, 12
+    z = rnd(N, Cc, H, W, seed=1).requires_grad_()
+    gamma, beta = (rnd(Cc, seed=2).abs() + 0.5).requires_grad_(), rnd(Cc, seed=3).requires_grad_()
+    y = F.relu(F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5))
+    p = F.max_pool2d(y, 2, 2)
+    gd, gp1, gp2 = rnd(N, 64, H, W, seed=4), rnd(N, 64, H // 2, W // 2, seed=5), rnd(N, Cc, H // 2, W // 2, seed=6)
+    loss = (y * gd[:, 16:48]).sum() + (p * gp1[:, 32:64]).sum() + (p * gp2).sum()
+    dz_ref, dg_ref, db_ref = torch.autograd.grad(loss, [z, gamma, beta])
+    st = torch.cuda.current_stream().cuda_stream
+    zd = z.detach().permute(0, 2, 3, 1).contiguous().to(dev)
+    # statistics exactly as the forward would produce them
+    part = torch.stack([zd.sum((0, 1, 2)), (zd ** 2).sum((0, 1, 2))])[None].contiguous()
+    ss, mr = ops.bn_finalize(part, N * H * W, gamma.detach().to(dev), beta.detach().to(dev), None, None, True)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dev)
+    d0, p0, p1 = nhwc(gd), nhwc(gp1), nhwc(gp2)
+    rows = lib.aide_bn_bwd_rows(N, H, W, Cc)
+    g = torch.empty(N, H, W, Cc, device=dev)
+    part1 = torch.empty(rows, 2, Cc, device=dev)
+    part2 = torch.empty(rows, Cc, device=dev)
+    dptr, dct, dco = (C.c_void_p * 3)(d0.data_ptr()), (C.c_int * 3)(64), (C.c_int * 3)(16)
+    pptr, pct, pco = (C.c_void_p * 3)(p0.data_ptr(), p1.data_ptr()), (C.c_int * 3)(64, Cc), (C.c_int * 3)(32, 0)
+    call("aide_bn_relu_bwd_reduce", zd.data_ptr(), ss.data_ptr(), mr.data_ptr(), N, H, W, Cc, dptr, dct, dco, 1,
+         pptr, pct, pco, 2, g.data_ptr(), part1.data_ptr(), st)
+    dz = ops.Act(N, H, W, Cc, fmt, dev)
+    small = torch.empty(3, Cc, device=dev)
+    call("aide_bn_relu_bwd_apply", fmt, g.data_ptr(), zd.data_ptr(), mr.data_ptr(), gamma.detach().to(dev).data_ptr(),
+         part1.data_ptr(), rows, N, H, W, Cc, dz.p0, dz.p1, small[1].data_ptr(), small[0].data_ptr(),
+         small[2].data_ptr(), part2.data_ptr(), st)
+    assert relmax(ops.to_nchw(dz), dz_ref) < 5e-5
+    assert relmax(small[1], dg_ref) < 5e-5 and relmax(small[0], db_ref) < 5e-5
+    assert small[2].abs().max().item() < 1e-4 * dz_ref.abs().max().item() * N * H * W   # sum dz == 0 analytically
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("hw", [(16, 16), (1, 1), (6, 10)])
+def test_upsample_bilinear(dev, fmt, hw):
+    from aide_b200 import ops
+    h, w = hw
+    x = rnd(2, 32, h, w, seed=1)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    y = ops.upsample2x(ops.from_nchw(x.to(dev), fmt))
+    assert relmax(ops.to_nchw(y), ref) < (1e-5 if fmt != 2 else 1e-2)
+    if fmt == 0:
+        g = rnd(2, 32, 2 * h, 2 * w, seed=2)
+        xr = x.clone().requires_grad_()
+        (F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True) * g).sum().backward()
+        dlo = ops.upsample2x_bwd(g.permute(0, 2, 3, 1).contiguous().to(dev))
+        assert relmax(ops.nhwc_to_nchw(dlo), xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_conv1x1_head(dev, fmt):
+    from aide_b200 import ops
+    x, w, b = rnd(2, 64, 20, 24, seed=1), rnd(2, 64, 1, 1, seed=2, scale=0.1), rnd(2, seed=3)
+    ref = F.conv2d(x, w, b)
+    a = ops.from_nchw(x.to(dev), fmt)
+    out = ops.conv1x1(a, w.view(2, 64).to(dev), b.to(dev))
+    tol = 1e-5 if fmt != 2 else 1e-2
+    assert relmax(out, ref) < tol
+    dl = rnd(2, 2, 20, 24, seed=4)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    (F.conv2d(xr, wr, br) * dl).sum().backward()
+    dx, dw, db = ops.conv1x1_bwd(a, w.view(2, 64).to(dev), dl.to(dev))
+    assert relmax(ops.nhwc_to_nchw(dx), xr.grad) < 1e-5
+    assert relmax(dw, wr.grad.view(2, 64)) < tol and relmax(db, br.grad) < 1e-5
+
+
+def test_losses_against_oracle(dev, golden, oracle):
+    import aide_b200 as A
+    g = golden["loss"]
+    lg, lg2, tg = g["logits"].to(dev), g["logits2"].to(dev), g["targets"].to(dev)
+    assert torch.allclose(A.CEMDiceLossImage([1., 1.], torch.tensor([1., 1.]), [1., 1.])(lg, tg).cpu(), g["cedice_img"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(A.CEMDiceLossImage([0.5, 2.0], [0.3, 1.7], None)(lg, tg).cpu(), g["cedice_img_w"], rtol=1e-5, atol=1e-6)
+    assert abs(A.CEMDiceLoss([1., 1.], [1., 1.], [1., 1.])(lg, tg).item() - g["cedice_mean"]) < 1e-5
+    assert abs(A.DiceLoss()(lg, tg).item() - g["dice_loss"]) < 1e-6
+    assert abs(A.Dice_fn(lg, tg).item() - g["dice_fn"]) < 1e-6
+    assert torch.allclose(A.CrossEntropyLoss2d(reduction="none")(lg, tg).cpu(), g["ce_none"], rtol=1e-5, atol=1e-6)
+    q, wm = A.pseudo_label([lg, lg2], 1.0)
+    assert torch.allclose(q.cpu(), g["q"], atol=1e-6) and torch.allclose(wm.cpu(), g["wmap"], atol=1e-6)
+    assert torch.allclose(A.pseudo_label([lg, lg2], 2.0, "chaos")[0].cpu(), g["q_T2_chaos"], atol=1e-6)
+    assert torch.allclose(A.pseudo_label([lg, lg2], 2.0, "kidney")[0].cpu(), g["q_T2_kidney"], atol=1e-6)
+    # empty / ragged: a 1-pixel image and an all-ignore target
+    one = A.CEMDiceLossImage()(lg[:1, :, :1, :1].contiguous(), tg[:1, :1, :1].contiguous())
+    assert torch.allclose(one.cpu(), oracle.ce_dice_per_image(g["logits"][:1, :, :1, :1], g["targets"][:1, :1, :1]), atol=1e-6)
+
+
+def test_loss_backward_against_autograd(dev, golden, oracle):
+    import aide_b200 as A
+    g = golden["loss"]
+    lg_c = g["logits"].clone().requires_grad_()
+    tg = g["targets"]
+    up = torch.tensor([0.3, -1.2, 2.0, 0.7, 1.1])
+    (oracle.ce_dice_per_image(lg_c, tg, (0.5, 2.0), (0.3, 1.7)) * up).sum().backward()
+    lg = g["logits"].to(dev).requires_grad_()
+    (A.CEMDiceLossImage([0.5, 2.0], [0.3, 1.7], None)(lg, tg.to(dev)) * up.to(dev)).sum().backward()
+    assert relmax(lg.grad, lg_c.grad) < 1e-5
+    for red in ("mean", "sum"):
+        lg_c.grad = None
+        lg.grad = None
+        import torch.nn.functional as F
+        w = torch.tensor([0.3, 1.7])
+        ce = F.cross_entropy(lg_c, tg, weight=w, reduction=red)
+        dl = oracle.dice_per_image(lg_c, tg)
+        ((ce * 0.5) + (dl.sum() / 5 if red == "mean" else dl.sum()) * 2.0).backward()
+        A.CEMDiceLoss([0.5, 2.0], [0.3, 1.7], None, reduction=red)(lg, tg.to(dev)).backward()
+        assert relmax(lg.grad, lg_c.grad) < 1e-5, red
+
+
+def test_coteach_step_against_oracle(dev, golden, oracle):
+    import aide_b200 as A
+    g = golden["loss"]
+    o1c, o2c = g["logits"].clone().requires_grad_(), g["logits2"].clone().requires_grad_()
+    gen = torch.Generator().manual_seed(5)
+    t1 = g["targets"]
+    t2 = (torch.rand(t1.shape, generator=gen) < 0.3).long()
+    a1, a2 = [torch.randn(o1c.shape, generator=gen) for _ in range(3)], [torch.randn(o1c.shape, generator=gen) for _ in range(3)]
+    q1c, w1c = oracle.pseudo_label(a1)
+    q2c, w2c = oracle.pseudo_label(a2)
+    for n_clean in (2, 3):
+        r = oracle.coteach_losses(o1c, o2c, t1, t2, q1c, w1c, q2c, w2c, 0.25, (1.0, 10.0), n_clean)
+        g1c, = torch.autograd.grad(r["loss1"], o1c, retain_graph=True)
+        g2c, = torch.autograd.grad(r["loss2"], o2c)
+        o1, o2 = g["logits"].to(dev).requires_grad_(), g["logits2"].to(dev).requires_grad_()
+        q1, w1 = A.pseudo_label([t.to(dev) for t in a1])
+        q2, w2 = A.pseudo_label([t.to(dev) for t in a2])
+        m = A.coteach_step(o1, o2, t1.to(dev), t2.to(dev), q1, w1, q2, w2, 0.25, (1.0, 10.0), n_clean)
+        assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"])
+        assert abs(m["loss1"].item() - r["loss1"].item()) < 2e-6 * max(1, abs(r["loss1"].item()))
+        assert abs(m["loss2"].item() - r["loss2"].item()) < 2e-6 * max(1, abs(r["loss2"].item()))
+        m["loss1"].backward(retain_graph=True)
+        m["loss2"].backward()
+        assert relmax(o1.grad, g1c) < 1e-5 and relmax(o2.grad, g2c) < 1e-5
+        assert abs(m["dice1"].item() - oracle.dice_fn(o1c.detach(), t2).item()) < 1e-6
+
+
+def test_coteach_classes(dev, golden):
+    import aide_b200 as A
+    g = golden["loss"]
+    lg, lg2, tg = g["logits"].to(dev), g["logits2"].to(dev), g["targets"].to(dev)
+    for name, (a, b) in g["coteach_classes"].items():
+        cls, _, variant = name.partition("@")
+        crit = getattr(A, cls)(reduction="none")
+        if variant:
+            o = crit(lg, lg2, tg, 0.4)
+        else:
+            o = crit(lg[:4].contiguous(), lg2[:4].contiguous(), tg[:4].contiguous(), 0.5)
+        assert abs(float(o[0]) - a) < 1e-5 * max(1, abs(a)) and abs(float(o[1]) - b) < 1e-5 * max(1, abs(b)), name
+
+
+def test_adam_amsgrad_matches_torch(dev):
+    import aide_b200 as A
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in [(7, 3, 3, 3), (7,), (130,)]]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt_ref = torch.optim.Adam(ref, lr=1e-3, amsgrad=True)
+    dps = [torch.nn.Parameter(p.detach().clone().to(dev)) for p in ps]
+    opt = A.FlatAdamAMSGrad(dps, lr=1e-3)
+    for step in range(5):
+        for p, r in zip(dps, ref):
+            gr = torch.randn(r.shape) * (0.1 if step % 2 else 1.0)
+            r.grad = gr.clone()
+            p.grad = gr.to(dev)
+        opt_ref.step()
+        opt.step()
+    for p, r in zip(dps, ref):
+        assert torch.allclose(p.detach().cpu(), r.detach(), rtol=1e-5, atol=1e-7)
