@@ -20,6 +20,7 @@ _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 SIGNATURES = {
     "aide_last_error": (C.c_char_p, []),
     "aide_version": (_i, []),
+    "aide_launch_count": (C.c_ulonglong, []),
     "aide_has_tma": (_i, []),
     "aide_nchw_to_nhwc": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_nhwc_to_nchw": (_i, [_i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -20,7 +20,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     cudaError_t _e = (expr);                                                     \
     if (_e != cudaSuccess) return ::aide::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
-#define AIDE_CHECK_LAUNCH() AIDE_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by exactly one AIDE_CHECK_LAUNCH(): it also feeds the
+// launch counter exported as aide_launch_count() (bench.py's "gpu_launches")
+void count_launch();
+#define AIDE_CHECK_LAUNCH()          \
+  do {                               \
+    ::aide::count_launch();          \
+    AIDE_CUDA(cudaGetLastError());   \
+  } while (0)
 #define AIDE_REQUIRE(cond, ...)                 \
   do {                                          \
     if (!(cond)) {                              \

@@ -41,12 +41,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+constexpr int kSwizzle128Atom32 = 1128;
+
 static int encode_tmap(CUtensorMap* m, bool bf16, int rank, const void* base, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   AIDE_REQUIRE(fn, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  // swizzle_bytes: 128 / 64 / 32 = classic 16B-chunk swizzles; kSwizzle128Atom32 = 128B span with 32B atoms
+  // (the only shared-memory layout tcgen05 accepts for MN-major 32-bit (tf32) operands)
+  CUtensorMapSwizzle sw = swizzle_bytes == kSwizzle128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                          : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
@@ -129,6 +134,11 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   constexpr int NPL = PARITY ? 2 : 1;
+  // tcgen05.mma truncates (rounds toward zero) when it adds into the TMEM accumulator, so the error of one
+  // accumulation chain grows linearly with its length (tools/accum_probe.py: 1.7e-5 rms at K = 9216 vs 1e-6 for
+  // fp32 FMA chains).  Parity mode therefore rotates the K blocks over NACC independent accumulators and adds
+  // them with round-to-nearest fp32 in the epilogue.
+  constexpr int NACC = PARITY ? 4 : 1;
   const int S = p.stages;
   const uint32_t bar_base = base + p.data_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -142,7 +152,8 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
   const int tw_i = m_tile % p.tiles_w, th_i = (m_tile / p.tiles_w) % p.tiles_h, n_img = m_tile / (p.tiles_w * p.tiles_h);
   const int h0 = th_i * p.TH, w0 = tw_i * p.TW, n0 = blockIdx.y * p.BN;
   const int num_kb = 9 * p.n_cchunks;
-  const uint32_t ncols = p.BN <= 32 ? 32u : p.BN <= 64 ? 64u : p.BN <= 128 ? 128u : 256u;
+  const uint32_t ncols_need = (uint32_t)(NACC * p.BN);
+  const uint32_t ncols = ncols_need <= 32 ? 32u : ncols_need <= 64 ? 64u : ncols_need <= 128 ? 128u : ncols_need <= 256 ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -193,24 +204,25 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
       const uint32_t layout = p.row_bytes == 128 ? 2u : 4u;
       const uint32_t sbo = 8u * p.row_bytes;
       const int nks = p.row_bytes / 32;
-      uint32_t accum = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % S, ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after_sync();
         const uint32_t a0 = base + s * p.stage_bytes;
         const uint32_t b0 = a0 + NPL * p.a_plane_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)((kb % NACC) * p.BN);
+        uint32_t accum = kb >= NACC ? 1u : 0u;
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t ko = ks * 32;
           if (PARITY) {
-            umma<TF32>(tmem_base, make_smem_desc(a0 + p.a_plane_bytes + ko, 16, sbo, layout),
+            umma<TF32>(acc, make_smem_desc(a0 + p.a_plane_bytes + ko, 16, sbo, layout),
                        make_smem_desc(b0 + ko, 16, sbo, layout), idesc, accum);
-            umma<TF32>(tmem_base, make_smem_desc(a0 + ko, 16, sbo, layout),
+            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout),
                        make_smem_desc(b0 + p.b_plane_bytes + ko, 16, sbo, layout), idesc, 1u);
-            umma<TF32>(tmem_base, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
+            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
                        idesc, 1u);
           } else {
-            umma<TF32>(tmem_base, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
+            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
                        idesc, accum);
           }
           accum = 1u;
@@ -235,6 +247,21 @@ __global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_const
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
       tmem_ld_wait();
+      if constexpr (NACC > 1) {
+        // pairwise (a0 + a1) + (a2 + a3), round-to-nearest fp32
+        uint32_t r1[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + ch * 32), r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r1[j]));
+        uint32_t r2[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.BN + ch * 32), r1);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * p.BN + ch * 32), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(__uint_as_float(r[j]) + (__uint_as_float(r1[j]) + __uint_as_float(r2[j])));
+      }
       float* dst = stg + (size_t)row * pitch + ch * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -378,7 +405,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, (uint32_t)p.BN);
-      const uint32_t layA = p.rbA == 128 ? 2u : 4u, layB = p.rbB == 128 ? 2u : 4u;
+      // MN-major operands.  16-bit: SWIZZLE_128B / SWIZZLE_64B atoms of 8 K-rows.  32-bit (tf32): the only legal
+      // layout is SWIZZLE_128B_BASE32B (type 1): 128-byte rows, 32-byte swizzle atoms, 4 K-rows per atom.
+      const uint32_t layA = TF32 ? 1u : (p.rbA == 128 ? 2u : 4u), layB = TF32 ? 1u : (p.rbB == 128 ? 2u : 4u);
+      const uint32_t krows = TF32 ? 4u : 8u;
       const int kel = TF32 ? 8 : 16;  // pixels (K elements) per MMA
       const int nks = p.KP / kel;
       uint32_t accum = 0;
@@ -391,11 +421,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
         const uint32_t b0 = a0 + NPL * p.a_plane_bytes;
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t ao = ks * kel * p.rbA, bo = ks * kel * p.rbB;
-          const uint64_t ah = make_smem_desc(a0 + ao, p.a_box_bytes, 8u * p.rbA, layA);
-          const uint64_t bh = make_smem_desc(b0 + bo, p.b_box_bytes, 8u * p.rbB, layB);
+          const uint64_t ah = make_smem_desc(a0 + ao, p.a_box_bytes, krows * p.rbA, layA);
+          const uint64_t bh = make_smem_desc(b0 + bo, p.b_box_bytes, krows * p.rbB, layB);
           if (PARITY) {
-            const uint64_t al = make_smem_desc(a0 + p.a_plane_bytes + ao, p.a_box_bytes, 8u * p.rbA, layA);
-            const uint64_t bl = make_smem_desc(b0 + p.b_plane_bytes + bo, p.b_box_bytes, 8u * p.rbB, layB);
+            const uint64_t al = make_smem_desc(a0 + p.a_plane_bytes + ao, p.a_box_bytes, krows * p.rbA, layA);
+            const uint64_t bl = make_smem_desc(b0 + p.b_plane_bytes + bo, p.b_box_bytes, krows * p.rbB, layB);
             umma<TF32>(tmem_base, al, bh, idesc, accum);
             umma<TF32>(tmem_base, ah, bl, idesc, 1u);
             umma<TF32>(tmem_base, ah, bh, idesc, 1u);
@@ -577,12 +607,14 @@ int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, in
   WgradParams& p = pl.p;
   AIDE_REQUIRE(ws && ws_bytes >= (size_t)pl.splits * 9 * cin * cout * sizeof(float), "conv3x3_wgrad(tc): workspace too small");
   p.ws = reinterpret_cast<float*>(ws);
-  if (act_tmap(&p.tmX0, bf16, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, p.rbA)) return 1;
-  if (act_tmap(&p.tmD0, bf16, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, p.rbB)) return 1;
+  const int swA = bf16 ? p.rbA : kSwizzle128Atom32, swB = bf16 ? p.rbB : kSwizzle128Atom32;
+  if (!bf16) AIDE_REQUIRE(p.rbA == 128 && p.rbB == 128, "conv3x3_wgrad(tc): tf32 operands need 32-channel (128 B) rows");
+  if (act_tmap(&p.tmX0, bf16, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+  if (act_tmap(&p.tmD0, bf16, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
   if (!bf16) {
     AIDE_REQUIRE(x1 && dz1, "conv3x3_wgrad(tc): TF32X2 needs hi and lo planes");
-    if (act_tmap(&p.tmX1, false, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, p.rbA)) return 1;
-    if (act_tmap(&p.tmD1, false, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, p.rbB)) return 1;
+    if (act_tmap(&p.tmX1, false, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+    if (act_tmap(&p.tmD1, false, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
   }
   dim3 grid(pl.mt, pl.nt, pl.splits);
   if (bf16) {

@@ -3,11 +3,15 @@
 #include <cstdarg>
 
 #include "common.cuh"
+#include <atomic>
 
 namespace aide {
 
 // ------------------------------------------------------------------ error plumbing (one TU owns it)
 static thread_local char g_err[1024] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -78,6 +82,7 @@ using namespace aide;
 
 extern "C" const char* aide_last_error(void) { return g_err; }
 extern "C" int aide_version(void) { return 100; }
+extern "C" unsigned long long aide_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
                                  int N, int C, int H, int W, void* stream) {

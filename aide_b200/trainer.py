@@ -1,0 +1,179 @@
+"""The AIDE training step on the B200 engine -- host orchestration only.
+
+Mirrors the inner loop of train_files/trainchaos_proposed_30cases1labeled.py:263-325 (kidney/breast flavours:
+trainkidney_proposed_mask1.py:267-333, trainbreast_dataset3_proposed_272cases25labeled.py:304):
+
+    4 augmented forwards per net (detached)          :265-269   train-mode BN (chaos) / eval-mode BN (kidney)
+    softmax, mean, sharpen, weight map               :274-292   -> aide_pseudo_label (one kernel per net)
+    train forwards of both nets                      :301-302
+    per-image CE+Dice, cross small-loss selection    :303-321   -> aide_loss_sums / aide_coteach_select
+    loss1.backward(); opt1.step(); loss2.backward(); opt2.step()   :322-325
+                                                     -> aide_loss_bwd, engine backward, aide_adam_amsgrad
+
+The two networks are independent until the selection needs the other net's per-image losses, so they run on
+two CUDA streams with two event joins (the reference runs them back to back on one stream).  Data-parallel
+training: every rank holds both nets and a local batch; BatchNorm statistics and the small-loss
+selection are local; the flat fp32 gradient of each net is all-reduced (mean) once per step -- net-1's
+all-reduce overlaps net-2's backward because they sit on different streams.
+
+Nothing here computes on the CPU; all device work goes through the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import engine as E
+from . import losses as L
+from ._lib import call, lib
+from .nets import UNet, fuseunet
+from .optim import FlatAdamAMSGrad
+
+
+def grad_order_params(net) -> List[torch.nn.Parameter]:
+    """Parameters in the order of the engine's flat gradient buffer (engine.GradLayout)."""
+    named = dict(net.named_parameters())
+    order = sorted(net._glayout.off.items(), key=lambda kv: kv[1][0])
+    return [named[name] for name, _ in order]
+
+
+class AideTrainer:
+    """Two co-trained networks + their Adam(amsgrad) state + the fused AIDE step.
+
+    kind: 'fuseunet' (two modalities) or 'unet' (one).  flavour: 'chaos' (train-mode augmented forwards,
+    sharpen = pow(T)) or 'kidney' (eval-mode augmented forwards, sharpen = pow(1/T)).
+    """
+
+    def __init__(self, kind: str = "fuseunet", mode: Optional[str] = None, device="cuda:0", seed: int = 2,
+                 lr: float = 1e-4, n_clean: int = 2, segcor_weight=(1.0, 10.0), temperature: float = 1.0,
+                 flavour: str = "chaos", two_streams: bool = True, process_group=None):
+        self.device = torch.device(device)
+        self.kind, self.flavour, self.temperature = kind, flavour, temperature
+        self.n_clean, self.segcor_weight = n_clean, segcor_weight
+        torch.manual_seed(seed)                      # net1 then net2: independent inits, as in :175-176
+        ctor = fuseunet if kind == "fuseunet" else UNet
+        self.net1 = ctor(num_classes=2, mode=mode).to(self.device).train()
+        self.net2 = ctor(num_classes=2, mode=mode).to(self.device).train()
+        self.opt1 = FlatAdamAMSGrad(grad_order_params(self.net1), lr=lr)
+        self.opt2 = FlatAdamAMSGrad(grad_order_params(self.net2), lr=lr)
+        for net, opt in ((self.net1, self.opt1), (self.net2, self.opt2)):
+            if opt.flat.numel() != net._glayout.total:
+                raise RuntimeError("flat parameter buffer and flat gradient layout disagree")
+            net._tensors = None                       # parameters were re-pointed into the flat buffer
+        self.group = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.two_streams = two_streams
+        if two_streams:
+            self.s1, self.s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.steps = 0
+
+    # ------------------------------------------------------------------------------------------
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Make every rank start from rank `src`'s weights (the reference's DataParallel replicates rank 0)."""
+        if self.world > 1:
+            for opt in (self.opt1, self.opt2):
+                torch.distributed.broadcast(opt.flat, src, group=self.group)
+            for net in (self.net1, self.net2):
+                for b in net.buffers():
+                    torch.distributed.broadcast(b, src, group=self.group)
+
+    def _inputs(self, x):
+        return tuple(x) if isinstance(x, (tuple, list)) else (x,)
+
+    def _half(self, net, opt, xs, augs, other: Dict, me: Dict, stage: int, t_other, rate: float):
+        """One network's share of the step, split in three stages around the two joins."""
+        if stage == 0:
+            # augmented forwards (no tape) -> pseudo label of THIS net; then the train forward (tape kept)
+            was_training = net.training
+            if self.flavour != "chaos":
+                net.eval()
+            with torch.no_grad():
+                a = [net._engine_forward(self._inputs(v), keep_tape=False)[0] for v in augs]
+            net.train(was_training)
+            if a:
+                me["q"], me["w"] = L.pseudo_label(a, self.temperature, self.flavour)
+            else:
+                me["q"] = me["w"] = None
+            me["logits"], me["tape"] = net._engine_forward(xs, keep_tape=True)
+        elif stage == 1:
+            # own per-image CE+Dice against the OTHER net's targets, consistency against the OTHER net's pseudo label
+            lg = me["logits"]
+            H, W = lg.shape[2:]
+            me["sums"] = L.image_sums(lg, t_other, other["q"], other["w"])
+            me["pre"], _, me["dice"] = L.image_finalize(me["sums"], H, W, 1.0, 1.0, 1.0, want_dice_fn=True)
+        else:
+            lg = me["logits"]
+            N, _, H, W = lg.shape
+            dev = lg.device
+            idx = torch.empty(N, dtype=torch.int64, device=dev)
+            coef = torch.empty((3, N), dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            call("aide_coteach_select", other["pre"].data_ptr(), me["pre"].data_ptr(), me["sums"].data_ptr(), N, H, W,
+                 min(self.n_clean, N), float(rate), float(self.segcor_weight[0]), float(self.segcor_weight[1]),
+                 1.0, 1.0, idx.data_ptr(), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
+                 loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            has_q = other["q"] is not None
+            d = L.loss_backward(lg, t_other, me["sums"], coef[0], coef[1], coef[2] if has_q else None,
+                                other["q"], other["w"])
+            net._engine_backward(me["tape"], d)
+            flat = net.last_grad_flat
+            if self.world > 1:
+                torch.distributed.all_reduce(flat, group=self.group)
+            opt.step(flat, grad_scale=1.0 / self.world)
+            me["loss"], me["idx"] = loss, idx
+            me["tape"] = None
+
+    def step(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float) -> Dict[str, torch.Tensor]:
+        """x / augs[i]: a tensor [B,3,H,W] (unet) or a pair of them (fuseunet), on the device.  t1, t2: [B,H,W] int64.
+        Returns device scalars loss1, loss2, dice1, dice2 (Dice_fn batch sums) and the index vectors; no host sync."""
+        xs = self._inputs(x)
+        m1: Dict = {}
+        m2: Dict = {}
+        cur = torch.cuda.current_stream(self.device)
+        if not self.two_streams:
+            for stage in range(3):
+                self._half(self.net1, self.opt1, xs, augs, m2, m1, stage, t2, rate)
+                self._half(self.net2, self.opt2, xs, augs, m1, m2, stage, t1, rate)
+        else:
+            s1, s2 = self.s1, self.s2
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            for stage in range(3):
+                with torch.cuda.stream(s1):
+                    self._half(self.net1, self.opt1, xs, augs, m2, m1, stage, t2, rate)
+                with torch.cuda.stream(s2):
+                    self._half(self.net2, self.opt2, xs, augs, m1, m2, stage, t1, rate)
+                if stage < 2:                      # join: each net needs the other's q/w (stage 1) and pre (stage 2)
+                    e1, e2 = s1.record_event(), s2.record_event()
+                    s1.wait_event(e2)
+                    s2.wait_event(e1)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+        self.steps += 1
+        return dict(loss1=m1["loss"], loss2=m2["loss"], dice1=m1["dice"], dice2=m2["dice"],
+                    indx1=m2["idx"], indx2=m1["idx"], pre1=m1["pre"], pre2=m2["pre"],
+                    out1=m1["logits"], out2=m2["logits"])
+
+    # ------------------------------------------------------------------------------------------
+    def step_from_host(self, host_batch: Dict, rate: float, device_batch: Optional[Dict] = None):
+        """End-to-end form: `host_batch` holds pinned CPU tensors (x: tuple, t1, t2, augs: list of tuples).
+        Copies them to the device (async, current stream), runs the step and reads the two losses and Dice sums
+        back to the host.  Returns (dict of python floats, h2d bytes, d2h bytes)."""
+        dev = self.device
+        h2d = 0
+
+        def up(t):
+            nonlocal h2d
+            h2d += t.numel() * t.element_size()
+            return t.to(dev, non_blocking=True)
+
+        xs = tuple(up(t) for t in self._inputs(host_batch["x"]))
+        t1, t2 = up(host_batch["t1"]), up(host_batch["t2"])
+        augs = [tuple(up(t) for t in self._inputs(a)) for a in host_batch["augs"]]
+        out = self.step(xs, t1, t2, augs, rate)
+        res = torch.stack([out["loss1"], out["loss2"], out["dice1"], out["dice2"]]).to("cpu")   # synchronising D2H
+        vals = res.tolist()
+        return dict(loss1=vals[0], loss2=vals[1], dice1=vals[2], dice2=vals[3]), h2d, res.numel() * 4

@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the AIDE hot path on B200, with the roofline of its dominant kernel and the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode parity|fast|exact]
+
+A *step* is one iteration of the AIDE proposed loop on one synthetic batch (BASELINE.json config 3,
+train_files/trainchaos_proposed_30cases1labeled.py:263-325): two fuseunets, per-GPU batch 8 of 2-modality
+256x256 slices, 4 augmented train-mode forwards per net -> pseudo labels, 2 train forwards, per-image CE+Dice,
+cross small-loss selection + weighted-MSE consistency, 2 backwards, (N>1: one gradient all-reduce per net over
+NCCL), 2 Adam(amsgrad) updates.  Nothing is skipped or cached inside the timed region.
+
+    value  = dual-network train slices/s, WHOLE job (all ranks), inputs resident in HBM
+    e2e    = the same through AideTrainer.step_from_host: pinned host buffers, H2D copies and the D2H read of
+             the losses inside the timed region
+    roofline     = the tcgen05 conv3x3 kernel (fwd/dgrad), every fuseunet layer shape timed alone with CUDA events
+    cpu_baseline = the oracle (CPU restatement of the reference step, torch CPU ops, all host threads) on a
+                   bounded sample of the same workload
+Under torchrun every rank runs its own batch (weak scaling); timing = max over ranks between barriers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FUSEUNET_FWD_GFLOP_256 = 116.207          # per slice per net, conv FLOPs only
+METRIC = "dual-FuseUNet train slices/sec @256x256x2 (AIDE proposed step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("AIDE_B200_MODE", "parity"), choices=["parity", "fast", "exact"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (slices per network per step)")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fast-mode / train-only side measurements")
+    ap.add_argument("--roofline-json", default="", help="also write the per-layer conv table to this file")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload: randn images, Bernoulli(0.08) masks, 4 augmented views, rate 0.25
+# ---------------------------------------------------------------------------------------------------------
+def make_batch(B, S, seed, device=None, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    img = lambda: torch.randn(B, 3, S, S, generator=g)
+    x = (img(), img())
+    t1 = (torch.rand(B, S, S, generator=g) < 0.08).long()
+    t2 = (torch.rand(B, S, S, generator=g) < 0.08).long()
+    augs = [(img(), img()) for _ in range(4)]
+    mv = (lambda t: t.pin_memory()) if pin else ((lambda t: t.to(device)) if device is not None else (lambda t: t))
+    return dict(x=tuple(mv(t) for t in x), t1=mv(t1), t2=mv(t2), augs=[tuple(mv(t) for t in a) for a in augs])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.th.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.impl == "engine":
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def timed_steps(fn, steps, world, device):
+    """barrier + sync, K steps between CUDA events, sync + barrier; returns max-over-ranks milliseconds."""
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.barrier()
+    return ms.item()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel: conv3x3 on tcgen05, every fuseunet layer shape, timed alone
+# ---------------------------------------------------------------------------------------------------------
+def conv_roofline(mode, B, S, device, peaks):
+    import aide_b200 as A
+    from aide_b200 import engine as E, ops
+    fmt = E.MODES[mode]
+    plan = E.plan_fuseunet(2)
+    shapes = {}
+    for u in plan.units:
+        if u.first:
+            continue
+        key = (u.cin, u.cout, S >> u.level)
+        shapes[key] = shapes.get(key, 0) + 1
+    rows, tot_flop, tot_ms = [], 0.0, 0.0
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # > 126 MB L2
+    for (cin, cout, hw), count in sorted(shapes.items(), key=lambda kv: -kv[0][2]):
+        x = ops.Act(B, hw, hw, cin, fmt, device)
+        x.planes.normal_()
+        w = torch.randn(cout, cin, 3, 3, device=device) * (9 * cin) ** -0.5
+        bias = torch.zeros(cout, device=device)
+        w0, w1, keep = ops.weight_prep(w, fmt)
+        z = torch.empty((B, hw, hw, cout), dtype=torch.float32, device=device)
+        nrows = A.lib.aide_conv3x3_stat_rows(fmt, B, hw, hw)
+        part = torch.empty((nrows, 2, cout), dtype=torch.float32, device=device)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def launch():
+            ops.call("aide_conv3x3_fwd", fmt, x.p0, x.p1, x.C, 0, cin, w0, w1, bias.data_ptr(), z.data_ptr(), cout, 0,
+                     cout, B, hw, hw, part.data_ptr(), st)
+        for _ in range(3):
+            launch()
+        reps, ms = 5, 0.0
+        for _ in range(reps):
+            flush.zero_()                                   # cold L2 for every timed launch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); launch(); e1.record()
+            torch.cuda.synchronize(device)
+            ms += e0.elapsed_time(e1)
+        ms /= reps
+        flop = 2.0 * B * hw * hw * cout * cin * 9
+        rows.append(dict(cin=cin, cout=cout, hw=hw, launches_per_fwd=count, ms=round(ms, 4),
+                         tflops=round(flop / ms / 1e9, 1)))
+        tot_flop += flop * count
+        tot_ms += ms * count
+        del x, z, part
+    achieved = tot_flop / tot_ms / 1e9
+    peak = peaks.get("bf16_tflops")
+    src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
+    if peak is None:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    passes = {"parity": 3, "fast": 1, "exact": 0}[mode]
+    return dict(bound="tensor", kernel="conv3x3_tc_kernel (tcgen05 implicit GEMM, fwd; dgrad is the same kernel)",
+                achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4), traffic=None,
+                peak_source=src, mma_passes=passes,
+                note=("algorithmic conv FLOPs (2*B*H*W*Cout*Cin*9) of one fuseunet forward's tensor-core layers / summed "
+                      "CUDA-event time of one launch per layer, L2 flushed before each launch; parity mode issues 3 "
+                      "kind::tf32 MMAs (half the bf16 rate) per algorithmic product, so its ceiling is peak/6"),
+                layers=rows)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle = CPU restatement of the reference step; the reference itself is Python and does not travel)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_fn(B, S):
+    from oracle import aide_oracle as O
+    torch.manual_seed(2)
+    p1 = O.clone_params(O.init_fuseunet(2), requires_grad=True)
+    p2 = O.clone_params(O.init_fuseunet(2), requires_grad=True)
+    st1, st2 = {}, {}
+    state = dict(step=0)
+
+    def run(i):
+        b = make_batch(B, S, 1234 + i)
+        r = O.aide_step(O.fuseunet_forward, p1, p2, b["x"], b["augs"], b["t1"], b["t2"], 0.25)
+        state["step"] += 1
+        O.adam_amsgrad_step(p1, r["grads1"], st1, state["step"])
+        O.adam_amsgrad_step(p2, r["grads2"], st2, state["step"])
+        return float(r["loss1"])
+    return run
+
+
+def cpu_baseline(B, S, budget_s=24.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe = cpu_step_fn(3, S)                  # 3 = smallest batch the step accepts (2 "clean" + >= 1 "rest")
+    t0 = time.time(); probe(0); t_one = (time.time() - t0) / 3.0   # also the warm-up (oneDNN primitive cache)
+    b = max(3, min(B, int(budget_s / 2.0 / max(t_one, 1e-3))))
+    run = cpu_step_fn(b, S)
+    n, t0 = 0, time.time()
+    while n < 1 or (time.time() - t0 < budget_s / 2.0 and n < 3):
+        run(n); n += 1
+    dt = (time.time() - t0) / n
+    return dict(value=round(b / dt, 4), unit="slices/s", cores=cores, kind="port",
+                sample=f"{n} AIDE step(s) at batch {b} (of {B}), {S}x{S}, after one batch-3 warm-up step; "
+                       f"oracle/aide_oracle.py (torch CPU fp32, {cores} threads), {dt:.2f} s/step")
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, S = args.batch, args.size
+    probe = cpu_step_fn(3, S)
+    t0 = time.time(); probe(0); t_one = (time.time() - t0) / 3.0
+    total = args.steps + args.warmup
+    b = max(3, min(B, int(150.0 / total / max(t_one, 1e-3))))
+    run = cpu_step_fn(b, S)
+    for i in range(args.warmup):
+        run(i)
+    t0 = time.time()
+    for i in range(args.steps):
+        run(args.warmup + i)
+    dt = (time.time() - t0) / max(args.steps, 1)
+    v = b / dt
+    sample = (f"{args.steps} timed AIDE steps at batch {b} (bounded sample of per-GPU batch {B}), {S}x{S}; "
+              f"oracle port of the reference step on {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "AIDE proposed step, 2x fuseunet, CPU reference path (BASELINE.json configs[2])",
+                   "per_gpu_batch": B, "sample_batch": b, "img_size": S, "modalities": 2, "aug_views": 4},
+        "cpu_baseline": {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    world, rank, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU path)")
+    import aide_b200 as A
+    from aide_b200.trainer import AideTrainer
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    B, S, K, W = args.batch, args.size, args.steps, max(args.warmup, 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+
+    def build(mode):
+        tr = AideTrainer("fuseunet", mode=mode, device=device, seed=2 + 0)
+        tr.broadcast_parameters(0)
+        return tr
+
+    tr = build(args.mode)
+    n_pool = 2
+    dev_batches = [make_batch(B, S, 1234 + 97 * rank + i, device=device) for i in range(n_pool)]
+
+    def dev_step(i):
+        b = dev_batches[i % n_pool]
+        tr.step(b["x"], b["t1"], b["t2"], b["augs"], 0.25)
+
+    for i in range(max(W, 3)):
+        dev_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = A.lib.aide_launch_count()
+    ms = timed_steps(dev_step, K, world, device)
+    launches = A.lib.aide_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of losses / Dice
+    host_batches = [make_batch(B, S, 4321 + 97 * rank + i, pin=True) for i in range(n_pool)]
+    io = {}
+
+    def host_step(i):
+        _, io["h2d"], io["d2h"] = tr.step_from_host(host_batches[i % n_pool], 0.25)
+
+    for i in range(2):
+        host_step(i)
+    ms_e2e = timed_steps(host_step, K, world, device)
+    e2e = dict(value=round(world * B * K / (ms_e2e / 1e3), 3), unit="slices/s", ms_per_step=round(ms_e2e / K, 3),
+               h2d_bytes_per_step=io["h2d"], d2h_bytes_per_step=io["d2h"],
+               api="aide_b200.trainer.AideTrainer.step_from_host (pinned host tensors in, python floats out)")
+
+    out = {
+        "metric": METRIC, "value": round(value, 3), "unit": "slices/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"parity": "tf32x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
+                  "fast": "bf16 operands, fp32 accumulate (NOT a parity mode)", "exact": "f32 CUDA cores"}[args.mode],
+        "data": "synthetic",
+        "config": {"workload": "AIDE proposed step: 2x fuseunet, 4 augmented forwards + train forward + backward per net, "
+                               "co-teaching selection, Adam-amsgrad (BASELINE.json configs[2]; configs[3] for N>1)",
+                   "mode": args.mode, "per_gpu_batch": B, "global_batch": B * world, "img_size": S, "modalities": 2,
+                   "aug_views": 4, "rate": 0.25, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; "
+                         f"{n_pool} distinct resident batches alternate",
+                   "algorithmic_gflop_per_slice": round((3 + 4) * 2 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2, 1)},
+        "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
+        "clocks": clocks, "e2e": e2e,
+    }
+    out["algorithmic_tflops"] = round(value * out["config"]["algorithmic_gflop_per_slice"] / 1e3, 1)
+
+    if rank == 0:
+        rl = conv_roofline(args.mode, B, S, device, peaks)
+        layers = rl.pop("layers")
+        out["roofline"] = rl
+        if args.roofline_json:
+            with open(args.roofline_json, "w") as f:
+                json.dump(dict(mode=args.mode, batch=B, size=S, summary=rl, layers=layers), f, indent=1)
+        if world == 1 and not args.no_extras and args.mode != "fast":
+            del tr
+            torch.cuda.empty_cache()
+            tr = build("fast")
+            for i in range(3):
+                dev_step(i)
+            ms_f = timed_steps(dev_step, K, world, device)
+            out["fast_mode"] = dict(value=round(B * K / (ms_f / 1e3), 3), unit="slices/s", ms_per_step=round(ms_f / K, 3),
+                                    note="single-pass bf16 operands; fails the 1e-3 logit parity bar (SURVEY.md 8d), "
+                                         "reported for context only")
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(B, S)
+            except Exception as e:  # noqa: BLE001 -- the GPU numbers above must still be reported
+                out["cpu_baseline"] = dict(value=None, unit="slices/s", cores=os.cpu_count(), kind="port",
+                                           sample=f"failed: {type(e).__name__}: {e}")
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,9 @@ enum { AIDE_FMT_F32 = 0, AIDE_FMT_TF32X2 = 1, AIDE_FMT_BF16 = 2 };
 
 const char* aide_last_error(void);
 int aide_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports the
+ * per-step difference as "gpu_launches"). */
+unsigned long long aide_launch_count(void);
 /* 1 if the tcgen05/TMA path can run (driver entry point for cuTensorMapEncodeTiled found). */
 int aide_has_tma(void);
 
