@@ -25,7 +25,7 @@ SIGNATURES = {
     "aide_nchw_to_nhwc": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_nhwc_to_nchw": (_i, [_i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_weight_prep": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "aide_conv3x3_stat_rows": (_i, [_i, _i, _i, _i]),
+    "aide_conv3x3_stat_rows": (_i, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "aide_conv3x3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
@@ -50,6 +50,7 @@ SIGNATURES = {
     "aide_pseudo_label": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aide_coteach_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_adam_amsgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
+    "aide_adam_amsgrad_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp, _vp, _f, _vp]),
 }
 
 

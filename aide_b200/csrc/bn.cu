@@ -35,17 +35,50 @@ int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* 
 }
 
 // ------------------------------------------------------------------ forward statistics finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
-                                   int training, float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
+// The conv kernels emit one partial row per output tile (thousands of rows at 256x256).  Stage 1 folds every
+// chunk of kStatChunk rows into an fp64 sum with many blocks and stores it IN PLACE as a (hi, lo) float pair in
+// the first two rows of its own chunk (no other block touches those cells); stage 2 -- the finalize kernel --
+// then walks only the folded rows.  Fixed order throughout: bit-reproducible run to run.
+constexpr int kStatChunk = 64;
+
+__global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int cols /* = 2*C */) {
+  __shared__ double sm[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kStatChunk;
+  const int r1 = min(rows, r0 + kStatChunk);
+  double acc = 0.0;
+  if (j < cols)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)partial[(size_t)r * cols + j];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    const float hi = (float)t;
+    partial[(size_t)r0 * cols + j] = hi;
+    if (r0 + 1 < rows) partial[(size_t)(r0 + 1) * cols + j] = (float)(t - (double)hi);
+  }
+}
+
+// rows are visited as r = g*row_stride + {0 .. sub-1} for g < groups  (plain: row_stride = 1, sub = 1, groups = rows)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups, int row_stride, int sub, int rows,
+                                   int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float momentum, float eps, int training,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
   __shared__ double s1[8][33], s2[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
   if (training && c < C) {
-    for (int r = threadIdx.y; r < rows; r += 8) {
-      a += (double)partial[((size_t)r * 2 + 0) * C + c];
-      b += (double)partial[((size_t)r * 2 + 1) * C + c];
+    for (int g = threadIdx.y; g < groups; g += 8) {
+      for (int k = 0; k < sub; ++k) {
+        const int r = g * row_stride + k;
+        if (r < rows) {
+          a += (double)partial[((size_t)r * 2 + 0) * C + c];
+          b += (double)partial[((size_t)r * 2 + 1) * C + c];
+        }
+      }
     }
   }
   s1[threadIdx.y][threadIdx.x] = a;
@@ -327,16 +360,24 @@ static BwdGeom bwd_geom(int N, int H, int W, int C) {
 
 using namespace aide;
 
-extern "C" int aide_bn_finalize(const float* stat_partial, int rows, int C, double count, const float* gamma,
+extern "C" int aide_bn_finalize(float* stat_partial, int rows, int C, double count, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, float momentum,
                                 float eps, int training, float* scale_shift, float* mean_rstd, void* stream) {
   AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift, "bn_finalize: bad arguments");
   AIDE_REQUIRE(training ? (stat_partial && rows > 0 && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics input");
   dim3 block(32, 8), grid(ceil_div(C, 32));
-  bn_finalize_kernel<<<grid, block, 0, as_stream(stream)>>>(stat_partial, rows, C, count, gamma, beta,
-                                                            running_mean, running_var, momentum, eps, training,
-                                                            scale_shift, mean_rstd);
+  int groups = rows, row_stride = 1, sub = 1;
+  if (training && rows > 2 * kStatChunk) {   // many tiles: fold chunks in parallel first (in place)
+    groups = ceil_div(rows, kStatChunk);
+    bn_stat_fold_kernel<<<dim3(ceil_div(2 * C, 32), groups), block, 0, as_stream(stream)>>>(stat_partial, rows, 2 * C);
+    AIDE_CHECK_LAUNCH();
+    row_stride = kStatChunk;
+    sub = 2;
+  }
+  bn_finalize_kernel<<<grid, block, 0, as_stream(stream)>>>(stat_partial, groups, row_stride, sub, rows, C, count,
+                                                            gamma, beta, running_mean, running_var, momentum, eps,
+                                                            training, scale_shift, mean_rstd);
   AIDE_CHECK_LAUNCH();
   return 0;
 }

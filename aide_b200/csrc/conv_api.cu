@@ -18,14 +18,22 @@ size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W)
 int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
              int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st);
 bool tma_available();
+bool c3_shape_ok(int cin, int cout);
+int c3_stat_rows(int N, int H, int W);
+int c3_conv3x3(const float* x, int x_ctot, int x_coff, const float* w, const float* bias, float* z, int z_ctot,
+               int z_coff, int cout, int N, int H, int W, float* stat_partial, cudaStream_t st);
+size_t c3_wgrad_workspace_bytes(int cout, int N, int H, int W);
+int c3_wgrad(const float* x, int x_ctot, int x_coff, const float* dz, int cout, int N, int H, int W, float* ws,
+             size_t ws_bytes, float* dw, cudaStream_t st);
 }  // namespace aide
 
 using namespace aide;
 
 extern "C" int aide_has_tma(void) { return tma_available() ? 1 : 0; }
 
-extern "C" int aide_conv3x3_stat_rows(int fmt, int N, int H, int W) {
-  return fmt == AIDE_FMT_F32 ? simt_stat_rows(N, H, W) : tc_stat_rows(N, H, W);
+extern "C" int aide_conv3x3_stat_rows(int fmt, int cin, int cout, int N, int H, int W) {
+  if (fmt != AIDE_FMT_F32) return tc_stat_rows(N, H, W);
+  return c3_shape_ok(cin, cout) ? c3_stat_rows(N, H, W) : simt_stat_rows(N, H, W);
 }
 
 extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
@@ -34,6 +42,9 @@ extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int
   AIDE_REQUIRE(x_p0 && w_p0 && z && cin > 0 && cout > 0 && N > 0 && H > 0 && W > 0, "conv3x3_fwd: bad arguments");
   AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot && z_coff >= 0 && z_coff + cout <= z_ctot,
                "conv3x3_fwd: channel view out of range");
+  if (fmt == AIDE_FMT_F32 && c3_shape_ok(cin, cout) && z_ctot % 4 == 0 && z_coff % 4 == 0)
+    return c3_conv3x3(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, reinterpret_cast<const float*>(w_p0), bias, z,
+                      z_ctot, z_coff, cout, N, H, W, stat_partial, as_stream(stream));
   if (fmt == AIDE_FMT_F32)
     return simt_conv3x3(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin,
                         reinterpret_cast<const float*>(w_p0), bias, z, z_ctot, z_coff, cout, N, H, W, stat_partial,
@@ -48,6 +59,7 @@ extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int
 }
 
 extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W) {
+  if (fmt == AIDE_FMT_F32 && c3_shape_ok(cin, cout)) return c3_wgrad_workspace_bytes(cout, N, H, W);
   if (fmt == AIDE_FMT_F32) return simt_wgrad_workspace_bytes(cin, cout, N, H, W);
   if (!tc_shape_ok(fmt, cin, cout)) return 0;
   return tc_wgrad_workspace_bytes(fmt, cin, cout, N, H, W);
@@ -58,6 +70,9 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
                                   size_t workspace_bytes, float* dw_oihw, void* stream) {
   AIDE_REQUIRE(x_p0 && dz_p0 && dw_oihw && workspace, "conv3x3_wgrad: null argument");
   AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot, "conv3x3_wgrad: channel view out of range");
+  if (fmt == AIDE_FMT_F32 && c3_shape_ok(cin, cout))
+    return c3_wgrad(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, reinterpret_cast<const float*>(dz_p0), cout, N,
+                    H, W, reinterpret_cast<float*>(workspace), workspace_bytes, dw_oihw, as_stream(stream));
   if (fmt == AIDE_FMT_F32)
     return simt_wgrad(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin, reinterpret_cast<const float*>(dz_p0),
                       cout, N, H, W, reinterpret_cast<float*>(workspace), workspace_bytes, dw_oihw, as_stream(stream));

@@ -476,9 +476,19 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
 constexpr int kSmemBudget2 = 100 * 1024;  // two CTAs per SM
 constexpr int kSmemBudget1 = 200 * 1024;  // one CTA per SM
 
+// opt in to > 48 KB dynamic shared memory: once per (kernel, device); not a stream operation
 template <typename K>
 static int set_smem(K kernel, int bytes) {
+  struct Seen { const void* fn; int dev; };
+  static thread_local Seen seen[64];
+  static thread_local int n_seen = 0;
+  int dev = 0;
+  AIDE_CUDA(cudaGetDevice(&dev));
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i].fn == fn && seen[i].dev == dev) return 0;
   AIDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (n_seen < 64) seen[n_seen++] = Seen{fn, dev};
   return 0;
 }
 

@@ -190,7 +190,7 @@ class Layout:
         for u in plan.units:
             h, w = H >> u.level, W >> u.level
             ufmt = FMT_F32 if u.first else fmt
-            rows = lib.aide_conv3x3_stat_rows(ufmt, N, h, w)
+            rows = lib.aide_conv3x3_stat_rows(ufmt, u.cin, u.cout, N, h, w)
             self.stat_rows[u.name] = rows
             self.off["z:" + u.name] = cur
             cur += _align(N * h * w * u.cout * 4)

@@ -135,7 +135,7 @@ class _EngineNet(nn.Module):
         named = self._named()
         training = self.training
         wkey = tuple((named[u.conv + ".weight"].data_ptr(), named[u.conv + ".weight"]._version) for u in plan.units)
-        need_dgrad = keep_tape
+        need_dgrad = keep_tape or getattr(self, "_prep_dgrad_always", False)
         if self._weights is None or self._weights.key != wkey or (need_dgrad and not self._weights.has_dgrad):
             self._weights = E.PreparedWeights(plan, named, fmt, need_dgrad)
         dev = inputs[0].device
@@ -161,7 +161,8 @@ class _EngineNet(nn.Module):
             raise NotImplementedError("backward through an eval-mode (running-statistics) BatchNorm forward is not "
                                       "supported; the reference never does this")
         named = self._named()
-        flat = torch.empty(self._glayout.total, dtype=torch.float32, device=dlogits.device)
+        # zeros, not empty: the 4-element alignment gaps between tensors are part of the flat Adam / all-reduce buffer
+        flat = torch.zeros(self._glayout.total, dtype=torch.float32, device=dlogits.device)
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
                        dlogits.contiguous(), flat)
         self.last_grad_flat = flat

@@ -85,7 +85,7 @@ def conv3x3(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], cin: Optional
     z = torch.empty((x.N, x.H, x.W, cout), dtype=torch.float32, device=w.device)
     part = None
     if stats:
-        rows = lib.aide_conv3x3_stat_rows(fmt, x.N, x.H, x.W)
+        rows = lib.aide_conv3x3_stat_rows(fmt, cin, cout, x.N, x.H, x.W)
         part = torch.zeros((rows, 2, cout), dtype=torch.float32, device=w.device)
     call("aide_conv3x3_fwd", fmt, x.p0, x.p1, x.C, coff, cin, w0, w1, bias.data_ptr() if bias is not None else None,
          z.data_ptr(), cout, 0, cout, x.N, x.H, x.W, part.data_ptr() if stats else None, _st())

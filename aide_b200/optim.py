@@ -36,6 +36,10 @@ class FlatAdamAMSGrad:
         self.v = torch.zeros_like(self.flat)
         self.vmax = torch.zeros_like(self.flat)
         self.gbuf = torch.zeros_like(self.flat)
+        # device-resident step counter + bias-correction scratch: nothing host-side changes between steps, so a
+        # captured CUDA graph of the training step replays correctly
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
 
     def flatten_grads(self) -> torch.Tensor:
         for p, o in zip(self.params, self.offsets):
@@ -54,10 +58,10 @@ class FlatAdamAMSGrad:
         g = self.flatten_grads() if grad_flat is None else grad_flat
         if g.numel() != self.flat.numel():
             raise ValueError("flat gradient does not match the flat parameter buffer")
-        self.t += 1
-        call("aide_adam_amsgrad", self.flat.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-             self.vmax.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t,
-             grad_scale, torch.cuda.current_stream().cuda_stream)
+        self.t += 1                      # host mirror (informational; the kernel uses the device counter)
+        call("aide_adam_amsgrad_dev", self.flat.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+             self.vmax.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+             self.step_dev.data_ptr(), self.bc_dev.data_ptr(), grad_scale, torch.cuda.current_stream().cuda_stream)
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that the
         # engine re-derives its operand-format weight planes (PreparedWeights is keyed on _version)
         torch.autograd.graph.increment_version(self.params)

@@ -20,6 +20,7 @@ Nothing here computes on the CPU; all device work goes through the C ABI.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -47,7 +48,8 @@ class AideTrainer:
 
     def __init__(self, kind: str = "fuseunet", mode: Optional[str] = None, device="cuda:0", seed: int = 2,
                  lr: float = 1e-4, n_clean: int = 2, segcor_weight=(1.0, 10.0), temperature: float = 1.0,
-                 flavour: str = "chaos", two_streams: bool = True, process_group=None):
+                 flavour: str = "chaos", two_streams: bool = True, process_group=None,
+                 cuda_graph: Optional[bool] = None):
         self.device = torch.device(device)
         self.kind, self.flavour, self.temperature = kind, flavour, temperature
         self.n_clean, self.segcor_weight = n_clean, segcor_weight
@@ -61,6 +63,7 @@ class AideTrainer:
             if opt.flat.numel() != net._glayout.total:
                 raise RuntimeError("flat parameter buffer and flat gradient layout disagree")
             net._tensors = None                       # parameters were re-pointed into the flat buffer
+            net._prep_dgrad_always = True             # one weight preparation per step serves all 5 forwards + dgrad
         self.group = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -69,8 +72,61 @@ class AideTrainer:
         if two_streams:
             self.s1, self.s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self.steps = 0
+        # One AIDE step is ~1 800 kernel launches; replaying it as ONE captured CUDA graph removes the per-launch
+        # host cost (ctypes marshalling + tensor-map encoding, ~50 us each) that otherwise bounds the step.
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("AIDE_B200_GRAPH", "1") != "0"
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs: Dict[tuple, tuple] = {}
+        self.graph_launches = 0          # kernels launched through graph replays (aide_launch_count() sees eager ones)
 
     # ------------------------------------------------------------------------------------------
+    def _state_tensors(self) -> List[torch.Tensor]:
+        out = []
+        for opt in (self.opt1, self.opt2):
+            out += [opt.flat, opt.m, opt.v, opt.vmax, opt.step_dev, opt.bc_dev]
+        for net in (self.net1, self.net2):
+            out += list(net.buffers())
+        return out
+
+    def _capture(self, key, x, t1, t2, augs, rate):
+        """Warm up eagerly (lazy initialisation, NCCL communicators, allocator), restore the training state the
+        warm-up step changed, then record the step into a CUDA graph on static input buffers."""
+        new = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        static = dict(x=tuple(new(t) for t in x), t1=new(t1), t2=new(t2), augs=[tuple(new(t) for t in a) for a in augs])
+        self._fill_static(static, x, t1, t2, augs)
+        state = self._state_tensors()
+        saved = [t.clone() for t in state]
+        host = (self.opt1.t, self.opt2.t, self.steps)
+        torch.cuda.synchronize(self.device)
+        self._step_eager(static["x"], static["t1"], static["t2"], static["augs"], rate)
+        torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for t, s in zip(state, saved):
+                t.copy_(s)
+        self.opt1.t, self.opt2.t, self.steps = host
+        for net in (self.net1, self.net2):
+            net._weights = None                       # force the weight preparation INTO the graph
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        n0 = lib.aide_launch_count()
+        with torch.cuda.graph(graph):
+            out = self._step_eager(static["x"], static["t1"], static["t2"], static["augs"], rate)
+        n_kernels = lib.aide_launch_count() - n0               # kernel nodes of this library recorded in the graph
+        self.opt1.t, self.opt2.t, self.steps = host          # capture records, it does not execute
+        self._graphs[key] = (graph, static, out, n_kernels)
+        return self._graphs[key]
+
+    @staticmethod
+    def _fill_static(static, x, t1, t2, augs):
+        for d, s in zip(static["x"], x):
+            d.copy_(s, non_blocking=True)
+        static["t1"].copy_(t1, non_blocking=True)
+        static["t2"].copy_(t2, non_blocking=True)
+        for da, sa in zip(static["augs"], augs):
+            for d, s in zip(da, sa):
+                d.copy_(s, non_blocking=True)
+
     def broadcast_parameters(self, src: int = 0) -> None:
         """Make every rank start from rank `src`'s weights (the reference's DataParallel replicates rank 0)."""
         if self.world > 1:
@@ -127,8 +183,32 @@ class AideTrainer:
             me["tape"] = None
 
     def step(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float) -> Dict[str, torch.Tensor]:
-        """x / augs[i]: a tensor [B,3,H,W] (unet) or a pair of them (fuseunet), on the device.  t1, t2: [B,H,W] int64.
-        Returns device scalars loss1, loss2, dice1, dice2 (Dice_fn batch sums) and the index vectors; no host sync."""
+        """x / augs[i]: a tensor [B,3,H,W] (unet) or a pair of them (fuseunet), on the device OR in (pinned) host
+        memory.  t1, t2: [B,H,W] int64.  Returns device scalars loss1, loss2, dice1, dice2 (Dice_fn batch sums), the
+        index vectors and both logits; no host sync.  With cuda_graph=True the returned tensors are the graph's
+        static outputs: they are overwritten by the next step()."""
+        xs = self._inputs(x)
+        augs = [self._inputs(a) for a in augs]
+        if not self.cuda_graph:
+            dev = self.device
+            mv = lambda t: t if t.is_cuda else t.to(dev, non_blocking=True)
+            return self._step_eager(tuple(mv(t) for t in xs), mv(t1), mv(t2), [tuple(mv(t) for t in a) for a in augs], rate)
+        key = (tuple(xs[0].shape), len(xs), len(augs), float(rate), self.flavour, self.world)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, xs, t1, t2, augs, rate)
+        graph, static, out, n_kernels = entry
+        self._fill_static(static, xs, t1, t2, augs)            # D2D, or H2D straight into the graph's inputs
+        graph.replay()
+        self.graph_launches += n_kernels
+        self.steps += 1
+        self.opt1.t += 1
+        self.opt2.t += 1
+        for net in (self.net1, self.net2):                      # operand-format weight planes live in the graph's pool
+            net._weights = None
+        return out
+
+    def _step_eager(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float) -> Dict[str, torch.Tensor]:
         xs = self._inputs(x)
         m1: Dict = {}
         m2: Dict = {}
@@ -162,18 +242,11 @@ class AideTrainer:
         """End-to-end form: `host_batch` holds pinned CPU tensors (x: tuple, t1, t2, augs: list of tuples).
         Copies them to the device (async, current stream), runs the step and reads the two losses and Dice sums
         back to the host.  Returns (dict of python floats, h2d bytes, d2h bytes)."""
-        dev = self.device
         h2d = 0
-
-        def up(t):
-            nonlocal h2d
+        for t in list(self._inputs(host_batch["x"])) + [host_batch["t1"], host_batch["t2"]] + \
+                [t for a in host_batch["augs"] for t in self._inputs(a)]:
             h2d += t.numel() * t.element_size()
-            return t.to(dev, non_blocking=True)
-
-        xs = tuple(up(t) for t in self._inputs(host_batch["x"]))
-        t1, t2 = up(host_batch["t1"]), up(host_batch["t2"])
-        augs = [tuple(up(t) for t in self._inputs(a)) for a in host_batch["augs"]]
-        out = self.step(xs, t1, t2, augs, rate)
+        out = self.step(host_batch["x"], host_batch["t1"], host_batch["t2"], host_batch["augs"], rate)
         res = torch.stack([out["loss1"], out["loss2"], out["dice1"], out["dice2"]]).to("cpu")   # synchronising D2H
         vals = res.tolist()
         return dict(loss1=vals[0], loss2=vals[1], dice1=vals[2], dice2=vals[3]), h2d, res.numel() * 4

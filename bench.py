@@ -129,8 +129,10 @@ def timed_steps(fn, steps, world, device):
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     for i in range(steps):
         fn(i)
+    timed_steps.host_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)     # CPU time to ENQUEUE one step
     e1.record()
     torch.cuda.synchronize(device)
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -163,7 +165,7 @@ def conv_roofline(mode, B, S, device, peaks):
         bias = torch.zeros(cout, device=device)
         w0, w1, keep = ops.weight_prep(w, fmt)
         z = torch.empty((B, hw, hw, cout), dtype=torch.float32, device=device)
-        nrows = A.lib.aide_conv3x3_stat_rows(fmt, B, hw, hw)
+        nrows = A.lib.aide_conv3x3_stat_rows(fmt, cin, cout, B, hw, hw)
         part = torch.empty((nrows, 2, cout), dtype=torch.float32, device=device)
         st = torch.cuda.current_stream().cuda_stream
 
@@ -308,9 +310,10 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = A.lib.aide_launch_count()
+    l0 = A.lib.aide_launch_count() + tr.graph_launches
     ms = timed_steps(dev_step, K, world, device)
-    launches = A.lib.aide_launch_count() - l0
+    launches = A.lib.aide_launch_count() + tr.graph_launches - l0
+    host_enqueue_ms = timed_steps.host_ms
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 
@@ -338,10 +341,12 @@ def main():
                                "co-teaching selection, Adam-amsgrad (BASELINE.json configs[2]; configs[3] for N>1)",
                    "mode": args.mode, "per_gpu_batch": B, "global_batch": B * world, "img_size": S, "modalities": 2,
                    "aug_views": 4, "rate": 0.25, "parallelism": f"dp{world}",
+                   "cuda_graph": bool(tr.cuda_graph),
                    "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; "
                          f"{n_pool} distinct resident batches alternate",
                    "algorithmic_gflop_per_slice": round((3 + 4) * 2 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2, 1)},
         "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
         "clocks": clocks, "e2e": e2e,
     }
     out["algorithmic_tflops"] = round(value * out["config"]["algorithmic_gflop_per_slice"] / 1e3, 1)

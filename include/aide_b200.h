@@ -59,9 +59,10 @@ int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
  * Also emits per-tile BatchNorm partial statistics (sum z, sum z^2 per channel) when stat_partial
  * != NULL: layout [rows][2][cout] fp32 with rows = aide_conv3x3_stat_rows(...).
  * The same entry point computes dgrad when given dgrad-prepared weights (bias = stats = NULL).
- * F32 -> CUDA-core kernel; TF32X2/BF16 -> tcgen05 implicit GEMM fed by TMA (needs cin%32==0
+ * F32 -> CUDA-core kernels (a dedicated HBM-bound kernel for the networks' first layer, cin == 3 and cout in
+ * {32, 64}; a generic tiled kernel otherwise); TF32X2/BF16 -> tcgen05 implicit GEMM fed by TMA (needs cin%32==0
  * (TF32X2) or cin%32==0 (BF16), cout%32==0; other shapes -> error). */
-int aide_conv3x3_stat_rows(int fmt, int N, int H, int W);
+int aide_conv3x3_stat_rows(int fmt, int cin, int cout, int N, int H, int W);
 int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
                      const void* w_p0, const void* w_p1, const float* bias,
                      float* z, int z_ctot, int z_coff, int cout, int N, int H, int W,
@@ -78,7 +79,7 @@ int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, 
  *   training: mean/biased var -> scale,shift ; running_mean/var updated with momentum, unbiased var
  *   eval    : scale,shift from running stats (stat_partial ignored)
  * scale_shift: [2][C] fp32 (y = scale*z + shift); mean_rstd: [2][C] fp32 (saved for backward). */
-int aide_bn_finalize(const float* stat_partial, int rows, int C, double count,
+int aide_bn_finalize(float* stat_partial /* folded in place: consumed */, int rows, int C, double count,
                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float momentum, float eps, int training,
                      float* scale_shift, float* mean_rstd, void* stream);
@@ -166,6 +167,12 @@ int aide_coteach_select(const float* pre_other, const float* loss_img, const dou
 /* ---- optimiser ("next" row f1): torch.optim.Adam(amsgrad=True) on a flat fp32 buffer ------------- */
 int aide_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, size_t n,
                       float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+/* Same update with the step count kept ON THE DEVICE: *step_counter is incremented and the two bias corrections are
+ * written to bc_scratch[2] by a one-thread prelude kernel -- no host scalar changes between steps, so a captured
+ * CUDA graph of the whole training step can be replayed. */
+int aide_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, size_t n,
+                          float lr, float beta1, float beta2, float eps, int* step_counter, float* bc_scratch,
+                          float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

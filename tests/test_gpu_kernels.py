@@ -62,6 +62,41 @@ def test_conv3x3_first_layer_cin3(dev):
     assert relmax(dw, ref) < 3e-5
 
 
+@pytest.mark.parametrize("cout", [32, 64])
+@pytest.mark.parametrize("shape", [(2, 20, 44), (1, 16, 16), (3, 33, 7), (2, 64, 64)])
+def test_conv3x3_first_layer_dedicated_kernels(dev, cout, shape):
+    """cin == 3 -> conv_first.cu (forward + BN partial statistics + weight gradient), ragged tiles included."""
+    from aide_b200 import ops
+    N, H, W = shape
+    x, w, b = rnd(N, 3, H, W, seed=1), rnd(cout, 3, 3, 3, seed=2, scale=0.2), rnd(cout, seed=3)
+    ref = F.conv2d(x, w, b, padding=1)
+    a = ops.from_nchw(x.to(dev), 0)
+    z, part = ops.conv3x3(a, w.to(dev), b.to(dev), stats=True)
+    got = ops.nhwc_to_nchw(z)
+    assert relmax(got, ref) < 2e-6
+    s = part.sum(0).cpu()
+    assert relmax(s[0], ref.sum((0, 2, 3))) < 1e-5 and relmax(s[1], (ref ** 2).sum((0, 2, 3))) < 1e-5
+    dz = rnd(N, cout, H, W, seed=5)
+    dw = ops.conv3x3_wgrad(a, ops.from_nchw(dz.to(dev), 0))
+    assert relmax(dw, torch.nn.grad.conv2d_weight(x, w.shape, dz, padding=1)) < 1e-5
+
+
+def test_bn_finalize_folds_many_rows(dev):
+    """> 128 partial rows take the two-stage (fold in place, then finalize) path; same statistics either way."""
+    from aide_b200 import ops
+    C, rows = 96, 1000
+    part = torch.randn(rows, 2, C, generator=torch.Generator().manual_seed(3)).abs() + 0.1
+    part[:, 1] += 50.0                                   # keep the variance positive
+    count = 4096.0
+    gamma, beta = rnd(C, seed=1).abs() + 0.5, rnd(C, seed=2)
+    s = part.double().sum(0)
+    mean = s[0] / count
+    var = s[1] / count - mean ** 2
+    ss, mr = ops.bn_finalize(part.to(dev), count, gamma.to(dev), beta.to(dev), None, None, True)
+    assert relmax(mr[0], mean) < 1e-6 and relmax(mr[1], 1.0 / torch.sqrt(var + 1e-5)) < 1e-6
+    assert relmax(ss[0], gamma.double() / torch.sqrt(var + 1e-5)) < 1e-6
+
+
 @pytest.mark.parametrize("fmt", [0, 1, 2])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_conv3x3_dgrad_wgrad(dev, fmt, shape):

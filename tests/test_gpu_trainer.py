@@ -1,0 +1,106 @@
+"""GPU: the fused AIDE training step (aide_b200.trainer.AideTrainer) against the oracle's restatement of
+train_files/trainchaos_proposed_30cases1labeled.py:263-325, eager launches vs the captured CUDA graph."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def batch(oracle, B, S, seed):
+    (x1, x2), t1, t2, augs = oracle.synthetic_batch(B, S, S, seed=seed, n_aug=4)
+    return (x1, x2), t1, t2, augs
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_step_vs_oracle(oracle, graph):
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+    torch.manual_seed(2)
+    p1 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
+    p2 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
+    st1, st2 = {}, {}
+    d = lambda t: t.to(dev)
+    for step in (1, 2):
+        x, t1, t2, augs = batch(oracle, B, S, 500 + step)
+        r = oracle.aide_step(oracle.fuseunet_forward, p1, p2, x, augs, t1, t2, 0.25)
+        m = tr.step(tuple(d(t) for t in x), d(t1), d(t2), [tuple(d(t) for t in a) for a in augs], 0.25)
+        tol = 2e-5 if step == 1 else 2e-3          # step 2 starts from Adam-updated weights (sign-like first update)
+        assert abs(m["loss1"].item() - r["loss1"].item()) < tol * max(1, abs(r["loss1"].item())), step
+        assert abs(m["loss2"].item() - r["loss2"].item()) < tol * max(1, abs(r["loss2"].item())), step
+        if step == 1:
+            assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"])
+            assert abs(m["dice1"].item() - r["dice1"].item()) < 4e-3
+        oracle.adam_amsgrad_step(p1, r["grads1"], st1, step)
+        oracle.adam_amsgrad_step(p2, r["grads2"], st2, step)
+    # parameters after two Adam-amsgrad updates: the first update is lr * sign(g), so elements whose gradient is at
+    # rounding level may differ by 2 * lr; everything else follows the oracle
+    sd = tr.net1.state_dict()
+    for k in ("last_conv1.weight", "up_block4.block.bn2.weight", "modal1_downblock3.block.conv1.weight"):
+        diff = (sd[k].cpu() - p1[k].detach()).abs()
+        assert diff.max().item() <= 4.1e-4 and diff.median().item() < 2e-5, (k, diff.max().item(), diff.median().item())
+    assert int(sd["modal1_downblock1.block.bn1.num_batches_tracked"]) == 10          # 5 train-mode forwards per step
+    assert tr.opt1.step_dev.item() == 2 and tr.steps == 2
+
+
+def test_graph_replay_equals_eager_launches(oracle):
+    """Same seeds, same batches: the captured graph and the eager launch sequence are the same kernels in the same
+    order on deterministic reductions, so the trained weights must be bit-identical."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 3, 32
+    tr_e = AideTrainer("fuseunet", mode="parity", device=dev, seed=5, cuda_graph=False)
+    tr_g = AideTrainer("fuseunet", mode="parity", device=dev, seed=5, cuda_graph=True)
+    assert torch.equal(tr_e.opt1.flat, tr_g.opt1.flat)
+    d = lambda t: t.to(dev)
+    for step in range(3):
+        x, t1, t2, augs = batch(oracle, B, S, 700 + step)
+        args = (tuple(d(t) for t in x), d(t1), d(t2), [tuple(d(t) for t in a) for a in augs], 0.5)
+        me = tr_e.step(*args)
+        mg = tr_g.step(*args)
+        assert torch.equal(me["loss1"], mg["loss1"]) and torch.equal(me["loss2"], mg["loss2"]), step
+    for a, b in ((tr_e.opt1, tr_g.opt1), (tr_e.opt2, tr_g.opt2)):
+        assert torch.equal(a.flat, b.flat) and torch.equal(a.vmax, b.vmax)
+    for (ka, va), (kb, vb) in zip(tr_e.net2.state_dict().items(), tr_g.net2.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    # host buffers go straight into the graph's static inputs
+    x, t1, t2, augs = batch(oracle, B, S, 800)
+    host = dict(x=tuple(t.pin_memory() for t in x), t1=t1.pin_memory(), t2=t2.pin_memory(),
+                augs=[tuple(t.pin_memory() for t in a) for a in augs])
+    vals, h2d, d2h = tr_g.step_from_host(host, 0.5)
+    ve = tr_e.step(tuple(d(t) for t in x), d(t1), d(t2), [tuple(d(t) for t in a) for a in augs], 0.5)
+    assert vals["loss1"] == ve["loss1"].item() and h2d == sum(t.numel() * t.element_size() for t in
+                                                               list(x) + [t1, t2] + [u for a in augs for u in a])
+
+
+def test_kidney_flavour_and_unet(oracle):
+    """Single-modal UNet pair, eval-mode augmented forwards, sharpen = pow(1/T) (trainkidney_proposed_mask1.py:267-333)."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 32
+    tr = AideTrainer("unet", mode="parity", device=dev, seed=2, flavour="kidney", temperature=2.0, cuda_graph=False)
+    torch.manual_seed(2)
+    p1 = oracle.clone_params(oracle.init_unet(2), requires_grad=True)
+    p2 = oracle.clone_params(oracle.init_unet(2), requires_grad=True)
+    (x1, _), t1, t2, augs = oracle.synthetic_batch(B, S, S, seed=42, n_aug=4)
+    r = oracle.aide_step(oracle.unet_forward, p1, p2, (x1,), [(a[0],) for a in augs], t1, t2, 0.25,
+                         temperature=2.0, flavour="kidney")
+    d = lambda t: t.to(dev)
+    m = tr.step(d(x1), d(t1), d(t2), [d(a[0]) for a in augs], 0.25)
+    assert abs(m["loss1"].item() - r["loss1"].item()) < 5e-5 and abs(m["loss2"].item() - r["loss2"].item()) < 5e-5
+    assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"])
+    assert int(tr.net1.state_dict()["down_block1.block.bn1.num_batches_tracked"]) == 1     # eval-mode aug forwards
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_step_equals_mean_of_shard_gradients(tmp_path):
+    """DDP semantics on 2 GPUs: launched as a subprocess under torchrun; see tools/ddp_check.py."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631",
+                          os.path.join(root, "tools", "ddp_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
