@@ -11,7 +11,7 @@ see INTEGRATION.md):
 Importing this package loads aide_b200/libaide_b200.so and raises ImportError if it has not been
 built: there is no CPU or PyTorch fallback for the compute path.
 """
-from ._lib import AideError, FMT_BF16, FMT_F32, FMT_TF32X2, LIB_PATH, lib  # noqa: F401
+from ._lib import AideError, FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, LIB_PATH, lib  # noqa: F401
 from .engine import MODES, default_mode  # noqa: F401
 from .nets import UNet, fuseunet  # noqa: F401
 from .losses import (CEDiceLoss, CEMDiceLoss, CEMDiceLossImage, CrossEntropyLoss2d, Dice_Loss, DiceLoss,  # noqa: F401

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaide_b200.so")
 
-FMT_F32, FMT_TF32X2, FMT_BF16 = 0, 1, 2
+FMT_F32, FMT_TF32X2, FMT_BF16, FMT_F16X2 = 0, 1, 2, 3
 
 _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -60,6 +61,20 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
+// ---- AIDE_FMT_F16X2: x * 2^s = hi + lo with hi = fp16(x * 2^s), lo = fp16(x * 2^s - hi) ------------------------
+// Two fp16 planes carry 22 significant bits; three kind::f16 MMAs (hi*hi + hi*lo + lo*hi) reproduce the fp32
+// product at TWICE the tcgen05 rate of kind::tf32 and with half the operand bytes of TF32X2.  fp16 has a narrow
+// exponent range, so every tensor is stored pre-scaled by a power of two (exact): activations by 2^8 (full 22-bit
+// precision for |x| in [5e-4, 255], absolute error <= 1e-10 below), weights by 2^12, gradients by a per-tensor
+// power of two chosen on the device.  Conversions saturate at +-65504 instead of producing inf.
+constexpr float kF16ActScale = 256.f;
+constexpr float kF16WScale = 4096.f;
+__device__ __forceinline__ void f16_split(float xs, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(xs, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  lo = __float2half_rn(c - __half2float(hi));
+}
+
 // Load/store 4 consecutive channels (c % 4 == 0, view channel offsets are multiples of 4).
 template <int FMT>
 __device__ __forceinline__ float4 ld4(const void* p0, const void* p1, size_t e) {
@@ -69,6 +84,15 @@ __device__ __forceinline__ float4 ld4(const void* p0, const void* p1, size_t e) 
     float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p0) + e);
     float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p1) + e);
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  } else if constexpr (FMT == AIDE_FMT_F16X2) {
+    const uint2 rh = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p0) + e);
+    const uint2 rl = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p1) + e);
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&rh.x));
+    const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&rh.y));
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&rl.x));
+    const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&rl.y));
+    constexpr float inv = 1.0f / kF16ActScale;
+    return make_float4((h0.x + l0.x) * inv, (h0.y + l0.y) * inv, (h1.x + l1.x) * inv, (h1.y + l1.y) * inv);
   } else {
     uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p0) + e);
     __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&r.x);
@@ -87,6 +111,14 @@ __device__ __forceinline__ void st4(void* p0, void* p1, size_t e, float4 v) {
     float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p0) + e) = h;
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p1) + e) = l;
+  } else if constexpr (FMT == AIDE_FMT_F16X2) {
+    __half h[4], l[4];
+    f16_split(v.x * kF16ActScale, h[0], l[0]);
+    f16_split(v.y * kF16ActScale, h[1], l[1]);
+    f16_split(v.z * kF16ActScale, h[2], l[2]);
+    f16_split(v.w * kF16ActScale, h[3], l[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p0) + e) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p1) + e) = *reinterpret_cast<const uint2*>(l);
   } else {
     __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
     __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
@@ -103,6 +135,9 @@ __device__ __forceinline__ float ld1(const void* p0, const void* p1, size_t e) {
     return reinterpret_cast<const float*>(p0)[e];
   } else if constexpr (FMT == AIDE_FMT_TF32X2) {
     return reinterpret_cast<const float*>(p0)[e] + reinterpret_cast<const float*>(p1)[e];
+  } else if constexpr (FMT == AIDE_FMT_F16X2) {
+    return (__half2float(reinterpret_cast<const __half*>(p0)[e]) + __half2float(reinterpret_cast<const __half*>(p1)[e])) *
+           (1.0f / kF16ActScale);
   } else {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p0)[e]);
   }
@@ -115,13 +150,19 @@ __device__ __forceinline__ void st1(void* p0, void* p1, size_t e, float v) {
     float h = tf32_rn(v);
     reinterpret_cast<float*>(p0)[e] = h;
     reinterpret_cast<float*>(p1)[e] = v - h;
+  } else if constexpr (FMT == AIDE_FMT_F16X2) {
+    __half h, l;
+    f16_split(v * kF16ActScale, h, l);
+    reinterpret_cast<__half*>(p0)[e] = h;
+    reinterpret_cast<__half*>(p1)[e] = l;
   } else {
     reinterpret_cast<__nv_bfloat16*>(p0)[e] = __float2bfloat16_rn(v);
   }
 }
 
-inline int fmt_elem_bytes(int fmt) { return fmt == AIDE_FMT_BF16 ? 2 : 4; }
-inline bool fmt_valid(int fmt) { return fmt >= 0 && fmt <= 2; }
+inline int fmt_elem_bytes(int fmt) { return (fmt == AIDE_FMT_BF16 || fmt == AIDE_FMT_F16X2) ? 2 : 4; }
+inline int fmt_planes(int fmt) { return (fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_F16X2) ? 2 : 1; }
+inline bool fmt_valid(int fmt) { return fmt >= 0 && fmt <= 3; }
 
 // dispatch a templated launcher on the runtime format
 #define AIDE_DISPATCH_FMT(fmt, ...)                                   \
@@ -129,6 +170,7 @@ inline bool fmt_valid(int fmt) { return fmt >= 0 && fmt <= 2; }
     case AIDE_FMT_F32: { constexpr int FMT = AIDE_FMT_F32; __VA_ARGS__; break; }       \
     case AIDE_FMT_TF32X2: { constexpr int FMT = AIDE_FMT_TF32X2; __VA_ARGS__; break; } \
     case AIDE_FMT_BF16: { constexpr int FMT = AIDE_FMT_BF16; __VA_ARGS__; break; }     \
+    case AIDE_FMT_F16X2: { constexpr int FMT = AIDE_FMT_F16X2; __VA_ARGS__; break; }   \
     default: ::aide::set_error("bad operand format %d", fmt); return 1;                 \
   }
 

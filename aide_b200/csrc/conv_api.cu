@@ -13,7 +13,7 @@ int tc_stat_rows(int N, int H, int W);
 bool tc_shape_ok(int fmt, int cin, int cout);
 int tc_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
                const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
-               cudaStream_t st);
+               float out_scale, const float* out_scale_ptr, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
 int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
              int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st);
@@ -49,13 +49,16 @@ extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int
     return simt_conv3x3(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin,
                         reinterpret_cast<const float*>(w_p0), bias, z, z_ctot, z_coff, cout, N, H, W, stat_partial,
                         as_stream(stream));
-  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16, "conv3x3_fwd: bad operand format %d", fmt);
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16 || fmt == AIDE_FMT_F16X2,
+               "conv3x3_fwd: bad operand format %d", fmt);
   AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout),
                "conv3x3_fwd: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0 (got %d -> %d); use AIDE_FMT_F32",
                cin, cout);
   AIDE_REQUIRE(z_ctot % 4 == 0 && z_coff % 4 == 0, "conv3x3_fwd: output view must be 16-byte aligned");
+  // F16X2 operands are stored pre-scaled: activations by 2^8, weights by 2^12 (common.cuh)
+  const float out_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / (256.0f * 4096.0f) : 1.0f;
   return tc_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
-                    stat_partial, as_stream(stream));
+                    stat_partial, out_scale, nullptr, as_stream(stream));
 }
 
 extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W) {
@@ -76,7 +79,8 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
   if (fmt == AIDE_FMT_F32)
     return simt_wgrad(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin, reinterpret_cast<const float*>(dz_p0),
                       cout, N, H, W, reinterpret_cast<float*>(workspace), workspace_bytes, dw_oihw, as_stream(stream));
-  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16, "conv3x3_wgrad: bad operand format %d", fmt);
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16,
+               "conv3x3_wgrad: operand format %d not supported (F16X2 is forward-only so far)", fmt);
   AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout), "conv3x3_wgrad: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0");
   return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes,
                   dw_oihw, as_stream(stream));

@@ -43,7 +43,8 @@ static EncodeTiledFn get_encode_fn() {
 
 constexpr int kSwizzle128Atom32 = 1128;
 
-static int encode_tmap(CUtensorMap* m, bool bf16, int rank, const void* base, const cuuint64_t* dims,
+// dtype: 0 = fp32 (also tf32), 1 = bf16, 2 = fp16
+static int encode_tmap(CUtensorMap* m, int dtype, int rank, const void* base, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   AIDE_REQUIRE(fn, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
@@ -54,7 +55,10 @@ static int encode_tmap(CUtensorMap* m, bool bf16, int rank, const void* base, co
                           : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+  const CUtensorMapDataType dt = dtype == 1   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(m, dt, (cuuint32_t)rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AIDE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d box %u,%u swizzle %d)", (int)r,
@@ -63,31 +67,31 @@ static int encode_tmap(CUtensorMap* m, bool bf16, int rank, const void* base, co
 }
 
 // NHWC activation view as a 4-D tensor (C_view, W, H, N); box = (box_c, box_w, box_h, 1)
-static int act_tmap(CUtensorMap* m, bool bf16, const void* plane, int ctot, int coff, int C, int N, int H, int W,
-                    int box_c, int box_w, int box_h, int swizzle_bytes) {
-  const size_t es = bf16 ? 2 : 4;
+int act_tmap(CUtensorMap* m, int dtype, const void* plane, int ctot, int coff, int C, int N, int H, int W,
+             int box_c, int box_w, int box_h, int swizzle_bytes) {
+  const size_t es = dtype ? 2 : 4;
   const char* base = reinterpret_cast<const char*>(plane) + (size_t)coff * es;
   AIDE_REQUIRE(((uintptr_t)base % 16) == 0 && ((size_t)ctot * es) % 16 == 0,
                "activation view is not 16-byte aligned (ctot=%d coff=%d)", ctot, coff);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t str[3] = {(cuuint64_t)ctot * es, (cuuint64_t)W * ctot * es, (cuuint64_t)H * W * ctot * es};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  return encode_tmap(m, bf16, 4, base, dims, str, box, swizzle_bytes);
+  return encode_tmap(m, dtype, 4, base, dims, str, box, swizzle_bytes);
 }
 
 // weights [rows][kdim] row-major as a 2-D tensor (kdim, rows); box = (box_k, box_rows)
-static int mat_tmap(CUtensorMap* m, bool bf16, const void* plane, int rows, int kdim, int box_k, int box_rows,
-                    int swizzle_bytes) {
-  const size_t es = bf16 ? 2 : 4;
+int mat_tmap(CUtensorMap* m, int dtype, const void* plane, int rows, int kdim, int box_k, int box_rows,
+             int swizzle_bytes) {
+  const size_t es = dtype ? 2 : 4;
   AIDE_REQUIRE(((uintptr_t)plane % 16) == 0 && ((size_t)kdim * es) % 16 == 0, "weight plane is not 16-byte aligned");
   cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
   cuuint64_t str[1] = {(cuuint64_t)kdim * es};
   cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
-  return encode_tmap(m, bf16, 2, plane, dims, str, box, swizzle_bytes);
+  return encode_tmap(m, dtype, 2, plane, dims, str, box, swizzle_bytes);
 }
 
 // pixel tile TW x TH (powers of two, TW*TH = npix) minimising the number of tiles covering H x W
-static void pick_tile(int H, int W, int npix, int* TW, int* TH) {
+void pick_tile(int H, int W, int npix, int* TW, int* TH) {
   long long best = -1;
   for (int tw = npix; tw >= 1; tw >>= 1) {
     int th = npix / tw;
@@ -100,7 +104,7 @@ static void pick_tile(int H, int W, int npix, int* TW, int* TH) {
     }
   }
 }
-static int ilog2(int v) {
+int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
   return l;
@@ -112,204 +116,6 @@ static uint32_t tmem_cols(int n) {
 }
 
 constexpr int kThreads = 192;
-
-// ================================================================================================
-// forward / dgrad
-// ================================================================================================
-struct FwdParams {
-  CUtensorMap tmA0, tmA1, tmB0, tmB1;
-  float* z;
-  const float* bias;
-  float* stat_partial;
-  int z_ctot, z_coff, cout, cin, H, W;
-  int TW, TH, tw_log2, tiles_w, tiles_h;
-  int BN, kc, n_cchunks, row_bytes, stages;
-  int a_plane_bytes, b_plane_bytes, stage_bytes, data_bytes;
-};
-
-template <bool TF32, bool PARITY>
-__global__ void __launch_bounds__(kThreads) conv3x3_tc_kernel(const __grid_constant__ FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - raw);
-  constexpr int NPL = PARITY ? 2 : 1;
-  // tcgen05.mma truncates (rounds toward zero) when it adds into the TMEM accumulator, so the error of one
-  // accumulation chain grows linearly with its length (tools/accum_probe.py: 1.7e-5 rms at K = 9216 vs 1e-6 for
-  // fp32 FMA chains).  Parity mode therefore rotates the K blocks over NACC independent accumulators and adds
-  // them with round-to-nearest fp32 in the epilogue.
-  constexpr int NACC = PARITY ? 4 : 1;
-  const int S = p.stages;
-  const uint32_t bar_base = base + p.data_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
-  const uint32_t slot_addr = bar_base + 8u * (2 * S + 1);
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.data_bytes + 8 * (2 * S + 1));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x;
-  const int tw_i = m_tile % p.tiles_w, th_i = (m_tile / p.tiles_w) % p.tiles_h, n_img = m_tile / (p.tiles_w * p.tiles_h);
-  const int h0 = th_i * p.TH, w0 = tw_i * p.TW, n0 = blockIdx.y * p.BN;
-  const int num_kb = 9 * p.n_cchunks;
-  const uint32_t ncols_need = (uint32_t)(NACC * p.BN);
-  const uint32_t ncols = ncols_need <= 32 ? 32u : ncols_need <= 64 ? 64u : ncols_need <= 128 ? 128u : ncols_need <= 256 ? 256u : 512u;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA0);
-    tma_prefetch_desc(&p.tmB0);
-    if (PARITY) {
-      tma_prefetch_desc(&p.tmA1);
-      tma_prefetch_desc(&p.tmB1);
-    }
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(slot_addr, ncols);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *slot_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = NPL * (p.a_plane_bytes + p.b_plane_bytes);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S, ph = (kb / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-        const int tap = kb / p.n_cchunks, cc = kb - tap * p.n_cchunks;
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const uint32_t a_dst = base + s * p.stage_bytes;
-        const uint32_t b_dst = a_dst + NPL * p.a_plane_bytes;
-        tma_load_4d(a_dst, &p.tmA0, full_bar(s), cc * p.kc, w0 + dx, h0 + dy, n_img);
-        tma_load_2d(b_dst, &p.tmB0, full_bar(s), tap * p.cin + cc * p.kc, n0);
-        if (PARITY) {
-          tma_load_4d(a_dst + p.a_plane_bytes, &p.tmA1, full_bar(s), cc * p.kc, w0 + dx, h0 + dy, n_img);
-          tma_load_2d(b_dst + p.b_plane_bytes, &p.tmB1, full_bar(s), tap * p.cin + cc * p.kc, n0);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, 0u, 128u, (uint32_t)p.BN);
-      const uint32_t layout = p.row_bytes == 128 ? 2u : 4u;
-      const uint32_t sbo = 8u * p.row_bytes;
-      const int nks = p.row_bytes / 32;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S, ph = (kb / S) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after_sync();
-        const uint32_t a0 = base + s * p.stage_bytes;
-        const uint32_t b0 = a0 + NPL * p.a_plane_bytes;
-        const uint32_t acc = tmem_base + (uint32_t)((kb % NACC) * p.BN);
-        uint32_t accum = kb >= NACC ? 1u : 0u;
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t ko = ks * 32;
-          if (PARITY) {
-            umma<TF32>(acc, make_smem_desc(a0 + p.a_plane_bytes + ko, 16, sbo, layout),
-                       make_smem_desc(b0 + ko, 16, sbo, layout), idesc, accum);
-            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout),
-                       make_smem_desc(b0 + p.b_plane_bytes + ko, 16, sbo, layout), idesc, 1u);
-            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
-                       idesc, 1u);
-          } else {
-            umma<TF32>(acc, make_smem_desc(a0 + ko, 16, sbo, layout), make_smem_desc(b0 + ko, 16, sbo, layout),
-                       idesc, accum);
-          }
-          accum = 1u;
-        }
-        umma_commit(empty_bar(s));
-      }
-      umma_commit(tmem_full_bar);
-    }
-    __syncwarp();
-  } else {
-    // ---------------- epilogue: TMEM -> registers -> smem staging -> coalesced global + BN partial stats
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
-    const int hh = h0 + (row >> p.tw_log2), ww = w0 + (row & (p.TW - 1));
-    const bool valid = hh < p.H && ww < p.W;
-    float* stg = reinterpret_cast<float*>(sm);
-    const int pitch = p.BN + 4;
-    for (int ch = 0; ch < p.BN / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-      tmem_ld_wait();
-      if constexpr (NACC > 1) {
-        // pairwise (a0 + a1) + (a2 + a3), round-to-nearest fp32
-        uint32_t r1[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + ch * 32), r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r1[j]));
-        uint32_t r2[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.BN + ch * 32), r1);
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * p.BN + ch * 32), r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          r[j] = __float_as_uint(__uint_as_float(r[j]) + (__uint_as_float(r1[j]) + __uint_as_float(r2[j])));
-      }
-      float* dst = stg + (size_t)row * pitch + ch * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3]));
-          if (p.bias) {
-            const float* bp = p.bias + n0 + ch * 32 + j;  // scalar loads: parameter storage may be only 4B-aligned
-            v.x += __ldg(bp); v.y += __ldg(bp + 1); v.z += __ldg(bp + 2); v.w += __ldg(bp + 3);
-          }
-        }
-        *reinterpret_cast<float4*>(dst + j) = v;
-      }
-    }
-    tc_fence_before_sync();
-    named_bar_sync(1, 128);
-    const int nq = p.BN >> 2;
-    for (int i = et; i < 128 * nq; i += 128) {
-      const int r = i / nq, c4 = i - r * nq;
-      const int h2 = h0 + (r >> p.tw_log2), w2 = w0 + (r & (p.TW - 1));
-      if (h2 < p.H && w2 < p.W) {
-        const float4 v = *reinterpret_cast<const float4*>(stg + (size_t)r * pitch + c4 * 4);
-        const size_t pix = ((size_t)n_img * p.H + h2) * p.W + w2;
-        *reinterpret_cast<float4*>(p.z + pix * p.z_ctot + p.z_coff + n0 + c4 * 4) = v;
-      }
-    }
-    if (p.stat_partial) {
-      for (int col = et; col < p.BN; col += 128) {
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 128; ++r) {
-          const float v = stg[(size_t)r * pitch + col];
-          s1 += v;
-          s2 = fmaf(v, v, s2);
-        }
-        p.stat_partial[((size_t)m_tile * 2 + 0) * p.cout + n0 + col] = s1;
-        p.stat_partial[((size_t)m_tile * 2 + 1) * p.cout + n0 + col] = s2;
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, ncols);
-  }
-}
 
 // ================================================================================================
 // wgrad
@@ -478,7 +284,7 @@ constexpr int kSmemBudget1 = 200 * 1024;  // one CTA per SM
 
 // opt in to > 48 KB dynamic shared memory: once per (kernel, device); not a stream operation
 template <typename K>
-static int set_smem(K kernel, int bytes) {
+int set_smem(K kernel, int bytes) {
   struct Seen { const void* fn; int dev; };
   static thread_local Seen seen[64];
   static thread_local int n_seen = 0;
@@ -489,68 +295,6 @@ static int set_smem(K kernel, int bytes) {
     if (seen[i].fn == fn && seen[i].dev == dev) return 0;
   AIDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if (n_seen < 64) seen[n_seen++] = Seen{fn, dev};
-  return 0;
-}
-
-int tc_stat_rows(int N, int H, int W) {
-  int TW = 128, TH = 1;
-  pick_tile(H, W, 128, &TW, &TH);
-  return N * ceil_div(W, TW) * ceil_div(H, TH);
-}
-
-bool tc_shape_ok(int fmt, int cin, int cout) {
-  if (fmt != AIDE_FMT_TF32X2 && fmt != AIDE_FMT_BF16) return false;
-  return cin % 32 == 0 && cout % 32 == 0 && cin >= 32 && cout >= 32;
-}
-
-int tc_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
-               const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
-               cudaStream_t st) {
-  const bool bf16 = fmt == AIDE_FMT_BF16;
-  const int es = bf16 ? 2 : 4, npl = bf16 ? 1 : 2;
-  FwdParams p{};
-  p.row_bytes = (cin * es >= 128 && cin % (128 / es) == 0) ? 128 : 64;
-  p.kc = p.row_bytes / es;
-  AIDE_REQUIRE(cin % p.kc == 0, "conv3x3(tc): cin=%d not a multiple of the K slice %d", cin, p.kc);
-  p.n_cchunks = cin / p.kc;
-  p.BN = cout % 128 == 0 ? 128 : cout % 64 == 0 ? 64 : 32;
-  pick_tile(H, W, 128, &p.TW, &p.TH);
-  p.tw_log2 = ilog2(p.TW);
-  p.tiles_w = ceil_div(W, p.TW);
-  p.tiles_h = ceil_div(H, p.TH);
-  p.z = z; p.bias = bias; p.stat_partial = stat_partial;
-  p.z_ctot = z_ctot; p.z_coff = z_coff; p.cout = cout; p.cin = cin; p.H = H; p.W = W;
-  p.a_plane_bytes = 128 * p.row_bytes;
-  p.b_plane_bytes = p.BN * p.row_bytes;
-  p.stage_bytes = npl * (p.a_plane_bytes + p.b_plane_bytes);
-  const int staging = 128 * (p.BN + 4) * 4;
-  int budget = (3 * p.stage_bytes <= kSmemBudget2 - 2048 && staging <= kSmemBudget2 - 2048) ? kSmemBudget2 : kSmemBudget1;
-  p.stages = (budget - 2048) / p.stage_bytes;
-  if (p.stages > 6) p.stages = 6;
-  if (p.stages > 9 * p.n_cchunks) p.stages = 9 * p.n_cchunks;
-  AIDE_REQUIRE(p.stages >= 2, "conv3x3(tc): stage too large (%d bytes)", p.stage_bytes);
-  int data = p.stages * p.stage_bytes;
-  if (data < staging) data = staging;
-  p.data_bytes = (data + 1023) / 1024 * 1024;
-  const int smem = p.data_bytes + 8 * (2 * p.stages + 2) + 1024;
-  AIDE_REQUIRE(smem <= 227 * 1024, "conv3x3(tc): shared memory %d too large", smem);
-
-  if (act_tmap(&p.tmA0, bf16, x0, x_ctot, x_coff, cin, N, H, W, p.kc, p.TW, p.TH, p.row_bytes)) return 1;
-  if (mat_tmap(&p.tmB0, bf16, w0, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
-  if (!bf16) {
-    AIDE_REQUIRE(x1 && w1, "conv3x3(tc): TF32X2 needs hi and lo planes");
-    if (act_tmap(&p.tmA1, false, x1, x_ctot, x_coff, cin, N, H, W, p.kc, p.TW, p.TH, p.row_bytes)) return 1;
-    if (mat_tmap(&p.tmB1, false, w1, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
-  }
-  dim3 grid(N * p.tiles_w * p.tiles_h, cout / p.BN);
-  if (bf16) {
-    if (set_smem(conv3x3_tc_kernel<false, false>, 227 * 1024)) return 2;
-    conv3x3_tc_kernel<false, false><<<grid, kThreads, smem, st>>>(p);
-  } else {
-    if (set_smem(conv3x3_tc_kernel<true, true>, 227 * 1024)) return 2;
-    conv3x3_tc_kernel<true, true><<<grid, kThreads, smem, st>>>(p);
-  }
-  AIDE_CHECK_LAUNCH();
   return 0;
 }
 
@@ -619,12 +363,12 @@ int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, in
   p.ws = reinterpret_cast<float*>(ws);
   const int swA = bf16 ? p.rbA : kSwizzle128Atom32, swB = bf16 ? p.rbB : kSwizzle128Atom32;
   if (!bf16) AIDE_REQUIRE(p.rbA == 128 && p.rbB == 128, "conv3x3_wgrad(tc): tf32 operands need 32-channel (128 B) rows");
-  if (act_tmap(&p.tmX0, bf16, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
-  if (act_tmap(&p.tmD0, bf16, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
+  if (act_tmap(&p.tmX0, bf16 ? 1 : 0, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+  if (act_tmap(&p.tmD0, bf16 ? 1 : 0, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
   if (!bf16) {
     AIDE_REQUIRE(x1 && dz1, "conv3x3_wgrad(tc): TF32X2 needs hi and lo planes");
-    if (act_tmap(&p.tmX1, false, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
-    if (act_tmap(&p.tmD1, false, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
+    if (act_tmap(&p.tmX1, 0, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+    if (act_tmap(&p.tmD1, 0, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
   }
   dim3 grid(pl.mt, pl.nt, pl.splits);
   if (bf16) {

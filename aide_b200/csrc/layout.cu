@@ -71,6 +71,7 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int cout, int ci
     int tap = (int)((i / cin) % 9);
     int co = (int)(i / ((size_t)cin * 9));
     float v = w[((size_t)co * cin + ci) * 9 + tap];
+    if constexpr (FMT == AIDE_FMT_F16X2) v *= kF16WScale / kF16ActScale;   // st1 applies 2^8; weights carry 2^12
     if (f0) st1<FMT>(f0, f1, i, v);
     if (d0) st1<FMT>(d0, d1, ((size_t)ci * 9 + (8 - tap)) * cout + co, v);
   }
@@ -87,7 +88,7 @@ extern "C" unsigned long long aide_launch_count(void) { return g_launches.load(s
 extern "C" int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
                                  int N, int C, int H, int W, void* stream) {
   AIDE_REQUIRE(src && dst_p0 && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
-  AIDE_REQUIRE(fmt != AIDE_FMT_TF32X2 || dst_p1, "nchw_to_nhwc: TF32X2 needs two planes");
+  AIDE_REQUIRE(fmt_planes(fmt) == 1 || dst_p1, "nchw_to_nhwc: TF32X2 / F16X2 need two planes");
   dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), N), block(32, 8);
   AIDE_DISPATCH_FMT(fmt, (nchw_to_nhwc_kernel<FMT><<<grid, block, 0, as_stream(stream)>>>(
                              src, dst_p0, dst_p1, dst_ctot, dst_coff, C, H * W)));
@@ -108,8 +109,8 @@ extern "C" int aide_nhwc_to_nchw(int fmt, const void* src_p0, const void* src_p1
 extern "C" int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin, void* fwd_p0, void* fwd_p1,
                                 void* dgrad_p0, void* dgrad_p1, void* stream) {
   AIDE_REQUIRE(w_oihw && cout > 0 && cin > 0 && (fwd_p0 || dgrad_p0), "weight_prep: bad arguments");
-  AIDE_REQUIRE(fmt != AIDE_FMT_TF32X2 || ((!fwd_p0 || fwd_p1) && (!dgrad_p0 || dgrad_p1)),
-               "weight_prep: TF32X2 needs two planes");
+  AIDE_REQUIRE(fmt_planes(fmt) == 1 || ((!fwd_p0 || fwd_p1) && (!dgrad_p0 || dgrad_p1)),
+               "weight_prep: TF32X2 / F16X2 need two planes");
   size_t total = (size_t)cout * cin * 9;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

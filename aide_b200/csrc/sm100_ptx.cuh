@@ -21,6 +21,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -107,6 +110,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // Instruction descriptor (InstrDescriptor): c_format F32 (1) @[4,6); a/b format @[7,10)/[10,13)
 // (BF16 = 1, TF32 = 2); a_major @15, b_major @16 (0 = K-major, 1 = MN-major); N>>3 @[17,23); M>>4 @[24,29).
+// kind::f16: format 0 = F16, 1 = BF16; kind::tf32: format 2 = TF32
 __host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t a_mn_major, uint32_t b_mn_major,
                                                         uint32_t M, uint32_t N) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |

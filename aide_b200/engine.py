@@ -24,27 +24,37 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import FMT_BF16, FMT_F32, FMT_TF32X2, call, lib
+from ._lib import FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, call, lib
 
-MODES = {"exact": FMT_F32, "parity": FMT_TF32X2, "fast": FMT_BF16}
+# mode -> (operand format of forwards that keep a tape for backward, format of inference-only forwards)
+#   parity       fp32-equivalent split-precision tcgen05.  Training forwards/backwards: TF32X2 (3 kind::tf32 MMAs);
+#                forwards that never see a backward (AIDE's 4 augmented pseudo-label forwards per step, eval):
+#                F16X2 (3 kind::f16 MMAs on two fp16 planes: same 22-bit products, twice the tensor rate)
+#   parity_tf32  TF32X2 everywhere          parity_f16  F16X2 everywhere (forward only so far)
+#   fast         single-pass BF16 (NOT a parity mode)      exact  fp32 CUDA cores
+MODES = {"exact": (FMT_F32, FMT_F32), "parity": (FMT_TF32X2, FMT_F16X2), "parity_tf32": (FMT_TF32X2, FMT_TF32X2),
+         "parity_f16": (FMT_F16X2, FMT_F16X2), "fast": (FMT_BF16, FMT_BF16)}
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 
 def default_mode() -> str:
-    """Engine precision mode: 'parity' (3xTF32 tcgen05, fp32-equivalent; default), 'fast' (single-pass
-    BF16 tcgen05) or 'exact' (fp32 CUDA cores).  Opt-in via AIDE_B200_MODE."""
+    """Engine precision mode (see MODES); opt-in via AIDE_B200_MODE."""
     m = os.environ.get("AIDE_B200_MODE", "parity")
     if m not in MODES:
         raise ValueError(f"AIDE_B200_MODE must be one of {sorted(MODES)}, got {m!r}")
     return m
 
 
+def mode_format(mode: str, keep_tape: bool) -> int:
+    return MODES[mode][0 if keep_tape else 1]
+
+
 def _planes(fmt: int) -> int:
-    return 2 if fmt == FMT_TF32X2 else 1
+    return 2 if fmt in (FMT_TF32X2, FMT_F16X2) else 1
 
 
 def _esize(fmt: int) -> int:
-    return 2 if fmt == FMT_BF16 else 4
+    return 2 if fmt in (FMT_BF16, FMT_F16X2) else 4
 
 
 def _align(n: int, a: int = 1024) -> int:

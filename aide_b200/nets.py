@@ -89,7 +89,7 @@ class _EngineNet(nn.Module):
         if self.engine_mode not in E.MODES:
             raise ValueError(f"mode must be one of {sorted(E.MODES)}")
         self._layouts: Dict[tuple, E.Layout] = {}
-        self._weights: Optional[E.PreparedWeights] = None
+        self._weights: Dict[int, E.PreparedWeights] = {}     # per operand format
         self._tensors: Optional[Dict[str, torch.Tensor]] = None
         self._scratch: Optional[torch.Tensor] = None
         self.last_grad_flat: Optional[torch.Tensor] = None
@@ -97,7 +97,7 @@ class _EngineNet(nn.Module):
     # ---- bookkeeping ---------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._tensors, self._weights, self._scratch = None, None, None
+        self._tensors, self._weights, self._scratch = None, {}, None
         return out
 
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -126,7 +126,7 @@ class _EngineNet(nn.Module):
     # ---- engine calls --------------------------------------------------------------------------
     def _engine_forward(self, inputs, keep_tape: bool):
         plan = self._plan
-        fmt = E.MODES[self.engine_mode]
+        fmt = E.mode_format(self.engine_mode, keep_tape)
         N, _, H, W = inputs[0].shape
         key = (N, H, W, fmt)
         layout = self._layouts.get(key)
@@ -135,9 +135,13 @@ class _EngineNet(nn.Module):
         named = self._named()
         training = self.training
         wkey = tuple((named[u.conv + ".weight"].data_ptr(), named[u.conv + ".weight"]._version) for u in plan.units)
-        need_dgrad = keep_tape or getattr(self, "_prep_dgrad_always", False)
-        if self._weights is None or self._weights.key != wkey or (need_dgrad and not self._weights.has_dgrad):
-            self._weights = E.PreparedWeights(plan, named, fmt, need_dgrad)
+        need_dgrad = keep_tape or (getattr(self, "_prep_dgrad_always", False)
+                                   and fmt == E.mode_format(self.engine_mode, True))
+        if self._weights is None:
+            self._weights = {}
+        wts = self._weights.get(fmt)
+        if wts is None or wts.key != wkey or (need_dgrad and not wts.has_dgrad):
+            wts = self._weights[fmt] = E.PreparedWeights(plan, named, fmt, need_dgrad)
         dev = inputs[0].device
         if keep_tape:
             arena = torch.empty(layout.total, dtype=torch.uint8, device=dev)
@@ -147,13 +151,13 @@ class _EngineNet(nn.Module):
             arena = self._scratch
         logits = torch.empty((N, plan.num_classes, H, W), dtype=torch.float32, device=dev)
         xs = [x.detach().contiguous() for x in inputs]
-        E.run_forward(plan, layout, named, self._weights, xs, training, logits, arena)
+        E.run_forward(plan, layout, named, wts, xs, training, logits, arena)
         if training:
             torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], 1)
         tape = None
         if keep_tape:
             tape = E.Tape()
-            tape.layout, tape.arena, tape.weights, tape.training = layout, arena, self._weights, training
+            tape.layout, tape.arena, tape.weights, tape.training = layout, arena, wts, training
         return logits, tape
 
     def _engine_backward(self, tape, dlogits):

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import FMT_BF16, FMT_F32, FMT_TF32X2, call, lib
+from ._lib import FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, call, lib
 
 
 def _st() -> int:
@@ -24,8 +24,8 @@ class Act:
 
     def __init__(self, N: int, H: int, W: int, C_: int, fmt: int, device):
         self.N, self.H, self.W, self.C, self.fmt = N, H, W, C_, fmt
-        dt = torch.bfloat16 if fmt == FMT_BF16 else torch.float32
-        self.planes = torch.zeros((2 if fmt == FMT_TF32X2 else 1, N, H, W, C_), dtype=dt, device=device)
+        dt = {FMT_BF16: torch.bfloat16, FMT_F16X2: torch.float16}.get(fmt, torch.float32)
+        self.planes = torch.zeros((2 if fmt in (FMT_TF32X2, FMT_F16X2) else 1, N, H, W, C_), dtype=dt, device=device)
 
     @property
     def p0(self) -> int:
@@ -33,14 +33,15 @@ class Act:
 
     @property
     def p1(self) -> Optional[int]:
-        return self.planes[1].data_ptr() if self.fmt == FMT_TF32X2 else None
+        return self.planes[1].data_ptr() if self.fmt in (FMT_TF32X2, FMT_F16X2) else None
 
     def view(self, coff: int = 0):
         return self.p0, self.p1, self.C, coff
 
     def float(self) -> torch.Tensor:
-        """fp32 [N,H,W,C] value (hi + lo for TF32X2)."""
-        return self.planes.float().sum(0)
+        """fp32 [N,H,W,C] value (hi + lo for TF32X2; (hi + lo) / 2^8 for F16X2)."""
+        v = self.planes.float().sum(0)
+        return v / 256.0 if self.fmt == FMT_F16X2 else v
 
 
 def from_nchw(x: torch.Tensor, fmt: int, ctot: Optional[int] = None, coff: int = 0, out: Optional[Act] = None) -> Act:
@@ -64,8 +65,8 @@ def nhwc_to_nchw(t: torch.Tensor) -> torch.Tensor:
 def weight_prep(w: torch.Tensor, fmt: int, dgrad: bool = False):
     """OIHW fp32 -> (p0, p1, keepalive) planes: fwd [Cout][9][Cin] or dgrad [Cin][9][Cout]."""
     cout, cin = w.shape[:2]
-    dt = torch.bfloat16 if fmt == FMT_BF16 else torch.float32
-    P = 2 if fmt == FMT_TF32X2 else 1
+    dt = {FMT_BF16: torch.bfloat16, FMT_F16X2: torch.float16}.get(fmt, torch.float32)
+    P = 2 if fmt in (FMT_TF32X2, FMT_F16X2) else 1
     buf = torch.empty((P, cout * 9 * cin), dtype=dt, device=w.device)
     p0, p1 = buf[0].data_ptr(), (buf[1].data_ptr() if P == 2 else None)
     if dgrad:

@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("AIDE_B200_MODE", "parity"), choices=["parity", "fast", "exact"])
+    ap.add_argument("--mode", default=os.environ.get("AIDE_B200_MODE", "parity"),
+                    choices=["parity", "parity_tf32", "fast", "exact"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (slices per network per step)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -145,10 +146,12 @@ def timed_steps(fn, steps, world, device):
 # ---------------------------------------------------------------------------------------------------------
 # roofline of the dominant kernel: conv3x3 on tcgen05, every fuseunet layer shape, timed alone
 # ---------------------------------------------------------------------------------------------------------
-def conv_roofline(mode, B, S, device, peaks):
+FMT_NAMES = {0: "f32", 1: "tf32x2", 2: "bf16", 3: "f16x2"}
+
+
+def conv_roofline(fmt, B, S, device, peaks):
     import aide_b200 as A
     from aide_b200 import engine as E, ops
-    fmt = E.MODES[mode]
     plan = E.plan_fuseunet(2)
     shapes = {}
     for u in plan.units:
@@ -193,13 +196,17 @@ def conv_roofline(mode, B, S, device, peaks):
     src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
     if peak is None:
         peak, src = 1590.0, "fallback (B200_PROFILING.md)"
-    passes = {"parity": 3, "fast": 1, "exact": 0}[mode]
-    return dict(bound="tensor", kernel="conv3x3_tc_kernel (tcgen05 implicit GEMM, fwd; dgrad is the same kernel)",
+    passes = {1: 3, 2: 1, 3: 3}.get(fmt, 0)
+    ceiling = {1: peak / 6.0, 2: peak, 3: peak / 3.0}.get(fmt, peak)
+    return dict(bound="tensor", kernel=f"conv3x3_fwd_tc_kernel<{FMT_NAMES[fmt]}> (persistent tcgen05 implicit GEMM; "
+                                       "dgrad is the same kernel)",
                 achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4), traffic=None,
-                peak_source=src, mma_passes=passes,
+                peak_source=src, operand_format=FMT_NAMES[fmt], mma_passes=passes,
+                frac_of_format_ceiling=round(achieved / ceiling, 4),
                 note=("algorithmic conv FLOPs (2*B*H*W*Cout*Cin*9) of one fuseunet forward's tensor-core layers / summed "
-                      "CUDA-event time of one launch per layer, L2 flushed before each launch; parity mode issues 3 "
-                      "kind::tf32 MMAs (half the bf16 rate) per algorithmic product, so its ceiling is peak/6"),
+                      "CUDA-event time of one launch per layer, L2 flushed before each launch.  Split-precision formats "
+                      "issue 3 MMAs per algorithmic product: f16x2 at the bf16 rate (ceiling peak/3), tf32x2 at half of "
+                      "it (ceiling peak/6)"),
                 layers=rows)
 
 
@@ -334,7 +341,10 @@ def main():
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "slices/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"parity": "tf32x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
+        "dtype": {"parity": "split-precision tcgen05, fp32-equivalent products, fp32 accumulate: f16x2 (3 kind::f16 MMAs) "
+                            "for the pseudo-label forwards, tf32x2 (3 kind::tf32 MMAs) for the training forward/backward",
+                  "parity_tf32": "tf32x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
+                  "parity_f16": "f16x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
                   "fast": "bf16 operands, fp32 accumulate (NOT a parity mode)", "exact": "f32 CUDA cores"}[args.mode],
         "data": "synthetic",
         "config": {"workload": "AIDE proposed step: 2x fuseunet, 4 augmented forwards + train forward + backward per net, "
@@ -352,9 +362,16 @@ def main():
     out["algorithmic_tflops"] = round(value * out["config"]["algorithmic_gflop_per_slice"] / 1e3, 1)
 
     if rank == 0:
-        rl = conv_roofline(args.mode, B, S, device, peaks)
-        layers = rl.pop("layers")
+        from aide_b200 import engine as E
+        fmt_inf, fmt_train = E.mode_format(args.mode, False), E.mode_format(args.mode, True)
+        rl = conv_roofline(fmt_inf, B, S, device, peaks)      # 4 of the 5 forwards per net run in this format
+        layers = {FMT_NAMES[fmt_inf]: rl.pop("layers")}
         out["roofline"] = rl
+        if fmt_train != fmt_inf:
+            rl2 = conv_roofline(fmt_train, B, S, device, peaks)   # train forward + dgrad
+            layers[FMT_NAMES[fmt_train]] = rl2.pop("layers")
+            out["roofline_train_format"] = {k: rl2[k] for k in ("kernel", "achieved", "frac", "frac_of_format_ceiling",
+                                                                "operand_format", "mma_passes")}
         if args.roofline_json:
             with open(args.roofline_json, "w") as f:
                 json.dump(dict(mode=args.mode, batch=B, size=S, summary=rl, layers=layers), f, indent=1)

@@ -18,6 +18,9 @@
  *       AIDE_FMT_TF32X2 two fp32 planes hi = rn_tf32(x), lo = x - hi ("parity mode": 3 tcgen05
  *                       kind::tf32 MMAs hi*hi + hi*lo + lo*hi reproduce fp32 products)
  *       AIDE_FMT_BF16   one bf16 plane ("fast mode": single kind::f16 MMA)
+ *       AIDE_FMT_F16X2  two fp16 planes hi = fp16(x*2^s), lo = fp16(x*2^s - hi), s a per-tensor-class power of
+ *                       two (activations 2^8, weights 2^12): three kind::f16 MMAs hi*hi + hi*lo + lo*hi give the
+ *                       same 22-bit products as TF32X2 at twice the tensor-core rate and half the operand bytes
  *     Raw convolution outputs (z), gradients w.r.t. activations and all reductions are fp32.
  */
 #ifndef AIDE_B200_H_
@@ -30,7 +33,7 @@
 extern "C" {
 #endif
 
-enum { AIDE_FMT_F32 = 0, AIDE_FMT_TF32X2 = 1, AIDE_FMT_BF16 = 2 };
+enum { AIDE_FMT_F32 = 0, AIDE_FMT_TF32X2 = 1, AIDE_FMT_BF16 = 2, AIDE_FMT_F16X2 = 3 };
 
 const char* aide_last_error(void);
 int aide_version(void);

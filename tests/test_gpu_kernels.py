@@ -9,8 +9,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = {0: 2e-5, 1: 3e-5, 2: 3e-2}          # FMT_F32, FMT_TF32X2, FMT_BF16
-NAMES = {0: "exact", 1: "parity", 2: "fast"}
+TOL = {0: 2e-5, 1: 3e-5, 2: 3e-2, 3: 3e-5}          # FMT_F32, FMT_TF32X2, FMT_BF16, FMT_F16X2
+NAMES = {0: "exact", 1: "parity(tf32x2)", 2: "fast", 3: "parity(f16x2)"}
 
 
 def relmax(a, b):
@@ -33,8 +33,8 @@ CONV_SHAPES = [  # N, H, W, cin, cout
 ]
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
-@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", CONV_SHAPES + [(2, 32, 32, 256, 512), (4, 64, 64, 64, 256)])
 def test_conv3x3_forward_and_stats(dev, fmt, shape):
     from aide_b200 import ops
     N, H, W, cin, cout = shape
@@ -113,6 +113,17 @@ def test_conv3x3_dgrad_wgrad(dev, fmt, shape):
     assert relmax(dw, ref_dw) < TOL[fmt], "wgrad " + NAMES[fmt]
 
 
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3x3_f16x2_dgrad(dev, shape):
+    """F16X2 is forward-only in the engine so far; the same kernel already computes dgrad for in-range gradients."""
+    from aide_b200 import ops
+    N, H, W, cin, cout = shape
+    w, dz = rnd(cout, cin, 3, 3, seed=5, scale=(9 * cin) ** -0.5), rnd(N, cout, H, W, seed=6)
+    ref_dx = torch.nn.grad.conv2d_input((N, cin, H, W), w, dz, padding=1)
+    dx = ops.nhwc_to_nchw(ops.conv3x3_dgrad(ops.from_nchw(dz.to(dev), 3), w.to(dev)))
+    assert relmax(dx, ref_dx) < TOL[3]
+
+
 @pytest.mark.parametrize("fmt", [1, 2])
 def test_conv3x3_channel_views(dev, fmt):
     """conv reading a channel slice of a wider buffer and writing... (zero-copy concat, fuseunet.py:49-55)."""
@@ -146,7 +157,7 @@ def test_conv_adjoint_identity_full_size(dev, fmt):
     assert abs(a - b) < tol * scale and abs(a - c) < tol * scale, (a, b, c)
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 @pytest.mark.parametrize("training", [True, False])
 def test_bn_relu_pool_forward(dev, fmt, training):
     from aide_b200 import ops
@@ -207,7 +218,7 @@ def test_bn_relu_pool_backward(dev, fmt):
     assert small[2].abs().max().item() < 1e-4 * dz_ref.abs().max().item() * N * H * W   # sum dz == 0 analytically
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 @pytest.mark.parametrize("hw", [(16, 16), (1, 1), (6, 10)])
 def test_upsample_bilinear(dev, fmt, hw):
     from aide_b200 import ops
@@ -224,7 +235,7 @@ def test_upsample_bilinear(dev, fmt, hw):
         assert relmax(ops.nhwc_to_nchw(dlo), xr.grad) < 1e-5
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 def test_conv1x1_head(dev, fmt):
     from aide_b200 import ops
     x, w, b = rnd(2, 64, 20, 24, seed=1), rnd(2, 64, 1, 1, seed=2, scale=0.1), rnd(2, seed=3)
