@@ -27,6 +27,7 @@ SIGNATURES = {
     "aide_weight_prep": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "aide_conv3x3_stat_rows": (_i, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "aide_conv3x3_plan_info": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_i)]),
     "aide_conv3x3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "aide_bn_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),

@@ -17,6 +17,11 @@ int tc_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, 
 size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
 int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
              int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st);
+bool halo_shape_ok(int fmt, int cin, int cout, int N, int H, int W);
+int halo_stat_rows(int N, int H, int W);
+int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
+                 const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
+                 float out_scale, const float* out_scale_ptr, cudaStream_t st);
 bool tma_available();
 bool c3_shape_ok(int cin, int cout);
 int c3_stat_rows(int N, int H, int W);
@@ -32,7 +37,7 @@ using namespace aide;
 extern "C" int aide_has_tma(void) { return tma_available() ? 1 : 0; }
 
 extern "C" int aide_conv3x3_stat_rows(int fmt, int cin, int cout, int N, int H, int W) {
-  if (fmt != AIDE_FMT_F32) return tc_stat_rows(N, H, W);
+  if (fmt != AIDE_FMT_F32) return halo_shape_ok(fmt, cin, cout, N, H, W) ? halo_stat_rows(N, H, W) : tc_stat_rows(N, H, W);
   return c3_shape_ok(cin, cout) ? c3_stat_rows(N, H, W) : simt_stat_rows(N, H, W);
 }
 
@@ -57,6 +62,11 @@ extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int
   AIDE_REQUIRE(z_ctot % 4 == 0 && z_coff % 4 == 0, "conv3x3_fwd: output view must be 16-byte aligned");
   // F16X2 operands are stored pre-scaled: activations by 2^8, weights by 2^12 (common.cuh)
   const float out_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / (256.0f * 4096.0f) : 1.0f;
+  // second-generation kernel (halo reuse across the 9 taps, pixel-tile blocking) wherever the feature map is large
+  // enough for whole 8-pixel output rows; the first-generation kernel covers the tiny maps of the deepest levels
+  if (halo_shape_ok(fmt, cin, cout, N, H, W))
+    return halo_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
+                        stat_partial, out_scale, nullptr, as_stream(stream));
   return tc_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
                     stat_partial, out_scale, nullptr, as_stream(stream));
 }

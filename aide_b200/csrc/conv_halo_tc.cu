@@ -1,0 +1,505 @@
+// conv_halo_tc.cu -- conv3x3 (stride 1, pad 1) forward / dgrad, second-generation tcgen05 kernel.
+//
+// Why it exists (profiles/r1a_*): the first kernel (conv_fwd_tc.cu) fetches a fresh 128-pixel activation box for each
+// of the 9 filter taps and a fresh weight slice per 128-pixel tile.  ncu shows it pinned at ~32 B/clk/SM of TMA
+// ingest (l1tex__m_xbar2l1tex_read_bytes 8.1-9.0 TB/s) with the tensor pipe 25-50 % busy: it is L2->SM bandwidth
+// bound, not tensor bound.  This kernel cuts the bytes per MMA:
+//
+//   * HALO REUSE.  An output tile is 8 (w) x 16 (h) pixels.  Its (8+2) x (16+2) input halo is loaded ONCE per channel
+//     slice as one dense 4-D TMA box (channels x 10 x 18 x 1, out-of-bounds zero fill = the convolution's padding) and
+//     all nine taps read it in place: tap (dy,dx) is the same shared-memory tile addressed from pixel
+//     (dy+1)*10 + (dx+1), i.e. the UMMA descriptor's start address moves by whole rows and the eight-row core
+//     matrices (one output row of 8 pixels each) sit 10 pixel rows apart (SBO = 10 * row bytes).  The 128B/64B
+//     swizzle is a function of the shared-memory address bits, so TMA's write pattern and the MMA's read pattern agree
+//     for any row offset.  Activation traffic drops from 9 x 128 to 180 pixel rows per slice (6.4x).
+//   * PIXEL-TILE BLOCKING.  One CTA iteration computes MB (1, 2 or 4) pixel tiles against the same weight stage, so
+//     each weight slice fetched from L2 feeds MB x 128 output pixels.
+//
+//   D_m[128 pixels, BN cout] += A_m,tap[128 pixels, kc] * W_tap[BN, kc]^T     m < MB, tap < 9, channel slices of kc
+//
+// Warp roles (192 threads): warp 0 = TMA producer (two rings: activation halos per channel slice, weights per
+// (slice, tap)); warp 1 = TMEM owner + MMA issuer; warps 2..5 = epilogue (tcgen05.ld -> scale, +bias -> 128-bit
+// stores, BatchNorm partial statistics by shuffle butterfly).  Accumulators are double-buffered in TMEM when
+// MB * nacc * BN * 2 <= 512 columns, so the epilogue of one item overlaps the MMAs of the next.
+// Operand kinds as in conv_fwd_tc.cu: BF16 (1 MMA), TF32X2 / F16X2 (3 MMAs lo*hi + hi*lo + hi*hi).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cstdlib>
+
+namespace aide {
+
+using namespace ptx;
+
+int act_tmap(CUtensorMap* m, int dtype, const void* plane, int ctot, int coff, int C, int N, int H, int W, int box_c,
+             int box_w, int box_h, int swizzle_bytes);
+int mat_tmap(CUtensorMap* m, int dtype, const void* plane, int rows, int kdim, int box_k, int box_rows,
+             int swizzle_bytes);
+
+namespace {
+
+enum { K_TF32X2 = 0, K_BF16 = 1, K_F16X2 = 2 };
+constexpr int kThreads = 192;
+constexpr int kTW = 8, kTH = 16;                 // output tile (pixels); 8 = one UMMA core-matrix group per output row
+constexpr int kHW = kTW + 2, kHH = kTH + 2;      // halo box
+constexpr int kHaloPix = kHW * kHH;              // 180 pixel rows per halo
+constexpr int kMaxAStages = 3, kMaxBStages = 8;
+
+struct HaloParams {
+  CUtensorMap tmA0, tmA1, tmB0, tmB1;
+  float* z;
+  const float* bias;
+  float* stat_partial;
+  const float* out_scale_ptr;
+  float out_scale;
+  int z_ctot, z_coff, cout, cin, H, W;
+  int tiles_w, tiles_h, m_tiles, n_tiles, total_items;
+  int BN, kc, n_cchunks, row_bytes;
+  int MB, nacc, nbuf, tmem_cols;
+  int a_slot_bytes, a_stage_bytes, a_stages;
+  int b_plane_bytes, b_stage_bytes, b_stages;
+  int b_off, bar_off;
+};
+
+__device__ __forceinline__ float column_sums_32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int KIND, int NKS>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr bool TF32 = KIND == K_TF32X2;
+  constexpr int NPL = KIND == K_BF16 ? 1 : 2;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const int SA = p.a_stages, SB = p.b_stages;
+  const uint32_t bar_base = base + p.bar_off;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  auto tfull = [&](int b) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + b); };
+  auto tempty = [&](int b) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 2 + b); };
+  constexpr int kSlotIdx = 2 * kMaxAStages + 2 * kMaxBStages + 4;
+  const uint32_t slot_addr = bar_base + 8u * kSlotIdx;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 8 * kSlotIdx);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB0);
+    if (NPL == 2) {
+      tma_prefetch_desc(&p.tmA1);
+      tma_prefetch_desc(&p.tmB1);
+    }
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot_addr, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    // The whole warp walks the loops (warp-uniform addresses and ring counters, no divisions in the inner loops);
+    // one elected lane arms the barriers and issues the bulk-tensor loads.
+    const bool leader = elect_one();
+    const uint32_t halo_bytes = kHaloPix * p.row_bytes;
+    const uint32_t b_tx = NPL * p.b_plane_bytes;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int n_tile = item % p.n_tiles, m0 = (item / p.n_tiles) * p.MB;
+      const int mbv = min(p.MB, p.m_tiles - m0);
+      const int n0 = n_tile * p.BN;
+      int th0[4], tw0[4], tn[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int mt = m0 + (m < mbv ? m : 0);
+        tn[m] = mt / tiles_per_img;
+        const int r = mt - tn[m] * tiles_per_img;
+        th0[m] = (r / p.tiles_w) * kTH - 1;
+        tw0[m] = (r % p.tiles_w) * kTW - 1;
+      }
+      int c0 = 0;
+      for (int c = 0; c < p.n_cchunks; ++c, c0 += p.kc) {
+        mbar_wait(aempty(sa), pha ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(afull(sa), NPL * mbv * halo_bytes);
+          const uint32_t a_dst = base + sa * p.a_stage_bytes;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m < mbv) {
+              tma_load_4d(a_dst + m * p.a_slot_bytes, &p.tmA0, afull(sa), c0, tw0[m], th0[m], tn[m]);
+              if (NPL == 2)
+                tma_load_4d(a_dst + (p.MB + m) * p.a_slot_bytes, &p.tmA1, afull(sa), c0, tw0[m], th0[m], tn[m]);
+            }
+          }
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+        int kcol = c0;                                  // column of (tap, channel slice) in the [cout][9*cin] matrix
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, kcol += p.cin) {
+          mbar_wait(bempty(sb), phb ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(bfull(sb), b_tx);
+            const uint32_t b_dst = base + p.b_off + sb * p.b_stage_bytes;
+            tma_load_2d(b_dst, &p.tmB0, bfull(sb), kcol, n0);
+            if (NPL == 2) tma_load_2d(b_dst + p.b_plane_bytes, &p.tmB1, bfull(sb), kcol, n0);
+          }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // The WHOLE warp walks the loop so that every address below is warp-uniform (uniform registers); one elected
+    // lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced with 64-bit adds on the start-address
+    // field (16-byte units): +2 per 32-byte K step, +row offset per tap, +slot per pixel tile.
+    const uint32_t idesc = make_idesc(TF32 ? 2u : (KIND == K_BF16 ? 1u : 0u), 0u, 0u, 128u, (uint32_t)p.BN);
+    const uint32_t layout = NKS == 4 ? 2u : 4u;
+    const uint64_t a_desc0 = make_smem_desc(base, 16, kHW * p.row_bytes, layout);
+    const uint64_t b_desc0 = make_smem_desc(base + p.b_off, 16, 8 * p.row_bytes, layout);
+    const uint32_t a_plane16 = (uint32_t)(p.MB * p.a_slot_bytes) >> 4;    // hi plane -> lo plane, in 16-byte units
+    const uint32_t b_plane16 = (uint32_t)p.b_plane_bytes >> 4;
+    const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
+    const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+    const uint32_t row16 = (uint32_t)p.row_bytes >> 4;
+    const uint32_t acc_tile = (uint32_t)(p.nacc * p.BN);
+    const bool leader = elect_one();
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0, tcount = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++tcount) {
+      const int m0 = (item / p.n_tiles) * p.MB;
+      const int mbv = min(p.MB, p.m_tiles - m0);
+      const uint32_t buf = tcount % p.nbuf, bph = (tcount / p.nbuf) & 1;
+      mbar_wait(tempty(buf), bph ^ 1);
+      tc_fence_after_sync();
+      const uint32_t acc_item = tmem_base + buf * p.MB * acc_tile;
+      int ai = 0;
+      uint32_t first = 0;                      // bit a set once accumulator a has been written in this item
+      for (int c = 0; c < p.n_cchunks; ++c) {
+        mbar_wait(afull(sa), pha);
+        tc_fence_after_sync();
+        uint64_t a_row = a_desc0 + (uint64_t)(sa * a_stage16);
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy, a_row += (uint64_t)(kHW * row16)) {
+          uint64_t a_tap = a_row;
+#pragma unroll 1
+          for (int dx = 0; dx < 3; ++dx, a_tap += (uint64_t)row16) {
+            mbar_wait(bfull(sb), phb);
+            tc_fence_after_sync();
+            if (leader) {
+              const uint64_t b_hi = b_desc0 + (uint64_t)(sb * b_stage16);
+              const uint32_t flag0 = (first >> ai) & 1u;
+              uint64_t a_hi = a_tap;
+              uint32_t acc = acc_item + (uint32_t)ai * p.BN;
+              for (int m = 0; m < mbv; ++m, a_hi += (uint64_t)a_slot16, acc += acc_tile) {
+#pragma unroll
+                for (int ks = 0; ks < NKS; ++ks) {
+                  const uint32_t flag = ks == 0 ? flag0 : 1u;
+                  if (NPL == 2) {
+                    umma<TF32>(acc, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, flag);
+                    umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(b_plane16 + 2 * ks), idesc, 1u);
+                    umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(2 * ks), idesc, 1u);
+                  } else {
+                    umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(2 * ks), idesc, flag);
+                  }
+                }
+              }
+              umma_commit(bempty(sb));
+            }
+            __syncwarp();
+            first |= 1u << ai;
+            ai = ai + 1 == p.nacc ? 0 : ai + 1;
+            if (++sb == SB) { sb = 0; phb ^= 1; }
+          }
+        }
+        if (leader) umma_commit(aempty(sa));
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+      }
+      if (leader) umma_commit(tfull(buf));
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = row >> 3, tx = row & 7;
+    float scale = p.out_scale;
+    if (p.out_scale_ptr) scale *= __ldg(p.out_scale_ptr);
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++tcount) {
+      const int n_tile = item % p.n_tiles, m0 = (item / p.n_tiles) * p.MB;
+      const int mbv = min(p.MB, p.m_tiles - m0);
+      const int n0 = n_tile * p.BN;
+      const uint32_t buf = tcount % p.nbuf, bph = (tcount / p.nbuf) & 1;
+      mbar_wait(tfull(buf), bph);
+      tc_fence_after_sync();
+      for (int m = 0; m < mbv; ++m) {
+        const int mt = m0 + m;
+        const int n_img = mt / tiles_per_img, r = mt - n_img * tiles_per_img;
+        const int hh = (r / p.tiles_w) * kTH + ty, ww = (r % p.tiles_w) * kTW + tx;
+        const bool valid = hh < p.H && ww < p.W;
+        float* zrow = p.z + (((size_t)n_img * p.H + hh) * p.W + ww) * p.z_ctot + p.z_coff + n0;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MB + m) * p.nacc * p.BN);
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tbase + (uint32_t)(ch * 32), rr);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          for (int a = 1; a < p.nacc; ++a) {
+            tmem_ld_32x32(tbase + (uint32_t)(a * p.BN + ch * 32), rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
+          }
+          const float* bp = p.bias ? p.bias + n0 + ch * 32 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = v[j] * scale;
+            if (bp) t += __ldg(bp + j);
+            v[j] = valid ? t : 0.f;
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(zrow + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.stat_partial) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s1 = column_sums_32(v, lane);
+            const float s2 = column_sums_32(sq, lane);
+            float* out = p.stat_partial + ((size_t)(mt * 4 + q) * 2) * p.cout + n0 + ch * 32 + lane;
+            out[0] = s1;
+            out[p.cout] = s2;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ================================================================================================ host side
+inline int kind_of(int fmt) { return fmt == AIDE_FMT_BF16 ? K_BF16 : fmt == AIDE_FMT_F16X2 ? K_F16X2 : K_TF32X2; }
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s && *s ? std::atoi(s) : dflt;
+}
+
+struct HaloPlan {
+  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages;
+  int a_slot, a_stage, b_plane, b_stage, smem;
+  double cost;
+};
+
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kBarBytes = 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4 + 1);
+
+// Accumulation chains are split over `nacc` TMEM accumulators in the split-precision formats: tcgen05.mma truncates
+// when it adds into the accumulator, so one chain's error grows linearly with its length (tools/accum_probe.py).
+int wanted_nacc(int fmt, long long chain) {
+  if (fmt == AIDE_FMT_BF16) return 1;
+  const int cap = env_int("AIDE_CONV_NACC_MAX", 4);
+  int n = chain > 1200 ? 4 : chain > 400 ? 2 : 1;
+  return n < cap ? n : cap;
+}
+
+// Pick (BN, MB, row bytes, stages) minimising a simple time model: per item max(MMA cycles, TMA bytes / 32 B per clk)
+// plus the epilogue when the accumulators cannot be double-buffered, times the number of waves over 148 SMs.
+bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
+  const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
+  const int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
+  best->cost = -1;
+  for (int rb = 128; rb >= 64; rb >>= 1) {
+    const int kc = rb / es;
+    if (cin % kc) continue;
+    const int n_cchunks = cin / kc;
+    const int nks = rb / 32;
+    const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? 3 : 1);
+    const int nacc = wanted_nacc(fmt, chain);
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+      if (cout % bn) continue;
+      if (force_bn && bn != force_bn) continue;
+      for (int mb = 4; mb >= 1; mb >>= 1) {
+        if (force_mb && mb != force_mb) continue;
+        if (mb * nacc * bn > 512) continue;
+        HaloPlan c{};
+        c.BN = bn; c.MB = mb; c.nacc = nacc; c.row_bytes = rb;
+        c.nbuf = (2 * mb * nacc * bn <= 512) ? 2 : 1;
+        c.a_slot = (kHaloPix * rb + 1023) / 1024 * 1024;
+        c.a_stage = npl * mb * c.a_slot;
+        c.b_plane = bn * rb;
+        c.b_stage = npl * c.b_plane;
+        const int avail = kSmemMax - 1024 - kBarBytes;
+        c.a_stages = 2;
+        int rest = avail - c.a_stages * c.a_stage;
+        if (rest < 2 * c.b_stage && c.a_stages == 2) {          // try a single halo stage before giving up
+          c.a_stages = 1;
+          rest = avail - c.a_stage;
+        }
+        if (rest < 2 * c.b_stage) continue;
+        c.b_stages = rest / c.b_stage;
+        if (c.b_stages > kMaxBStages) c.b_stages = kMaxBStages;
+        if (c.a_stages == 2 && n_cchunks > 2 && c.b_stages > 4 && rest - 4 * c.b_stage >= c.a_stage) {
+          c.a_stages = 3;                                        // spare room: a third halo stage instead of > 4 weight stages
+          c.b_stages = (avail - 3 * c.a_stage) / c.b_stage;
+          if (c.b_stages > kMaxBStages) c.b_stages = kMaxBStages;
+        }
+        c.smem = 1024 + c.a_stages * c.a_stage + c.b_stages * c.b_stage + kBarBytes;
+        // ---- time model (SM clocks); constants fitted to the per-layer (cout tile, blocking) sweep of
+        // tools/halo_probe.py --sweep on B200 (profiles/r1b_halo_sweep.json): an MMA of 128 x bn x 32 B costs
+        // max(bn/2, (256+bn)/3) + 20 clk (tensor rate vs operand fetch + issue), every (slice, tap) stage ~100 clk of
+        // barrier round trip, TMA ingest ~32 B/clk/SM, epilogue ~150 clk per 32 columns per tile
+        const long long items = (m_tiles + mb - 1) / mb * (cout / bn);
+        const long long waves = (items + kNumSMs - 1) / kNumSMs;
+        const double per_mma = (bn / 2.0 > (256 + bn) / 3.0 ? bn / 2.0 : (256 + bn) / 3.0) + 20.0;
+        const double mma = (double)mb * 9 * n_cchunks * nks * (npl == 2 ? 3 : 1) * per_mma + 9.0 * n_cchunks * 100.0;
+        const double bytes = (double)n_cchunks * npl * rb * (mb * kHaloPix + 9.0 * bn);
+        const double epi = (double)mb * (bn / 32) * 150.0 * nacc;
+        double t = mma > bytes / 32.0 ? mma : bytes / 32.0;
+        t *= 1.0 + 0.2 / c.b_stages;                             // shallow weight rings expose L2 latency
+        if (c.nbuf == 1) t += epi;
+        else if (epi > t) t = epi;
+        c.cost = (double)waves * t;
+        if (best->cost < 0 || c.cost < best->cost * 0.999) *best = c;
+      }
+    }
+  }
+  return best->cost >= 0;
+}
+
+template <int KIND, int NKS>
+int launch2(const HaloParams& p, int grid, int smem, cudaStream_t st) {
+  static thread_local bool done[16] = {false};
+  int dev = 0;
+  AIDE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 16 || !done[dev]) {
+    AIDE_CUDA(cudaFuncSetAttribute(conv3x3_halo_tc_kernel<KIND, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    if (dev < 16) done[dev] = true;
+  }
+  conv3x3_halo_tc_kernel<KIND, NKS><<<grid, kThreads, smem, st>>>(p);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+template <int KIND>
+int launch(const HaloParams& p, int grid, int smem, cudaStream_t st) {
+  return p.row_bytes == 128 ? launch2<KIND, 4>(p, grid, smem, st) : launch2<KIND, 2>(p, grid, smem, st);
+}
+
+}  // namespace
+
+// The halo kernel needs whole 8-pixel output rows per UMMA core-matrix group; tiny feature maps (tests at 32x32
+// inputs reach 2x2) stay on the first-generation kernel.
+bool halo_shape_ok(int fmt, int cin, int cout, int N, int H, int W) {
+  if (fmt != AIDE_FMT_TF32X2 && fmt != AIDE_FMT_BF16 && fmt != AIDE_FMT_F16X2) return false;
+  if (env_int("AIDE_CONV_HALO", 1) == 0) return false;
+  if (cin % 32 || cout % 32 || cin < 32 || cout < 32) return false;
+  if (W < kTW || H < kTH / 2) return false;
+  HaloPlan pl;
+  const long long m_tiles = (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH);
+  return make_plan(fmt, cin, cout, m_tiles, &pl);
+}
+
+int halo_stat_rows(int N, int H, int W) { return 4 * N * ceil_div(W, kTW) * ceil_div(H, kTH); }
+
+int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
+                 const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
+                 float out_scale, const float* out_scale_ptr, cudaStream_t st) {
+  const int kind = kind_of(fmt);
+  const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
+  const int dtype = fmt == AIDE_FMT_BF16 ? 1 : fmt == AIDE_FMT_F16X2 ? 2 : 0;
+  AIDE_REQUIRE(npl == 1 || (x1 && w1), "conv3x3(halo): two-plane operand formats need hi and lo planes");
+  HaloParams p{};
+  p.tiles_w = ceil_div(W, kTW);
+  p.tiles_h = ceil_div(H, kTH);
+  p.m_tiles = N * p.tiles_w * p.tiles_h;
+  HaloPlan pl;
+  AIDE_REQUIRE(make_plan(fmt, cin, cout, p.m_tiles, &pl), "conv3x3(halo): no tiling fits (cin=%d cout=%d)", cin, cout);
+  p.BN = pl.BN; p.MB = pl.MB; p.nacc = pl.nacc; p.nbuf = pl.nbuf;
+  p.row_bytes = pl.row_bytes;
+  p.kc = pl.row_bytes / es;
+  p.n_cchunks = cin / p.kc;
+  p.n_tiles = cout / p.BN;
+  p.total_items = ceil_div(p.m_tiles, p.MB) * p.n_tiles;
+  p.a_slot_bytes = pl.a_slot; p.a_stage_bytes = pl.a_stage; p.a_stages = pl.a_stages;
+  p.b_plane_bytes = pl.b_plane; p.b_stage_bytes = pl.b_stage; p.b_stages = pl.b_stages;
+  p.b_off = pl.a_stages * pl.a_stage;
+  p.bar_off = p.b_off + pl.b_stages * pl.b_stage;
+  int cols = p.nbuf * p.MB * p.nacc * p.BN;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+  p.z = z; p.bias = bias; p.stat_partial = stat_partial;
+  p.out_scale = out_scale; p.out_scale_ptr = out_scale_ptr;
+  p.z_ctot = z_ctot; p.z_coff = z_coff; p.cout = cout; p.cin = cin; p.H = H; p.W = W;
+  AIDE_REQUIRE(pl.smem <= kSmemMax, "conv3x3(halo): shared memory %d too large", pl.smem);
+
+  if (act_tmap(&p.tmA0, dtype, x0, x_ctot, x_coff, cin, N, H, W, p.kc, kHW, kHH, p.row_bytes)) return 1;
+  if (mat_tmap(&p.tmB0, dtype, w0, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
+  if (npl == 2) {
+    if (act_tmap(&p.tmA1, dtype, x1, x_ctot, x_coff, cin, N, H, W, p.kc, kHW, kHH, p.row_bytes)) return 1;
+    if (mat_tmap(&p.tmB1, dtype, w1, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
+  }
+  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
+  if (kind == K_BF16) return launch<K_BF16>(p, grid, pl.smem, st);
+  if (kind == K_F16X2) return launch<K_F16X2>(p, grid, pl.smem, st);
+  return launch<K_TF32X2>(p, grid, pl.smem, st);
+}
+
+// for tools/ and bench.py: the tiling chosen for a layer
+extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out /*[8]*/) {
+  if (!halo_shape_ok(fmt, cin, cout, N, H, W)) return 1;
+  HaloPlan pl;
+  make_plan(fmt, cin, cout, (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH), &pl);
+  out[0] = pl.BN; out[1] = pl.MB; out[2] = pl.nacc; out[3] = pl.nbuf; out[4] = pl.row_bytes; out[5] = pl.a_stages;
+  out[6] = pl.b_stages; out[7] = pl.smem;
+  return 0;
+}
+
+}  // namespace aide

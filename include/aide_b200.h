@@ -70,6 +70,10 @@ int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
                      const void* w_p0, const void* w_p1, const float* bias,
                      float* z, int z_ctot, int z_coff, int cout, int N, int H, int W,
                      float* stat_partial, void* stream);
+/* Tiling the tcgen05 forward/dgrad kernel picks for a layer (diagnostics for bench.py / tools): out[8] =
+ * {cout tile, pixel tiles per CTA iteration, accumulators per tile, TMEM buffers, smem row bytes, halo stages,
+ *  weight stages, dynamic smem bytes}.  Returns non-zero when the layer runs on the first-generation kernel. */
+int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out);
 /* dW[co,ci,ky,kx] = sum_{n,h,w} dz[n,h,w,co] * x[n,h+ky-1,w+kx-1,ci]  (ATen conv backward-filter).
  * dz is a plain [N,H,W,cout] operand-format buffer.  Result written (not accumulated) as OIHW fp32. */
 size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);

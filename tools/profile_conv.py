@@ -17,11 +17,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--fmt", type=int, default=3)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--layers", nargs="+", default=["512,256,64"])          # cin,cout,hw
+ap.add_argument("--layers", nargs="+", default=["512,256,64"])          # cin,cout,hw[,BN,MB] (forced tiling)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 for spec in args.layers:
-    cin, cout, hw = (int(v) for v in spec.split(","))
+    vals = [int(v) for v in spec.split(",")]
+    cin, cout, hw = vals[:3]
+    for k in ("AIDE_CONV_BN", "AIDE_CONV_MB"):
+        os.environ.pop(k, None)
+    if len(vals) >= 5:
+        os.environ["AIDE_CONV_BN"], os.environ["AIDE_CONV_MB"] = str(vals[3]), str(vals[4])
     x = ops.Act(args.batch, hw, hw, cin, args.fmt, dev)
     x.planes.normal_()
     w = torch.randn(cout, cin, 3, 3, device=dev) * (9 * cin) ** -0.5

@@ -1,0 +1,91 @@
+"""Turn the raw ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py launches gpurun_out/launches_r1.csv profiles/r1_launches
+    python tools/summarize_profiles.py full gpurun_out/conv_full.ncu-rep profiles/r1_conv_f16x2_full
+
+`launches`: the `ncu --metrics gpu__time_duration.sum` launch list of `bench.py`.  Steps are delimited by the two
+Adam kernels that end each AIDE step; the LAST complete step (a timed CUDA-graph replay) is written out launch by
+launch (<out>_step.csv) and aggregated per kernel (<out>_summary.md).
+`full`: selected metrics of an `ncu --set full` report (<out>.csv, one column per captured launch).
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+
+def short(name: str) -> str:
+    n = re.sub(r"^void ", "", name)
+    m = re.match(r"([\w:]+)(<[^(]*>)?", n)
+    return ((m.group(1) + (m.group(2) or "")) if m else n)[:100]
+
+
+def launches(src: str, out: str) -> None:
+    rows = []
+    with open(src) as f:
+        for line in f:
+            if line.startswith('"ID"'):
+                break
+        for r in csv.reader(f):
+            if len(r) >= 15:
+                rows.append((int(r[0]), r[4], r[6], r[7], r[8], float(r[14].replace(",", ""))))
+    ends = [i for i, r in enumerate(rows) if "adam_amsgrad_kernel" in r[1]]
+    # two Adam kernels per step (one per net); a step = (previous step's 2nd Adam, this step's 2nd Adam]
+    ends = ends[1::2]
+    if len(ends) < 2:
+        raise SystemExit("fewer than two complete steps in the launch list")
+    # choose the last step whose length equals the most common step length (graph replays are identical)
+    lens = [ends[i] - ends[i - 1] for i in range(1, len(ends))]
+    common = collections.Counter(lens).most_common(1)[0][0]
+    k = max(i for i in range(1, len(ends)) if ends[i] - ends[i - 1] == common)
+    seg = rows[ends[k - 1] + 1: ends[k] + 1]
+    with open(out + "_step.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["ncu_id", "kernel", "stream", "block", "grid", "gpu__time_duration_ns"])
+        for r in seg:
+            w.writerow([r[0], short(r[1]), r[2], r[3], r[4], int(r[5])])
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in seg:
+        a = agg[short(r[1])]
+        a[0] += 1
+        a[1] += r[5]
+    tot = sum(v[1] for v in agg.values())
+    with open(out + "_summary.md", "w") as f:
+        f.write(f"# ncu launch list of one AIDE step ({len(seg)} launches, serialised total {tot / 1e6:.3f} ms)\n\n")
+        f.write(f"Source: `{src}` ({len(rows)} launches in the whole `bench.py` run, {len(ends)} complete steps; "
+                f"step {k} shown).\nPer-launch times are cold-cache and serialised by ncu: compare SHARES, not "
+                "absolutes (the two networks overlap on two streams in a real step).\n\n")
+        f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {n} | {t / 1e6:.3f} | {100 * t / tot:.1f} % |\n")
+    print(f"wrote {out}_step.csv and {out}_summary.md ({len(seg)} launches, {tot / 1e6:.2f} ms)")
+
+
+FULL_PAT = re.compile(
+    r"^(Kernel Name|Grid Size|Block Size|gpu__time_duration\.sum|dram__bytes_(read|write)\.sum(\.per_second)?"
+    r"|gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed|launch__registers_per_thread"
+    r"|launch__shared_mem_per_block_dynamic|launch__occupancy_limit_\w+|sm__warps_active\.avg\.pct_of_peak_sustained_active"
+    r"|sm__throughput\.avg\.pct_of_peak_sustained_elapsed|sm__cycles_elapsed\.(avg|max)(\.per_second)?"
+    r"|sm__cycles_active\.avg|sm__inst_executed_pipe_tensor\w*\.sum|sm__pipe_tensor[\w.]*"
+    r"|\w+\.TriageCompute\.sm__pipe_tensor[\w.]*"
+    r"|l1tex__m_xbar2l1tex_read_bytes(_mem_global_op_tma_ld)?\.sum(\.per_second)?"
+    r"|lts__t_bytes\.sum(\.per_second)?|lts__t_sector_hit_rate\.pct|lts__throughput\.avg\.pct_of_peak_sustained_elapsed"
+    r"|l1tex__throughput\.avg\.pct_of_peak_sustained_elapsed|smsp__cycles_active\.avg)$")
+
+
+def full(src: str, out: str) -> None:
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(out + ".csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(data))])
+        for i, h in enumerate(hdr):
+            if FULL_PAT.match(h):
+                w.writerow([h, units[i]] + [r[i] for r in data])
+    print(f"wrote {out}.csv ({len(data)} launches)")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
