@@ -29,16 +29,17 @@ SIGNATURES = {
     "aide_conv3x3_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "aide_conv3x3_plan_info": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_i)]),
     "aide_conv3x3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "aide_conv3x3_dgrad": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "aide_bn_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
     "aide_bn_relu_apply": (_i, [_i, _vp, _i, _i, _i, _i, _vp,
                                 _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "aide_bn_bwd_rows": (_i, [_i, _i, _i, _i]),
     "aide_bn_relu_bwd_reduce": (_i, [_vp, _vp, _vp, _i, _i, _i, _i,
                                      C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i,
-                                     C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _vp]),
+                                     C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     "aide_bn_relu_bwd_apply": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
-                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_upsample2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_upsample2x_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_conv1x1_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

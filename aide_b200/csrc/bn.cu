@@ -197,8 +197,10 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
 template <bool WINDOW>
 __global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ scale_shift,
                                           const float* __restrict__ mean_rstd, int N, int H, int W, int C,
-                                          BwdSrcs s, float* __restrict__ g, float* __restrict__ partial) {
+                                          BwdSrcs s, float* __restrict__ g, float* __restrict__ partial,
+                                          unsigned int* __restrict__ gmax_bits) {
   extern __shared__ float smem[];  // [ty][cx*8]
+  float gmax = 0.f;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const bool cvalid = c < C;
   constexpr int KP = WINDOW ? 4 : 1;
@@ -260,6 +262,7 @@ __global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const flo
         o.z = yy[k].z > 0.f ? gg[k].z : 0.f;
         o.w = yy[k].w > 0.f ? gg[k].w : 0.f;
         *reinterpret_cast<float4*>(g + p[k] * C + c) = o;
+        gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
         sg[0] += o.x; sg[1] += o.y; sg[2] += o.z; sg[3] += o.w;
         sgx[0] += o.x * ((zz[k].x - mu.x) * rs.x);
         sgx[1] += o.y * ((zz[k].y - mu.y) * rs.y);
@@ -287,6 +290,45 @@ __global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const flo
     *reinterpret_cast<float4*>(out + c) = make_float4(a[0], a[1], a[2], a[3]);
     *reinterpret_cast<float4*>(out + C + c) = make_float4(a[4], a[5], a[6], a[7]);
   }
+  if (gmax_bits) {   // max |g| of the whole tensor: order-independent, so the atomic keeps the result deterministic
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && gmax > 0.f) atomicMax(gmax_bits, __float_as_uint(gmax));
+  }
+}
+
+// F16X2 gradients: choose the power-of-two scale s of dZ from a bound on max|dz|,
+//   |dz| <= |gamma*rstd| * (|g| + |mean g| + |xhat| * |mean g*xhat|),  |xhat| taken as <= 16,
+// so that the bound lands at 2^10 (64x headroom to the fp16 maximum; conversions saturate beyond it, and the two
+// fp16 planes keep 22 significant bits down to 2^-24 of the bound).  scale_out = {s, 1/s}.
+__global__ void dz_scale_kernel(const unsigned int* __restrict__ gmax_bits, const float* __restrict__ mean_rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int C,
+                                float* __restrict__ scale_out) {
+  __shared__ float red[32];
+  const float gmax = __uint_as_float(*gmax_bits);
+  float b = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float k0 = fabsf(gamma[c] * mean_rstd[C + c]);
+    b = fmaxf(b, k0 * (gmax + fabsf(sums[c] * inv_count) + 16.f * fabsf(sums[C + c] * inv_count)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) b = fmaxf(b, red[i]);
+    int e = 0;
+    if (b > 0.f && isfinite(b)) {
+      frexpf(b, &e);                 // b = m * 2^e, m in [0.5, 1)
+      e = 10 - e;
+      e = e < -100 ? -100 : e > 100 ? 100 : e;
+    }
+    scale_out[0] = ldexpf(1.f, e);
+    scale_out[1] = ldexpf(1.f, -e);
+  }
 }
 
 // ------------------------------------------------------------------ backward stage 2
@@ -294,8 +336,12 @@ template <int FMT>
 __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z,
                                          const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                          const float* __restrict__ sums /*[2][C]: sum g, sum g*xhat*/, float inv_count,
-                                         size_t npix, int C, void* dz0, void* dz1, float* __restrict__ partial2) {
+                                         size_t npix, int C, void* dz0, void* dz1, float* __restrict__ partial2,
+                                         const float* __restrict__ dz_scale) {
   extern __shared__ float smem[];  // [ty][cx*4]
+  // F16X2 planes store dz * s / 2^8 through st4 (which multiplies by the activation scale 2^8): pass dz * s * 2^-8
+  float fs = 1.f;
+  if constexpr (FMT == AIDE_FMT_F16X2) fs = __ldg(dz_scale) * (1.0f / kF16ActScale);
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const bool cvalid = c < C;
   float sd[4] = {0, 0, 0, 0};
@@ -316,7 +362,10 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ g, const floa
       d.y = k0.y * (gv.y - m1.y - ((zv.y - mu.y) * rs.y) * m2.y);
       d.z = k0.z * (gv.z - m1.z - ((zv.z - mu.z) * rs.z) * m2.z);
       d.w = k0.w * (gv.w - m1.w - ((zv.w - mu.w) * rs.w) * m2.w);
-      st4<FMT>(dz0, dz1, p * C + c, d);
+      if constexpr (FMT == AIDE_FMT_F16X2)
+        st4<FMT>(dz0, dz1, p * C + c, make_float4(d.x * fs, d.y * fs, d.z * fs, d.w * fs));
+      else
+        st4<FMT>(dz0, dz1, p * C + c, d);
       sd[0] += d.x; sd[1] += d.y; sd[2] += d.z; sd[3] += d.w;
     }
   }
@@ -415,7 +464,7 @@ extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift,
                                        int H, int W, int C, const float* const* direct_ptr, const int* direct_ctot,
                                        const int* direct_coff, int n_direct, const float* const* pool_ptr,
                                        const int* pool_ctot, const int* pool_coff, int n_pool, float* g,
-                                       float* partial, void* stream) {
+                                       float* partial, float* gmax, void* stream) {
   AIDE_REQUIRE(z && scale_shift && mean_rstd && g && partial, "bn_relu_bwd_reduce: null argument");
   AIDE_REQUIRE(C % 4 == 0, "bn_relu_bwd_reduce: need C%%4==0");
   AIDE_REQUIRE(n_pool == 0 || (H % 2 == 0 && W % 2 == 0), "bn_relu_bwd_reduce: pooled sources need even H,W");
@@ -439,12 +488,14 @@ extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift,
   BwdGeom gm = bwd_geom(N, H, W, C);
   dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
   size_t smem = (size_t)gm.cx * gm.ty * 8 * sizeof(float);
+  unsigned int* gbits = reinterpret_cast<unsigned int*>(gmax);
+  if (gbits) AIDE_CUDA(cudaMemsetAsync(gbits, 0, sizeof(unsigned int), as_stream(stream)));
   if (n_pool > 0)
     bn_relu_bwd_reduce_kernel<true><<<grid, block, smem, as_stream(stream)>>>(z, scale_shift, mean_rstd, N, H, W, C,
-                                                                              s, g, partial);
+                                                                              s, g, partial, gbits);
   else
     bn_relu_bwd_reduce_kernel<false><<<grid, block, smem, as_stream(stream)>>>(z, scale_shift, mean_rstd, N, H, W, C,
-                                                                               s, g, partial);
+                                                                               s, g, partial, gbits);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -452,7 +503,7 @@ extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift,
 extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd,
                                       const float* gamma, const float* partial, int rows, int N, int H, int W, int C,
                                       void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
-                                      float* partial2, void* stream) {
+                                      float* partial2, const float* gmax, float* dz_scale, void* stream) {
   AIDE_REQUIRE(g && z && mean_rstd && gamma && partial && dz_p0 && dgamma && dbeta && partial2,
                "bn_relu_bwd_apply: null argument");
   AIDE_REQUIRE(dbeta + C == dgamma, "bn_relu_bwd_apply: dbeta/dgamma must be adjacent ([2][C] buffer: dbeta, dgamma)");
@@ -466,8 +517,14 @@ extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, c
   dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
   size_t smem = (size_t)gm.cx * gm.ty * 4 * sizeof(float);
   float inv = (float)(1.0 / (double)npix);
+  if (fmt == AIDE_FMT_F16X2) {
+    AIDE_REQUIRE(gmax && dz_scale, "bn_relu_bwd_apply: F16X2 needs gmax (from bn_relu_bwd_reduce) and dz_scale[2]");
+    dz_scale_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const unsigned int*>(gmax), mean_rstd, gamma, dbeta, inv, C,
+                                       dz_scale);
+    AIDE_CHECK_LAUNCH();
+  }
   AIDE_DISPATCH_FMT(fmt, (bn_relu_bwd_apply_kernel<FMT><<<grid, block, smem, st>>>(
-                             g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2)));
+                             g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2, dz_scale)));
   AIDE_CHECK_LAUNCH();
   if (dbias_conv) {
     reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(partial2, rows, C, C, dbias_conv);

@@ -16,7 +16,8 @@ int tc_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, 
                float out_scale, const float* out_scale_ptr, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
 int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
-             int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st);
+             int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, float out_scale,
+             const float* out_scale_ptr, cudaStream_t st);
 bool halo_shape_ok(int fmt, int cin, int cout, int N, int H, int W);
 int halo_stat_rows(int N, int H, int W);
 int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
@@ -41,7 +42,7 @@ extern "C" int aide_conv3x3_stat_rows(int fmt, int cin, int cout, int N, int H, 
   return c3_shape_ok(cin, cout) ? c3_stat_rows(N, H, W) : simt_stat_rows(N, H, W);
 }
 
-extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+static int conv3x3_any(int fmt, float op_scale, const float* out_scale_ptr, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
                                 const void* w_p0, const void* w_p1, const float* bias, float* z, int z_ctot,
                                 int z_coff, int cout, int N, int H, int W, float* stat_partial, void* stream) {
   AIDE_REQUIRE(x_p0 && w_p0 && z && cin > 0 && cout > 0 && N > 0 && H > 0 && W > 0, "conv3x3_fwd: bad arguments");
@@ -60,15 +61,34 @@ extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int
                "conv3x3_fwd: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0 (got %d -> %d); use AIDE_FMT_F32",
                cin, cout);
   AIDE_REQUIRE(z_ctot % 4 == 0 && z_coff % 4 == 0, "conv3x3_fwd: output view must be 16-byte aligned");
-  // F16X2 operands are stored pre-scaled: activations by 2^8, weights by 2^12 (common.cuh)
-  const float out_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / (256.0f * 4096.0f) : 1.0f;
+  const float out_scale = op_scale;
   // second-generation kernel (halo reuse across the 9 taps, pixel-tile blocking) wherever the feature map is large
   // enough for whole 8-pixel output rows; the first-generation kernel covers the tiny maps of the deepest levels
   if (halo_shape_ok(fmt, cin, cout, N, H, W))
     return halo_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
-                        stat_partial, out_scale, nullptr, as_stream(stream));
+                        stat_partial, out_scale, out_scale_ptr, as_stream(stream));
   return tc_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H, W,
-                    stat_partial, out_scale, nullptr, as_stream(stream));
+                    stat_partial, out_scale, out_scale_ptr, as_stream(stream));
+}
+
+extern "C" int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                                const void* w_p0, const void* w_p1, const float* bias, float* z, int z_ctot,
+                                int z_coff, int cout, int N, int H, int W, float* stat_partial, void* stream) {
+  // F16X2 operands are stored pre-scaled: activations by 2^8, weights by 2^12 (common.cuh)
+  const float op_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / (kF16ActScale * kF16WScale) : 1.0f;
+  return conv3x3_any(fmt, op_scale, nullptr, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, z, z_ctot, z_coff, cout, N, H,
+                     W, stat_partial, stream);
+}
+
+extern "C" int aide_conv3x3_dgrad(int fmt, const void* dz_p0, const void* dz_p1, int cout, const void* w_p0,
+                                  const void* w_p1, const float* dz_inv_scale, float* dx, int dx_ctot, int dx_coff,
+                                  int cin, int N, int H, int W, void* stream) {
+  // F16X2: dZ is stored as dz * s with s a power of two chosen on the device (aide_bn_relu_bwd_apply writes
+  // {s, 1/s}); the epilogue multiplies by 1/s (dz_inv_scale) and by the static 2^-12 of the weight planes
+  AIDE_REQUIRE(fmt != AIDE_FMT_F16X2 || dz_inv_scale, "conv3x3_dgrad: F16X2 needs the gradient's inverse scale");
+  const float op_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / kF16WScale : 1.0f;
+  return conv3x3_any(fmt, op_scale, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr, dz_p0, dz_p1, cout, 0, cout, w_p0, w_p1,
+                     nullptr, dx, dx_ctot, dx_coff, cin, N, H, W, nullptr, stream);
 }
 
 extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W) {
@@ -79,8 +99,8 @@ extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout,
 }
 
 extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
-                                  const void* dz_p0, const void* dz_p1, int cout, int N, int H, int W, void* workspace,
-                                  size_t workspace_bytes, float* dw_oihw, void* stream) {
+                                  const void* dz_p0, const void* dz_p1, const float* dz_inv_scale, int cout, int N, int H,
+                                  int W, void* workspace, size_t workspace_bytes, float* dw_oihw, void* stream) {
   AIDE_REQUIRE(x_p0 && dz_p0 && dw_oihw && workspace, "conv3x3_wgrad: null argument");
   AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot, "conv3x3_wgrad: channel view out of range");
   if (fmt == AIDE_FMT_F32 && c3_shape_ok(cin, cout))
@@ -89,9 +109,12 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
   if (fmt == AIDE_FMT_F32)
     return simt_wgrad(reinterpret_cast<const float*>(x_p0), x_ctot, x_coff, cin, reinterpret_cast<const float*>(dz_p0),
                       cout, N, H, W, reinterpret_cast<float*>(workspace), workspace_bytes, dw_oihw, as_stream(stream));
-  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16,
-               "conv3x3_wgrad: operand format %d not supported (F16X2 is forward-only so far)", fmt);
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16 || fmt == AIDE_FMT_F16X2, "conv3x3_wgrad: bad operand format %d",
+               fmt);
+  AIDE_REQUIRE(fmt != AIDE_FMT_F16X2 || dz_inv_scale, "conv3x3_wgrad: F16X2 needs the gradient's inverse scale");
   AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout), "conv3x3_wgrad: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0");
-  return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes,
-                  dw_oihw, as_stream(stream));
+  // F16X2: x planes carry 2^8, dZ planes carry the dynamic scale s -> dW = acc * 2^-8 * (1/s)
+  return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes, dw_oihw,
+                  fmt == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr,
+                  as_stream(stream));
 }

@@ -178,8 +178,9 @@ wgrad_simt_kernel(const float* __restrict__ x, int x_ctot, int x_coff, int cin, 
 
 // dw_oihw[co][ci][tap] = sum_split ws[split][...]; layout 0: [co][tap][ci], layout 1: [tap][ci][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int layout,
-                                    float* __restrict__ dw) {
+                                    float* __restrict__ dw, float scale, const float* __restrict__ scale_ptr) {
   size_t total = (size_t)cout * cin * 9;
+  if (scale_ptr) scale *= __ldg(scale_ptr);      // descale of the operand formats (static) x gradient scale (dynamic)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     // i indexes the workspace layout (coalesced reads)
     int co, ci, tap;
@@ -194,15 +195,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
     }
     float a = 0.f;
     for (int s = 0; s < splits; ++s) a += ws[(size_t)s * total + i];
-    dw[((size_t)co * cin + ci) * 9 + tap] = a;
+    dw[((size_t)co * cin + ci) * 9 + tap] = a * scale;
   }
 }
 
-int launch_wgrad_reduce(const float* ws, int splits, int cout, int cin, int layout, float* dw, cudaStream_t st) {
+int launch_wgrad_reduce(const float* ws, int splits, int cout, int cin, int layout, float* dw, float scale,
+                        const float* scale_ptr, cudaStream_t st) {
   size_t total = (size_t)cout * cin * 9;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, cout, cin, layout, dw);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, cout, cin, layout, dw, scale, scale_ptr);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -243,7 +245,7 @@ int simt_wgrad(const float* x, int x_ctot, int x_coff, int cin, const float* dz,
   dim3 grid(ceil_div(cout, 64) * ci_tiles, 9, splits);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(x, x_ctot, x_coff, cin, dz, cout, N, H, W, ci_tiles, per, ws);
   AIDE_CHECK_LAUNCH();
-  return launch_wgrad_reduce(ws, splits, cout, cin, 0, dw, st);
+  return launch_wgrad_reduce(ws, splits, cout, cin, 0, dw, 1.0f, nullptr, st);
 }
 
 }  // namespace aide

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, (uint32_t)p.BN);
+      const uint32_t idesc = make_idesc(TF32 ? 2u : (PARITY ? 0u : 1u), 1u, 1u, 128u, (uint32_t)p.BN);   // tf32 | fp16 (F16X2) | bf16
       // MN-major operands.  16-bit: SWIZZLE_128B / SWIZZLE_64B atoms of 8 K-rows.  32-bit (tf32): the only legal
       // layout is SWIZZLE_128B_BASE32B (type 1): 128-byte rows, 32-byte swizzle atoms, 4 K-rows per atom.
       const uint32_t layA = TF32 ? 1u : (p.rbA == 128 ? 2u : 4u), layB = TF32 ? 1u : (p.rbB == 128 ? 2u : 4u);
@@ -304,8 +304,8 @@ struct WgradPlan {
 };
 
 static int wgrad_plan(int fmt, int cin, int cout, int N, int H, int W, WgradPlan* o) {
-  const bool bf16 = fmt == AIDE_FMT_BF16;
-  const int es = bf16 ? 2 : 4, npl = bf16 ? 1 : 2;
+  const bool bf16 = fmt != AIDE_FMT_TF32X2;            // 16-bit operands (BF16 one plane, F16X2 two planes)
+  const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
   WgradParams& p = o->p;
   p = WgradParams{};
   p.cin = cin; p.cout = cout; p.H = H; p.W = W;
@@ -351,11 +351,15 @@ size_t tc_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W)
   return (size_t)pl.splits * 9 * cin * cout * sizeof(float);
 }
 
-int launch_wgrad_reduce(const float* ws, int splits, int cout, int cin, int layout, float* dw, cudaStream_t st);
+int launch_wgrad_reduce(const float* ws, int splits, int cout, int cin, int layout, float* dw, float scale,
+                        const float* scale_ptr, cudaStream_t st);
 
 int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
-             int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, cudaStream_t st) {
-  const bool bf16 = fmt == AIDE_FMT_BF16;
+             int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, float out_scale,
+             const float* out_scale_ptr, cudaStream_t st) {
+  const bool bf16 = fmt != AIDE_FMT_TF32X2;
+  const int npl = fmt_planes(fmt);
+  const int dtype = fmt == AIDE_FMT_BF16 ? 1 : fmt == AIDE_FMT_F16X2 ? 2 : 0;
   WgradPlan pl;
   if (wgrad_plan(fmt, cin, cout, N, H, W, &pl)) return 1;
   WgradParams& p = pl.p;
@@ -363,23 +367,26 @@ int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, in
   p.ws = reinterpret_cast<float*>(ws);
   const int swA = bf16 ? p.rbA : kSwizzle128Atom32, swB = bf16 ? p.rbB : kSwizzle128Atom32;
   if (!bf16) AIDE_REQUIRE(p.rbA == 128 && p.rbB == 128, "conv3x3_wgrad(tc): tf32 operands need 32-channel (128 B) rows");
-  if (act_tmap(&p.tmX0, bf16 ? 1 : 0, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
-  if (act_tmap(&p.tmD0, bf16 ? 1 : 0, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
-  if (!bf16) {
-    AIDE_REQUIRE(x1 && dz1, "conv3x3_wgrad(tc): TF32X2 needs hi and lo planes");
-    if (act_tmap(&p.tmX1, 0, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
-    if (act_tmap(&p.tmD1, 0, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
+  if (act_tmap(&p.tmX0, dtype, x0, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+  if (act_tmap(&p.tmD0, dtype, dz0, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
+  if (npl == 2) {
+    AIDE_REQUIRE(x1 && dz1, "conv3x3_wgrad(tc): two-plane operand formats need hi and lo planes");
+    if (act_tmap(&p.tmX1, dtype, x1, x_ctot, x_coff, cin, N, H, W, p.kcA, p.TW, p.TH, swA)) return 1;
+    if (act_tmap(&p.tmD1, dtype, dz1, cout, 0, cout, N, H, W, p.kcB, p.TW, p.TH, swB)) return 1;
   }
   dim3 grid(pl.mt, pl.nt, pl.splits);
-  if (bf16) {
+  if (fmt == AIDE_FMT_BF16) {
     if (set_smem(wgrad_tc_kernel<false, false>, 227 * 1024)) return 2;
     wgrad_tc_kernel<false, false><<<grid, kThreads, pl.smem, st>>>(p);
+  } else if (fmt == AIDE_FMT_F16X2) {
+    if (set_smem(wgrad_tc_kernel<false, true>, 227 * 1024)) return 2;
+    wgrad_tc_kernel<false, true><<<grid, kThreads, pl.smem, st>>>(p);
   } else {
     if (set_smem(wgrad_tc_kernel<true, true>, 227 * 1024)) return 2;
     wgrad_tc_kernel<true, true><<<grid, kThreads, pl.smem, st>>>(p);
   }
   AIDE_CHECK_LAUNCH();
-  return launch_wgrad_reduce(p.ws, pl.splits, cout, cin, 1, dw, st);
+  return launch_wgrad_reduce(p.ws, pl.splits, cout, cin, 1, dw, out_scale, out_scale_ptr, st);
 }
 
 bool tma_available() { return get_encode_fn() != nullptr; }

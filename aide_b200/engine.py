@@ -27,13 +27,14 @@ from . import _lib
 from ._lib import FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, call, lib
 
 # mode -> (operand format of forwards that keep a tape for backward, format of inference-only forwards)
-#   parity       fp32-equivalent split-precision tcgen05.  Training forwards/backwards: TF32X2 (3 kind::tf32 MMAs);
-#                forwards that never see a backward (AIDE's 4 augmented pseudo-label forwards per step, eval):
-#                F16X2 (3 kind::f16 MMAs on two fp16 planes: same 22-bit products, twice the tensor rate)
-#   parity_tf32  TF32X2 everywhere          parity_f16  F16X2 everywhere (forward only so far)
+#   parity       fp32-equivalent split-precision tcgen05, F16X2 everywhere: two fp16 planes of the power-of-two
+#                pre-scaled tensor, 3 kind::f16 MMAs (lo*hi + hi*lo + hi*hi) = 22-bit products at the full f16 tensor
+#                rate; gradients carry a per-tensor power-of-two scale chosen on the device (aide_bn_relu_bwd_apply)
+#   parity_tf32  TF32X2 everywhere (3 kind::tf32 MMAs at half the rate, twice the operand bytes)
+#   parity_mixed TF32X2 for the train forward/backward, F16X2 for forwards without a backward
 #   fast         single-pass BF16 (NOT a parity mode)      exact  fp32 CUDA cores
-MODES = {"exact": (FMT_F32, FMT_F32), "parity": (FMT_TF32X2, FMT_F16X2), "parity_tf32": (FMT_TF32X2, FMT_TF32X2),
-         "parity_f16": (FMT_F16X2, FMT_F16X2), "fast": (FMT_BF16, FMT_BF16)}
+MODES = {"exact": (FMT_F32, FMT_F32), "parity": (FMT_F16X2, FMT_F16X2), "parity_tf32": (FMT_TF32X2, FMT_TF32X2),
+         "parity_f16": (FMT_F16X2, FMT_F16X2), "parity_mixed": (FMT_TF32X2, FMT_F16X2), "fast": (FMT_BF16, FMT_BF16)}
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 
@@ -443,6 +444,7 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
     reserve("part", max_part)
     reserve("part2", max_part)
     reserve("ws", max_ws)
+    reserve("gscale", 16)          # [0] max |g| (bits), [1..2] = {s, 1/s}: dynamic power-of-two scale of an F16X2 dZ
     barena = torch.empty(cur, dtype=torch.uint8, device=arena.device)
     bb = barena.data_ptr()
 
@@ -481,18 +483,22 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             ss = base + layout.off["ss:" + u.name]
             mr = ss + 2 * u.cout * 4
             g, part, part2 = bb + off["g"], bb + off["part"], bb + off["part2"]
+            dyn = ufmt == FMT_F16X2
+            gmax = bb + off["gscale"] if dyn else None
+            dz_scale = bb + off["gscale"] + 4 if dyn else None
+            dz_inv = bb + off["gscale"] + 8 if dyn else None
             call("aide_bn_relu_bwd_reduce", z, ss, mr, N, h, w, u.cout, dptr, dct, dco, len(direct),
-                 pptr, pct, pco, len(pooled), g, part, st)
+                 pptr, pct, pco, len(pooled), g, part, gmax, st)
             rows = lib.aide_bn_bwd_rows(N, h, w, u.cout)
             dz0 = bb + off["dz"]
             dz1 = dz0 + _align(N * h * w * u.cout * _esize(ufmt)) if _planes(ufmt) == 2 else None
             call("aide_bn_relu_bwd_apply", ufmt, g, z, mr, params[u.bn + ".weight"].data_ptr(), part, rows,
                  N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"), gptr(u.conv + ".bias"),
-                 part2, st)
+                 part2, gmax, dz_scale, st)
             x0, x1, xct, xco = _view(layout, base, u.src[0], u.src[1])
-            call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, u.cout, N, h, w,
+            call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
                  bb + off["ws"], max_ws, gptr(u.conv + ".weight"), st)
             if not u.first:
                 w0, w1 = weights.dgrad(u, fmt)
-                call("aide_conv3x3_fwd", fmt, dz0, dz1, u.cout, 0, u.cout, w0, w1, None,
-                     bb + off["dx:" + u.name], u.cin, 0, u.cin, N, h, w, None, st)
+                call("aide_conv3x3_dgrad", fmt, dz0, dz1, u.cout, w0, w1, dz_inv,
+                     bb + off["dx:" + u.name], u.cin, 0, u.cin, N, h, w, st)

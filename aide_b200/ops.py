@@ -93,24 +93,37 @@ def conv3x3(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor], cin: Optional
     return z, part
 
 
-def conv3x3_dgrad(dz: Act, w: torch.Tensor) -> torch.Tensor:
+def _inv_scale(dz: Act, inv_scale):
+    """Device scalar 1/s for F16X2 gradient planes that hold dz*s; Act planes made by from_nchw carry the static
+    activation scale 2^8, i.e. s = 2^8."""
+    if dz.fmt != FMT_F16X2:
+        return None
+    if inv_scale is None:
+        inv_scale = torch.full((1,), 1.0 / 256.0, dtype=torch.float32, device=dz.planes.device)
+    return inv_scale
+
+
+def conv3x3_dgrad(dz: Act, w: torch.Tensor, inv_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dX [N,H,W,Cin] fp32 from dZ (operand format) and OIHW weights."""
     cout, cin = w.shape[:2]
     w0, w1, keep = weight_prep(w, dz.fmt, dgrad=True)
     dx = torch.empty((dz.N, dz.H, dz.W, cin), dtype=torch.float32, device=w.device)
-    call("aide_conv3x3_fwd", dz.fmt, dz.p0, dz.p1, dz.C, 0, cout, w0, w1, None, dx.data_ptr(), cin, 0, cin,
-         dz.N, dz.H, dz.W, None, _st())
+    inv = _inv_scale(dz, inv_scale)
+    call("aide_conv3x3_dgrad", dz.fmt, dz.p0, dz.p1, cout, w0, w1, inv.data_ptr() if inv is not None else None,
+         dx.data_ptr(), cin, 0, cin, dz.N, dz.H, dz.W, _st())
     return dx
 
 
-def conv3x3_wgrad(x: Act, dz: Act, cin: Optional[int] = None, coff: int = 0) -> torch.Tensor:
+def conv3x3_wgrad(x: Act, dz: Act, cin: Optional[int] = None, coff: int = 0,
+                  inv_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     cin = cin or x.C
     cout = dz.C
     nbytes = lib.aide_conv3x3_wgrad_workspace_bytes(x.fmt, cin, cout, x.N, x.H, x.W)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.planes.device)
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.planes.device)
-    call("aide_conv3x3_wgrad", x.fmt, x.p0, x.p1, x.C, coff, cin, dz.p0, dz.p1, cout, x.N, x.H, x.W,
-         ws.data_ptr(), nbytes, dw.data_ptr(), _st())
+    inv = _inv_scale(dz, inv_scale)
+    call("aide_conv3x3_wgrad", x.fmt, x.p0, x.p1, x.C, coff, cin, dz.p0, dz.p1,
+         inv.data_ptr() if inv is not None else None, cout, x.N, x.H, x.W, ws.data_ptr(), nbytes, dw.data_ptr(), _st())
     return dw
 
 

@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--mode", default=os.environ.get("AIDE_B200_MODE", "parity"),
-                    choices=["parity", "parity_tf32", "fast", "exact"])
+                    choices=["parity", "parity_tf32", "parity_mixed", "fast", "exact"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (slices per network per step)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -341,10 +341,10 @@ def main():
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "slices/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"parity": "split-precision tcgen05, fp32-equivalent products, fp32 accumulate: f16x2 (3 kind::f16 MMAs) "
-                            "for the pseudo-label forwards, tf32x2 (3 kind::tf32 MMAs) for the training forward/backward",
-                  "parity_tf32": "tf32x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
-                  "parity_f16": "f16x3 split-precision on tcgen05 (fp32-equivalent products, fp32 accumulate)",
+        "dtype": {"parity": "f16x2: split-precision tcgen05 (two fp16 planes, 3 kind::f16 MMAs per product = fp32-equivalent "
+                            "22-bit products), fp32 accumulate in TMEM; gradients with a device-chosen power-of-two scale",
+                  "parity_tf32": "tf32x2: split-precision tcgen05 (3 kind::tf32 MMAs per product), fp32 accumulate",
+                  "parity_mixed": "tf32x2 for the train forward/backward, f16x2 for the pseudo-label forwards",
                   "fast": "bf16 operands, fp32 accumulate (NOT a parity mode)", "exact": "f32 CUDA cores"}[args.mode],
         "data": "synthetic",
         "config": {"workload": "AIDE proposed step: 2x fuseunet, 4 augmented forwards + train forward + backward per net, "

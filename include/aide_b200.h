@@ -74,11 +74,19 @@ int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
  * {cout tile, pixel tiles per CTA iteration, accumulators per tile, TMEM buffers, smem row bytes, halo stages,
  *  weight stages, dynamic smem bytes}.  Returns non-zero when the layer runs on the first-generation kernel. */
 int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out);
+/* dX[n,h,w,ci] = sum_{tap,co} dz[n,h+dy,w+dx,co] * w[co][ci][flipped tap]  (ATen conv backward-data): the forward
+ * kernel on dgrad-prepared weights (aide_weight_prep).  dz is a plain [N,H,W,cout] operand-format buffer, dx an fp32
+ * NHWC view.  dz_inv_scale: device pointer to 1/s where the dz planes hold dz*s (AIDE_FMT_F16X2 gradients are stored
+ * with a power-of-two scale chosen on the device by aide_bn_relu_bwd_apply); NULL for the other formats. */
+int aide_conv3x3_dgrad(int fmt, const void* dz_p0, const void* dz_p1, int cout, const void* w_p0, const void* w_p1,
+                       const float* dz_inv_scale, float* dx, int dx_ctot, int dx_coff, int cin, int N, int H, int W,
+                       void* stream);
 /* dW[co,ci,ky,kx] = sum_{n,h,w} dz[n,h,w,co] * x[n,h+ky-1,w+kx-1,ci]  (ATen conv backward-filter).
- * dz is a plain [N,H,W,cout] operand-format buffer.  Result written (not accumulated) as OIHW fp32. */
+ * dz is a plain [N,H,W,cout] operand-format buffer (dz_inv_scale as above).  Result written (not accumulated) as
+ * OIHW fp32. */
 size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
 int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
-                       const void* dz_p0, const void* dz_p1, int cout, int N, int H, int W,
+                       const void* dz_p0, const void* dz_p1, const float* dz_inv_scale, int cout, int N, int H, int W,
                        void* workspace, size_t workspace_bytes, float* dw_oihw, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +MaxPool2d(2,2), +concat slot) (netblocks.py:25,27,28; fuseunet.py:13-31) */
@@ -106,15 +114,18 @@ int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift, const floa
                             int N, int H, int W, int C,
                             const float* const* direct_ptr, const int* direct_ctot, const int* direct_coff, int n_direct,
                             const float* const* pool_ptr, const int* pool_ctot, const int* pool_coff, int n_pool,
-                            float* g, float* partial, void* stream);
+                            float* g, float* partial, float* gmax /* nullable: device scalar <- max |g| */, void* stream);
 /* backward, stage 2: sums = fixed-order reduction of `partial`; dgamma = sum g*xhat, dbeta = sum g,
  * dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) stored in operand format [N,H,W,C];
  * dbias_conv = sum dz (mathematically 0 under train-mode BN; kept for fidelity).
- * partial2: scratch [rows][C] fp32 (rows as above). */
+ * partial2: scratch [rows][C] fp32 (rows as above).
+ * AIDE_FMT_F16X2: the dz planes hold dz*s, s a power of two derived on the device from `gmax` (the reduce stage's
+ * max |g|) and the channel statistics; dz_scale[2] receives {s, 1/s} for aide_conv3x3_dgrad / _wgrad.  Both may be
+ * NULL for the other formats. */
 int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd, const float* gamma,
                            const float* partial, int rows, int N, int H, int W, int C,
                            void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
-                           float* partial2, void* stream);
+                           float* partial2, const float* gmax, float* dz_scale, void* stream);
 
 /* ---- nn.Upsample(scale_factor=2, bilinear, align_corners=True) (netblocks.py:16) ---------------- */
 int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,

@@ -97,7 +97,7 @@ def test_bn_finalize_folds_many_rows(dev):
     assert relmax(ss[0], gamma.double() / torch.sqrt(var + 1e-5)) < 1e-6
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_conv3x3_dgrad_wgrad(dev, fmt, shape):
     from aide_b200 import ops
@@ -113,18 +113,23 @@ def test_conv3x3_dgrad_wgrad(dev, fmt, shape):
     assert relmax(dw, ref_dw) < TOL[fmt], "wgrad " + NAMES[fmt]
 
 
-@pytest.mark.parametrize("shape", CONV_SHAPES)
-def test_conv3x3_f16x2_dgrad(dev, shape):
-    """F16X2 is forward-only in the engine so far; the same kernel already computes dgrad for in-range gradients."""
+@pytest.mark.parametrize("mag", [1e-6, 30.0])
+def test_conv3x3_f16x2_backward_with_gradient_scale(dev, mag):
+    """F16X2 gradient planes hold dz*s (s a device-side power of two); dgrad/wgrad multiply 1/s back in."""
     from aide_b200 import ops
-    N, H, W, cin, cout = shape
-    w, dz = rnd(cout, cin, 3, 3, seed=5, scale=(9 * cin) ** -0.5), rnd(N, cout, H, W, seed=6)
-    ref_dx = torch.nn.grad.conv2d_input((N, cin, H, W), w, dz, padding=1)
-    dx = ops.nhwc_to_nchw(ops.conv3x3_dgrad(ops.from_nchw(dz.to(dev), 3), w.to(dev)))
-    assert relmax(dx, ref_dx) < TOL[3]
+    N, H, W, cin, cout = 2, 16, 24, 64, 128
+    x, w = rnd(N, cin, H, W, seed=4), rnd(cout, cin, 3, 3, seed=5, scale=(9 * cin) ** -0.5)
+    dz = rnd(N, cout, H, W, seed=6) * mag
+    s_ = 2.0 ** round(float(torch.log2(torch.tensor(1024.0 / (4.5 * mag)))))      # max|dz|*s ~ 2^10
+    dza = ops.from_nchw((dz * (s_ / 256.0)).to(dev), 3)                             # from_nchw multiplies by 2^8
+    inv = torch.full((1,), 1.0 / s_, device=dev)
+    dx = ops.nhwc_to_nchw(ops.conv3x3_dgrad(dza, w.to(dev), inv_scale=inv))
+    dw = ops.conv3x3_wgrad(ops.from_nchw(x.to(dev), 3), dza, inv_scale=inv)
+    assert relmax(dx, torch.nn.grad.conv2d_input(x.shape, w, dz, padding=1)) < TOL[3]
+    assert relmax(dw, torch.nn.grad.conv2d_weight(x, w.shape, dz, padding=1)) < TOL[3]
 
 
-@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("fmt", [1, 2, 3])
 def test_conv3x3_channel_views(dev, fmt):
     """conv reading a channel slice of a wider buffer and writing... (zero-copy concat, fuseunet.py:49-55)."""
     from aide_b200 import ops
@@ -137,7 +142,7 @@ def test_conv3x3_channel_views(dev, fmt):
     assert relmax(dw, torch.nn.grad.conv2d_weight(x[:, 64:96], w.shape, dz, padding=1)) < TOL[fmt]
 
 
-@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("fmt", [1, 2, 3])
 def test_conv_adjoint_identity_full_size(dev, fmt):
     """Size-independent property at a BASELINE-sized layer (B=4, 128x128, 128->64):
     <conv(x,w), dz> == <x, dgrad(dz,w)> == <w, wgrad(x,dz)>."""
@@ -152,7 +157,7 @@ def test_conv_adjoint_identity_full_size(dev, fmt):
     a = (z.double() * dza.float().double()).sum().item()
     b = (ops.conv3x3_dgrad(dza, w).double() * xa.float().double()).sum().item()
     c = (ops.conv3x3_wgrad(xa, dza).double() * w.double()).sum().item()
-    tol = 1e-5 if fmt == 1 else 2e-2
+    tol = 1e-5 if fmt != 2 else 2e-2
     scale = (z.double().norm() * dza.float().double().norm()).item()
     assert abs(a - b) < tol * scale and abs(a - c) < tol * scale, (a, b, c)
 
@@ -179,9 +184,13 @@ def test_bn_relu_pool_forward(dev, fmt, training):
     assert relmax(rmd, rm_ref) < 1e-5 and relmax(rvd, rv_ref) < 1e-5
 
 
-@pytest.mark.parametrize("fmt", [0, 1])
-def test_bn_relu_pool_backward(dev, fmt):
-    """g routing: one same-resolution source + two pooled sources (the modal-2 level-1 pattern)."""
+@pytest.mark.parametrize("gscale", [1.0, 3e-7, 2e3])
+@pytest.mark.parametrize("fmt", [0, 1, 3])
+def test_bn_relu_pool_backward(dev, fmt, gscale):
+    """g routing: one same-resolution source + two pooled sources (the modal-2 level-1 pattern).  F16X2 stores dZ
+    with a power-of-two scale chosen on the device: exercised with tiny and huge upstream gradients."""
+    if fmt != 3 and gscale != 1.0:
+        pytest.skip("gradient magnitude only matters for the dynamically scaled format")
     from aide_b200 import ops
     from aide_b200._lib import call, lib
     import ctypes as C
@@ -190,7 +199,8 @@ def test_bn_relu_pool_backward(dev, fmt):
     gamma, beta = (rnd(Cc, seed=2).abs() + 0.5).requires_grad_(), rnd(Cc, seed=3).requires_grad_()
     y = F.relu(F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5))
     p = F.max_pool2d(y, 2, 2)
-    gd, gp1, gp2 = rnd(N, 64, H, W, seed=4), rnd(N, 64, H // 2, W // 2, seed=5), rnd(N, Cc, H // 2, W // 2, seed=6)
+    gd, gp1, gp2 = (rnd(N, 64, H, W, seed=4) * gscale, rnd(N, 64, H // 2, W // 2, seed=5) * gscale,
+                    rnd(N, Cc, H // 2, W // 2, seed=6) * gscale)
     loss = (y * gd[:, 16:48]).sum() + (p * gp1[:, 32:64]).sum() + (p * gp2).sum()
     dz_ref, dg_ref, db_ref = torch.autograd.grad(loss, [z, gamma, beta])
     st = torch.cuda.current_stream().cuda_stream
@@ -206,14 +216,23 @@ def test_bn_relu_pool_backward(dev, fmt):
     part2 = torch.empty(rows, Cc, device=dev)
     dptr, dct, dco = (C.c_void_p * 3)(d0.data_ptr()), (C.c_int * 3)(64), (C.c_int * 3)(16)
     pptr, pct, pco = (C.c_void_p * 3)(p0.data_ptr(), p1.data_ptr()), (C.c_int * 3)(64, Cc), (C.c_int * 3)(32, 0)
+    gs = torch.zeros(4, device=dev)             # [0] max|g| bits, [1] s, [2] 1/s
+    dyn = fmt == 3
     call("aide_bn_relu_bwd_reduce", zd.data_ptr(), ss.data_ptr(), mr.data_ptr(), N, H, W, Cc, dptr, dct, dco, 1,
-         pptr, pct, pco, 2, g.data_ptr(), part1.data_ptr(), st)
+         pptr, pct, pco, 2, g.data_ptr(), part1.data_ptr(), gs[0:].data_ptr() if dyn else None, st)
     dz = ops.Act(N, H, W, Cc, fmt, dev)
     small = torch.empty(3, Cc, device=dev)
     call("aide_bn_relu_bwd_apply", fmt, g.data_ptr(), zd.data_ptr(), mr.data_ptr(), gamma.detach().to(dev).data_ptr(),
          part1.data_ptr(), rows, N, H, W, Cc, dz.p0, dz.p1, small[1].data_ptr(), small[0].data_ptr(),
-         small[2].data_ptr(), part2.data_ptr(), st)
-    assert relmax(ops.to_nchw(dz), dz_ref) < 5e-5
+         small[2].data_ptr(), part2.data_ptr(), gs[0:].data_ptr() if dyn else None, gs[1:].data_ptr() if dyn else None, st)
+    got = ops.to_nchw(dz)
+    if dyn:
+        s_, inv = gs[1].item(), gs[2].item()
+        assert s_ > 0 and abs(s_ * inv - 1.0) < 1e-6 and abs(torch.tensor(s_).log2().item() % 1.0) < 1e-6   # power of two
+        assert abs(gs[0:1].view(torch.int32).view(torch.float32).item() - g.abs().max().item()) == 0.0
+        got = got * 256.0 * inv                     # Act.to_nchw divides by the static activation scale 2^8
+        assert (got.abs().max() * s_).item() < 65504 / 4      # head-room of the bound
+    assert relmax(got, dz_ref) < 5e-5
     assert relmax(small[1], dg_ref) < 5e-5 and relmax(small[0], db_ref) < 5e-5
     assert small[2].abs().max().item() < 1e-4 * dz_ref.abs().max().item() * N * H * W   # sum dz == 0 analytically
 

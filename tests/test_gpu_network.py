@@ -21,7 +21,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = {"exact": 1e-4, "parity": 2e-4, "fast": 2.5e-1}    # measured: exact 2e-5, parity 5e-5..6e-5
+LOGIT_TOL = {"exact": 1e-4, "parity": 2e-4, "parity_tf32": 2e-4, "fast": 2.5e-1}    # measured: exact 2e-5, parity 5e-5..6e-5
 
 
 def relmax(a, b):
@@ -83,7 +83,7 @@ def fwd_oracle(oracle, kind, p, xs, training=True):
     return oracle.fuseunet_forward(p, *xs, training=training) if kind == "fuse" else oracle.unet_forward(p, xs[0], training=training)
 
 
-@pytest.mark.parametrize("mode", ["exact", "parity"])
+@pytest.mark.parametrize("mode", ["exact", "parity", "parity_tf32"])
 @pytest.mark.parametrize("kind", ["fuse", "unet"])
 @pytest.mark.parametrize("tag,shape", [("s32", (2, 32, 32)), ("s48x64", (3, 48, 64))])
 def test_forward_backward_vs_golden_and_oracle(golden, oracle, mode, kind, tag, shape):
