@@ -23,6 +23,11 @@ int halo_stat_rows(int N, int H, int W);
 int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
                  const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
                  float out_scale, const float* out_scale_ptr, cudaStream_t st);
+bool wgrad_halo_ok(int fmt, int cin, int cout, int N, int H, int W);
+size_t wgrad_halo_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
+int wgrad_halo(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
+               int cout, int N, int H, int W, void* ws, size_t ws_bytes, float* dw, float out_scale,
+               const float* out_scale_ptr, cudaStream_t st);
 bool tma_available();
 bool c3_shape_ok(int cin, int cout);
 int c3_stat_rows(int N, int H, int W);
@@ -95,6 +100,7 @@ extern "C" size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout,
   if (fmt == AIDE_FMT_F32 && c3_shape_ok(cin, cout)) return c3_wgrad_workspace_bytes(cout, N, H, W);
   if (fmt == AIDE_FMT_F32) return simt_wgrad_workspace_bytes(cin, cout, N, H, W);
   if (!tc_shape_ok(fmt, cin, cout)) return 0;
+  if (wgrad_halo_ok(fmt, cin, cout, N, H, W)) return wgrad_halo_workspace_bytes(fmt, cin, cout, N, H, W);
   return tc_wgrad_workspace_bytes(fmt, cin, cout, N, H, W);
 }
 
@@ -114,6 +120,10 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
   AIDE_REQUIRE(fmt != AIDE_FMT_F16X2 || dz_inv_scale, "conv3x3_wgrad: F16X2 needs the gradient's inverse scale");
   AIDE_REQUIRE(tc_shape_ok(fmt, cin, cout), "conv3x3_wgrad: tcgen05 path needs cin %% 32 == 0 and cout %% 32 == 0");
   // F16X2: x planes carry 2^8, dZ planes carry the dynamic scale s -> dW = acc * 2^-8 * (1/s)
+  if (wgrad_halo_ok(fmt, cin, cout, N, H, W))
+    return wgrad_halo(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes, dw_oihw,
+                      fmt == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr,
+                      as_stream(stream));
   return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes, dw_oihw,
                   fmt == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr,
                   as_stream(stream));

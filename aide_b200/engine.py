@@ -282,16 +282,31 @@ def _view(layout: Layout, base: int, name: str, coff: int):
 
 
 def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], weights: PreparedWeights,
-                inputs: Sequence[torch.Tensor], training: bool, logits: torch.Tensor,
-                arena: torch.Tensor) -> None:
+                inputs: Sequence, training: bool, logits: torch.Tensor, arena: torch.Tensor, groups: int = 1) -> None:
+    """One forward pass.  groups > 1: `inputs` is a list of `groups` input tuples (the AIDE step's augmented views,
+    trainchaos_proposed_30cases1labeled.py:265-269) stacked along the batch: every convolution / upsample / the head
+    run ONCE on the stacked batch, while BatchNorm statistics, the running-statistics updates and the normalisation
+    stay per group, in order -- exactly what `groups` separate forward calls compute (only for forwards that keep no
+    tape: the per-unit scale/shift scratch is reused from group to group)."""
     N, H, W, fmt = layout.N, layout.H, layout.W, layout.fmt
+    G = groups
+    Ng = N // G
     base = arena.data_ptr()
     st = _stream()
+
+    def gview(name, coff, lvl, g):
+        """channel view of buffer `name`, advanced to the first image of group g"""
+        p0, p1, ctot, co = _view(layout, base, name, coff)
+        skip = g * Ng * (H >> lvl) * (W >> lvl) * ctot * _esize(layout.buf_fmt(name))
+        return p0 + skip, (p1 + skip if p1 is not None else None), ctot, co
+
     for op in plan.ops:
         if isinstance(op, tuple) and op[0] == "input":
             _, i, name = op
-            p0, p1, ctot, _ = _view(layout, base, name, 0)
-            call("aide_nchw_to_nhwc", FMT_F32, inputs[i].data_ptr(), p0, None, ctot, 0, N, 3, H, W, st)
+            for g in range(G):
+                src = inputs[g][i] if G > 1 else inputs[i]
+                p0, p1, ctot, _ = gview(name, 0, 0, g)
+                call("aide_nchw_to_nhwc", FMT_F32, src.data_ptr(), p0, None, ctot, 0, Ng, 3, H, W, st)
         elif isinstance(op, Unit):
             u = op
             h, w = H >> u.level, W >> u.level
@@ -303,14 +318,16 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             ss = base + layout.off["ss:" + u.name]
             call("aide_conv3x3_fwd", ufmt, x0, x1, xct, xco, u.cin, w0, w1, params[u.conv + ".bias"].data_ptr(),
                  z, u.cout, 0, u.cout, N, h, w, stp if training else None, st)
-            call("aide_bn_finalize", stp, layout.stat_rows[u.name], u.cout, float(N * h * w),
-                 params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
-                 params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
-                 BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + 2 * u.cout * 4, st)
-            d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
-            pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
-            pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
-            call("aide_bn_relu_apply", fmt, z, N, h, w, u.cout, ss, *d, *pa, *pb, st)
+            rows_g = layout.stat_rows[u.name] // G
+            for g in range(G):
+                call("aide_bn_finalize", stp + g * rows_g * 2 * u.cout * 4, rows_g, u.cout, float(Ng * h * w),
+                     params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
+                     params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
+                     BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + 2 * u.cout * 4, st)
+                d = gview(u.dst[0], u.dst[1], u.level, g) if u.dst else (None, None, 0, 0)
+                pa = gview(u.pools[0][0], u.pools[0][1], u.level + 1, g) if len(u.pools) > 0 else (None, None, 0, 0)
+                pb = gview(u.pools[1][0], u.pools[1][1], u.level + 1, g) if len(u.pools) > 1 else (None, None, 0, 0)
+                call("aide_bn_relu_apply", fmt, z + g * Ng * h * w * u.cout * 4, Ng, h, w, u.cout, ss, *d, *pa, *pb, st)
         elif isinstance(op, Upsample):
             h, w = H >> op.level, W >> op.level
             s = _view(layout, base, op.src, 0)

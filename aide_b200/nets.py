@@ -124,10 +124,28 @@ class _EngineNet(nn.Module):
             raise RuntimeError(f"module is on {p.device}, inputs on {x0.device}")
 
     # ---- engine calls --------------------------------------------------------------------------
-    def _engine_forward(self, inputs, keep_tape: bool):
+    def _engine_forward_grouped(self, views):
+        """`views`: list of input tuples of identical shape (the augmented views of one AIDE step).  Equivalent to
+        [self._engine_forward(v, keep_tape=False)[0] for v in views] -- same BatchNorm statistics per view, same
+        order of running-statistics updates -- but every convolution runs once on the stacked batch (more tiles per
+        launch: better SM occupancy on the deep, small feature maps; a quarter of the launches).  Returns the list of
+        per-view logits (views of one [G*B,K,H,W] tensor)."""
+        G = len(views)
+        if G == 1:
+            return [self._engine_forward(views[0], keep_tape=False)[0]]
+        for v in views:
+            self._check_inputs(v)
+            if v[0].shape != views[0][0].shape:
+                raise ValueError("grouped forward needs identically shaped views")
+        logits, _ = self._engine_forward(views, keep_tape=False, groups=G)
+        return list(logits.chunk(G, dim=0))
+
+    def _engine_forward(self, inputs, keep_tape: bool, groups: int = 1):
         plan = self._plan
         fmt = E.mode_format(self.engine_mode, keep_tape)
-        N, _, H, W = inputs[0].shape
+        first = inputs[0][0] if groups > 1 else inputs[0]
+        N, _, H, W = first.shape
+        N *= groups
         key = (N, H, W, fmt)
         layout = self._layouts.get(key)
         if layout is None:
@@ -142,7 +160,7 @@ class _EngineNet(nn.Module):
         wts = self._weights.get(fmt)
         if wts is None or wts.key != wkey or (need_dgrad and not wts.has_dgrad):
             wts = self._weights[fmt] = E.PreparedWeights(plan, named, fmt, need_dgrad)
-        dev = inputs[0].device
+        dev = first.device
         if keep_tape:
             arena = torch.empty(layout.total, dtype=torch.uint8, device=dev)
         else:
@@ -150,10 +168,13 @@ class _EngineNet(nn.Module):
                 self._scratch = torch.empty(layout.total, dtype=torch.uint8, device=dev)
             arena = self._scratch
         logits = torch.empty((N, plan.num_classes, H, W), dtype=torch.float32, device=dev)
-        xs = [x.detach().contiguous() for x in inputs]
-        E.run_forward(plan, layout, named, wts, xs, training, logits, arena)
+        if groups > 1:
+            xs = [[x.detach().contiguous() for x in v] for v in inputs]
+        else:
+            xs = [x.detach().contiguous() for x in inputs]
+        E.run_forward(plan, layout, named, wts, xs, training, logits, arena, groups)
         if training:
-            torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], 1)
+            torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], groups)
         tape = None
         if keep_tape:
             tape = E.Tape()

@@ -68,6 +68,8 @@ class AideTrainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
+        self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
         self.two_streams = two_streams
         if two_streams:
             self.s1, self.s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
@@ -147,7 +149,10 @@ class AideTrainer:
             if self.flavour != "chaos":
                 net.eval()
             with torch.no_grad():
-                a = [net._engine_forward(self._inputs(v), keep_tape=False)[0] for v in augs]
+                if self.group_augs and len(augs) > 1:
+                    a = net._engine_forward_grouped([self._inputs(v) for v in augs])
+                else:
+                    a = [net._engine_forward(self._inputs(v), keep_tape=False)[0] for v in augs]
             net.train(was_training)
             if a:
                 me["q"], me["w"] = L.pseudo_label(a, self.temperature, self.flavour)

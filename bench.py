@@ -192,6 +192,7 @@ def conv_roofline(fmt, B, S, device, peaks):
         tot_ms += ms * count
         del x, z, part
     achieved = tot_flop / tot_ms / 1e9
+    traffic, traffic_note = conv_traffic(fmt, B, S, rows)
     peak = peaks.get("bf16_tflops")
     src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
     if peak is None:
@@ -200,7 +201,9 @@ def conv_roofline(fmt, B, S, device, peaks):
     ceiling = {1: peak / 6.0, 2: peak, 3: peak / 3.0}.get(fmt, peak)
     return dict(bound="tensor", kernel=f"conv3x3_fwd_tc_kernel<{FMT_NAMES[fmt]}> (persistent tcgen05 implicit GEMM; "
                                        "dgrad is the same kernel)",
-                achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4), traffic=None,
+                achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4), traffic=traffic,
+                traffic_note=traffic_note, launches=int(sum(r["launches_per_fwd"] for r in rows)),
+                algorithmic_gflop_per_launch=round(tot_flop / 1e9 / sum(r["launches_per_fwd"] for r in rows), 2),
                 peak_source=src, operand_format=FMT_NAMES[fmt], mma_passes=passes,
                 frac_of_format_ceiling=round(achieved / ceiling, 4),
                 note=("algorithmic conv FLOPs (2*B*H*W*Cout*Cin*9) of one fuseunet forward's tensor-core layers / summed "
@@ -208,6 +211,29 @@ def conv_roofline(fmt, B, S, device, peaks):
                       "issue 3 MMAs per algorithmic product: f16x2 at the bf16 rate (ceiling peak/3), tf32x2 at half of "
                       "it (ceiling peak/6)"),
                 layers=rows)
+
+
+def conv_traffic(fmt, B, S, rows):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch, averaged over the launches of one forward,
+    from the committed ncu capture of tools/profile_conv.py (profiles/conv_traffic.json); None if the capture does
+    not cover this format / batch / size."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    try:
+        cap = json.load(open(path))
+    except (OSError, ValueError):
+        return None, "no ncu capture committed"
+    ent = cap.get(f"{FMT_NAMES[fmt]}:B{B}:S{S}")
+    if not ent:
+        return None, f"profiles/conv_traffic.json has no capture for {FMT_NAMES[fmt]} at batch {B}, {S}x{S}"
+    tot, n = 0.0, 0
+    for r in rows:
+        b = ent.get(f"{r['cin']},{r['cout']},{r['hw']}")
+        if b is None:
+            return None, "capture incomplete"
+        tot += b * r["launches_per_fwd"]
+        n += r["launches_per_fwd"]
+    return round(tot / n), ("average DRAM bytes per conv launch over the %d launches of one forward, ncu "
+                            "dram__bytes_read.sum + dram__bytes_write.sum (profiles/conv_traffic.json)" % n)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -375,6 +401,18 @@ def main():
         if args.roofline_json:
             with open(args.roofline_json, "w") as f:
                 json.dump(dict(mode=args.mode, batch=B, size=S, summary=rl, layers=layers), f, indent=1)
+        if world == 1 and not args.no_extras:
+            # R_train: forward + backward + Adam of both nets only (no pseudo-label forwards, no
+            # consistency term) = 697.2 GFLOP per slice; context for BASELINE.json's 1000 slices/s target
+            def train_only(i):
+                b = dev_batches[i % n_pool]
+                tr.step(b["x"], b["t1"], b["t2"], [], 0.25)
+            for i in range(3):
+                train_only(i)
+            ms_t = timed_steps(train_only, K, world, device)
+            out["train_only"] = dict(value=round(B * K / (ms_t / 1e3), 3), unit="slices/s", ms_per_step=round(ms_t / K, 3),
+                                     algorithmic_tflops=round(B * K / (ms_t / 1e3) * 6 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2 / 1e3, 1),
+                                     note="train forward + backward + Adam of both nets, no augmented forwards (R_train)")
         if world == 1 and not args.no_extras and args.mode != "fast":
             del tr
             torch.cuda.empty_cache()
@@ -382,7 +420,11 @@ def main():
             for i in range(3):
                 dev_step(i)
             ms_f = timed_steps(dev_step, K, world, device)
+            for i in range(3):
+                train_only(i)
+            ms_ft = timed_steps(train_only, K, world, device)
             out["fast_mode"] = dict(value=round(B * K / (ms_f / 1e3), 3), unit="slices/s", ms_per_step=round(ms_f / K, 3),
+                                    train_only=round(B * K / (ms_ft / 1e3), 3),
                                     note="single-pass bf16 operands; fails the 1e-3 logit parity bar (SURVEY.md 8d), "
                                          "reported for context only")
         if world == 1 and not args.no_cpu_baseline:

@@ -308,3 +308,31 @@ def test_teacher_forced_training_steps(oracle):
         oracle.adam_amsgrad_step(p1, r["grads1"], st1, step)
         oracle.adam_amsgrad_step(p2, r["grads2"], st2, step)
     print(f"teacher-forced {steps} steps @ {size}: worst |dDice_fn/B| {worst_dice:.2e}, worst logit rel {worst_logit:.2e}")
+
+
+@pytest.mark.parametrize("kind,training", [("fuse", True), ("unet", True), ("fuse", False)])
+def test_grouped_augmented_forward_equals_sequential_forwards(oracle, kind, training):
+    """The AIDE step's 4 augmented forwards per net (trainchaos_proposed_30cases1labeled.py:265-269) run as ONE
+    stacked-batch forward with per-view BatchNorm statistics: logits, running statistics and num_batches_tracked must
+    match 4 separate forward calls (different tile shapes -> not bit-identical, fp32 summation-order level)."""
+    dev = torch.device("cuda:0")
+    B, S, G = 3, 64, 4
+    a, b = build(kind, "parity", dev), build(kind, "parity", dev)
+    b.load_state_dict(a.state_dict())
+    a.train(training)
+    b.train(training)
+    g = torch.Generator().manual_seed(11)
+    n_in = 2 if kind == "fuse" else 1
+    views = [tuple(torch.randn(B, 3, S, S, generator=g).to(dev) for _ in range(n_in)) for _ in range(G)]
+    with torch.no_grad():
+        seq = [a(*v) for v in views]
+        grp = b._engine_forward_grouped(views)
+    torch.cuda.synchronize()
+    for s_, g_ in zip(seq, grp):
+        assert relmax(g_, s_) < 2e-5
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) == (G if training else 0)
+        elif "running" in k:
+            assert relmax(sb[k], sa[k]) < 1e-5, k

@@ -87,5 +87,38 @@ def full(src: str, out: str) -> None:
     print(f"wrote {out}.csv ({len(data)} launches)")
 
 
+def traffic(src: str, out: str) -> None:
+    """`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv` log of `tools/profile_conv.py --reps 1
+    --layers ...` -> profiles/conv_traffic.json entry.  Extra argv: key (e.g. f16x2:B8:S256) then the layer specs in
+    launch order."""
+    import json
+    import os
+    key, layers = sys.argv[4], sys.argv[5:]
+    per = []
+    with open(src) as f:
+        for line in f:
+            if line.startswith('"ID"'):
+                break
+        cur = {}
+        for r in csv.reader(f):
+            if len(r) < 15 or "conv3x3" not in r[4]:
+                continue
+            v = float(r[14].replace(",", ""))
+            unit = r[13].lower()
+            v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+            cur.setdefault(int(r[0]), 0.0)
+            cur[int(r[0])] += v
+        per = [cur[k] for k in sorted(cur)]
+    if len(per) != len(layers):
+        raise SystemExit(f"{len(per)} conv launches in the log, {len(layers)} layer specs")
+    data = {}
+    if os.path.exists(out):
+        data = json.load(open(out))
+    data[key] = {",".join(l.split(",")[:3]): round(b) for l, b in zip(layers, per)}
+    with open(out, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+    print(f"wrote {out}: {key} ({len(per)} layers, {sum(per) / 1e6:.1f} MB total)")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
