@@ -41,20 +41,24 @@ int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* 
 // then walks only the folded rows.  Fixed order throughout: bit-reproducible run to run.
 constexpr int kStatChunk = 64;
 
+constexpr int kStatLanes = 32;   // row lanes per block: these kernels are latency bound (a handful of dependent loads)
+
 __global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int cols /* = 2*C */) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kStatLanes][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * kStatChunk;
   const int r1 = min(rows, r0 + kStatChunk);
   double acc = 0.0;
-  if (j < cols)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)partial[(size_t)r * cols + j];
+  if (j < cols) {
+#pragma unroll 2
+    for (int r = r0 + threadIdx.y; r < r1; r += kStatLanes) acc += (double)partial[(size_t)r * cols + j];
+  }
   sm[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && j < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    for (int k = 0; k < kStatLanes; ++k) t += sm[k][threadIdx.x];
     const float hi = (float)t;
     partial[(size_t)r0 * cols + j] = hi;
     if (r0 + 1 < rows) partial[(size_t)(r0 + 1) * cols + j] = (float)(t - (double)hi);
@@ -67,11 +71,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float momentum, float eps, int training,
                                    float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
-  __shared__ double s1[8][33], s2[8][33];
+  __shared__ double s1[kStatLanes][33], s2[kStatLanes][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
   if (training && c < C) {
-    for (int g = threadIdx.y; g < groups; g += 8) {
+#pragma unroll 4
+    for (int g = threadIdx.y; g < groups; g += kStatLanes) {
       for (int k = 0; k < sub; ++k) {
         const int r = g * row_stride + k;
         if (r < rows) {
@@ -89,7 +94,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups
   if (training) {
     double sa = 0.0, sb = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < kStatLanes; ++k) {
       sa += s1[k][threadIdx.x];
       sb += s2[k][threadIdx.x];
     }
@@ -415,7 +420,7 @@ extern "C" int aide_bn_finalize(float* stat_partial, int rows, int C, double cou
   AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift, "bn_finalize: bad arguments");
   AIDE_REQUIRE(training ? (stat_partial && rows > 0 && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics input");
-  dim3 block(32, 8), grid(ceil_div(C, 32));
+  dim3 block(32, kStatLanes), grid(ceil_div(C, 32));
   int groups = rows, row_stride = 1, sub = 1;
   if (training && rows > 2 * kStatChunk) {   // many tiles: fold chunks in parallel first (in place)
     groups = ceil_div(rows, kStatChunk);

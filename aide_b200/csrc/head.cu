@@ -50,6 +50,71 @@ __global__ void conv1x1_fwd_kernel(CView x, int C, const float* __restrict__ w, 
   }
 }
 
+// 16-bit operand planes (F16X2 / BF16), K == 2, C == 8 * LP with LP a power of two <= 32: each lane owns 8 channels
+// (one 128-bit load per plane), keeps its 2 x 8 weights in registers, LP lanes finish a pixel with log2(LP) shuffles.
+template <int FMT, int LP>
+__global__ void conv1x1_fwd16_kernel(CView x, const float* __restrict__ w, const float* __restrict__ bias,
+                                     float* __restrict__ out, size_t npix, int HW) {
+  constexpr int C = 8 * LP, PW = 32 / LP;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LP, l = lane % LP;
+  const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float w0[8], w1[8];
+  constexpr float inv = FMT == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f;      // fold the activation prescale into w
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    w0[k] = __ldg(w + l * 8 + k) * inv;
+    w1[k] = __ldg(w + C + l * 8 + k) * inv;
+  }
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
+  for (size_t base = warp * PW; base < npix; base += nwarps * PW) {
+    const size_t pix = base + sub;
+    const bool valid = pix < npix;
+    float a0 = 0.f, a1 = 0.f;
+    if (valid) {
+      const size_t e = pix * x.ctot + x.coff + l * 8;
+      float v[8];
+      if constexpr (FMT == AIDE_FMT_F16X2) {
+        const uint4 rh = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x.p0) + e);
+        const uint4 rl = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x.p1) + e);
+        const __half2* h = reinterpret_cast<const __half2*>(&rh);
+        const __half2* lo = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 p = __half22float2(h[k]), q = __half22float2(lo[k]);
+          v[2 * k] = p.x + q.x;
+          v[2 * k + 1] = p.y + q.y;
+        }
+      } else {
+        const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x.p0) + e);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 p = __bfloat1622float2(h[k]);
+          v[2 * k] = p.x;
+          v[2 * k + 1] = p.y;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a0 += v[k] * w0[k];
+        a1 += v[k] * w1[k];
+      }
+    }
+#pragma unroll
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (valid && l == 0) {
+      const size_t n = pix / HW, hw = pix % HW;
+      out[(n * 2 + 0) * HW + hw] = a0 + b0;
+      out[(n * 2 + 1) * HW + hw] = a1 + b1;
+    }
+  }
+}
+
 // blockDim = (cx, ty), grid = (rows, cgroups); each thread owns 4 channels.
 template <int FMT>
 __global__ void conv1x1_bwd_kernel(CView x, int C, const float* __restrict__ w, const float* __restrict__ dl, int K,
@@ -127,9 +192,20 @@ extern "C" int aide_conv1x1_fwd(int fmt, const void* x_p0, const void* x_p1, int
   AIDE_REQUIRE(x_p0 && w && logits_nchw && C % 4 == 0 && x_coff % 4 == 0 && K >= 1 && K <= kMaxK,
                "conv1x1_fwd: bad arguments (C%%4==0, 1<=K<=%d)", kMaxK);
   CView x{x_p0, x_p1, x_ctot, x_coff};
+  size_t npix = (size_t)N * H * W;
+  if ((fmt == AIDE_FMT_F16X2 || fmt == AIDE_FMT_BF16) && K == 2 && C == 64 && x_ctot % 8 == 0 && x_coff % 8 == 0) {
+    size_t warps16 = (npix + 3) / 4;
+    long long blocks16 = (long long)((warps16 + 7) / 8);
+    if (blocks16 > kNumSMs * 16) blocks16 = kNumSMs * 16;
+    if (fmt == AIDE_FMT_F16X2)
+      conv1x1_fwd16_kernel<AIDE_FMT_F16X2, 8><<<(int)blocks16, 256, 0, as_stream(stream)>>>(x, w, bias, logits_nchw, npix, H * W);
+    else
+      conv1x1_fwd16_kernel<AIDE_FMT_BF16, 8><<<(int)blocks16, 256, 0, as_stream(stream)>>>(x, w, bias, logits_nchw, npix, H * W);
+    AIDE_CHECK_LAUNCH();
+    return 0;
+  }
   int LP = 1;
   while (LP < C / 4 && LP < 32) LP <<= 1;
-  size_t npix = (size_t)N * H * W;
   size_t warps = (npix + (32 / LP) - 1) / (32 / LP);
   int blocks = (int)((warps + 7) / 8);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

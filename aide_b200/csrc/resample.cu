@@ -46,6 +46,83 @@ __global__ void upsample2x_fwd_kernel(CView src, View dst, int N, int h, int w, 
   }
 }
 
+// 16-bit operand planes (F16X2 / BF16): 8 channels = one 128-bit access per plane per thread
+template <int FMT>
+__device__ __forceinline__ void ld8(const void* p0, const void* p1, size_t e, float (&v)[8]) {
+  if constexpr (FMT == AIDE_FMT_F16X2) {
+    const uint4 rh = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p0) + e);
+    const uint4 rl = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p1) + e);
+    const __half2* h = reinterpret_cast<const __half2*>(&rh);
+    const __half2* l = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __half22float2(h[k]), b = __half22float2(l[k]);
+      v[2 * k] = a.x + b.x;            // kept in the 2^8-prescaled domain: the interpolation is linear
+      v[2 * k + 1] = a.y + b.y;
+    }
+  } else {
+    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p0) + e);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __bfloat1622float2(h[k]);
+      v[2 * k] = a.x;
+      v[2 * k + 1] = a.y;
+    }
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void st8(void* p0, void* p1, size_t e, const float (&v)[8]) {
+  if constexpr (FMT == AIDE_FMT_F16X2) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f16_split(v[k], h[k], l[k]);      // already prescaled
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p0) + e) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p1) + e) = *reinterpret_cast<const uint4*>(l);
+  } else {
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = __float2bfloat16_rn(v[k]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p0) + e) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// one thread = one output pixel x 8 channels; blockDim.x walks the channels of a pixel, blockIdx / threadIdx.y the
+// pixels, so the source-index arithmetic is done once per pixel row of threads and all accesses are 128-bit
+template <int FMT>
+__global__ void upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w, int C, float sh, float sw) {
+  const int H = 2 * h, W = 2 * w;
+  const size_t npix = (size_t)N * H * W;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += (size_t)gridDim.x * blockDim.y) {
+    const int ox = (int)(pix % W);
+    const int oy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(sh, oy, h, y0, y1, ly0, ly1);
+    src_index(sw, ox, w, x0, x1, lx0, lx1);
+    const size_t r0 = ((size_t)n * h + y0) * w, r1 = ((size_t)n * h + y1) * w;
+    const size_t s00 = (r0 + x0) * src.ctot + src.coff, s01 = (r0 + x1) * src.ctot + src.coff;
+    const size_t s10 = (r1 + x0) * src.ctot + src.coff, s11 = (r1 + x1) * src.ctot + src.coff;
+    const size_t d0 = pix * dst.ctot + dst.coff;
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+      float a[8], b[8], d[8], e[8], o[8];
+      ld8<FMT>(src.p0, src.p1, s00 + c, a);
+      ld8<FMT>(src.p0, src.p1, s01 + c, b);
+      ld8<FMT>(src.p0, src.p1, s10 + c, d);
+      ld8<FMT>(src.p0, src.p1, s11 + c, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        // same operation order as the 4-channel kernel: along W first, then along H
+        const float t0 = lx0 * a[k] + lx1 * b[k], t1 = lx0 * d[k] + lx1 * e[k];
+        o[k] = ly0 * t0 + ly1 * t1;
+      }
+      st8<FMT>(dst.p0, dst.p1, d0 + c, o);
+    }
+  }
+}
+
 // Gather form of the transpose: every low-res pixel sums the (<= ~5x5) high-res pixels that read it.
 __global__ void upsample2x_bwd_kernel(const float* __restrict__ dhi, int ctot, int coff, float* __restrict__ dlo,
                                       int N, int h, int w, int C, float sh, float sw) {
@@ -105,6 +182,22 @@ extern "C" int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_
                "upsample2x_fwd: bad arguments");
   CView src{src_p0, src_p1, src_ctot, src_coff};
   View dst{dst_p0, dst_p1, dst_ctot, dst_coff};
+  if ((fmt == AIDE_FMT_F16X2 || fmt == AIDE_FMT_BF16) && C % 8 == 0 && src_coff % 8 == 0 && dst_coff % 8 == 0 &&
+      src_ctot % 8 == 0 && dst_ctot % 8 == 0) {
+    int cx = C / 8 < 32 ? C / 8 : 32;                   // threads across the channels of one pixel
+    while (cx & (cx - 1)) cx &= cx - 1;                 // power of two
+    const dim3 block(cx, 256 / cx);
+    const size_t npix = (size_t)N * 4 * h * w;
+    long long blocks = (long long)((npix + block.y - 1) / block.y);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    const float sh = ac_scale(h, 2 * h), sw = ac_scale(w, 2 * w);
+    if (fmt == AIDE_FMT_F16X2)
+      upsample2x_fwd16_kernel<AIDE_FMT_F16X2><<<(int)blocks, block, 0, as_stream(stream)>>>(src, dst, N, h, w, C, sh, sw);
+    else
+      upsample2x_fwd16_kernel<AIDE_FMT_BF16><<<(int)blocks, block, 0, as_stream(stream)>>>(src, dst, N, h, w, C, sh, sw);
+    AIDE_CHECK_LAUNCH();
+    return 0;
+  }
   size_t total = (size_t)N * 4 * h * w * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
