@@ -44,6 +44,7 @@ constexpr int kStatChunk = 64;
 constexpr int kStatLanes = 32;   // row lanes per block: these kernels are latency bound (a handful of dependent loads)
 
 __global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int cols /* = 2*C */) {
+  partial += (size_t)blockIdx.z * rows * cols;          // statistics group (stacked-batch forward): its own row block
   __shared__ double sm[kStatLanes][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * kStatChunk;
@@ -65,60 +66,78 @@ __global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int c
   }
 }
 
-// rows are visited as r = g*row_stride + {0 .. sub-1} for g < groups  (plain: row_stride = 1, sub = 1, groups = rows)
+// rows are visited as r = g*row_stride + {0 .. sub-1} for g < groups  (plain: row_stride = 1, sub = 1, groups = rows).
+// `sgroups` statistics groups (the views of a stacked-batch forward) are finalised one after the other by the same
+// block, so the running-statistics updates chain in group order exactly like `sgroups` separate forward calls.
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups, int row_stride, int sub, int rows,
                                    int C, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float momentum, float eps, int training,
-                                   float* __restrict__ scale_shift, float* __restrict__ mean_rstd) {
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_rstd, int sgroups) {
   __shared__ double s1[kStatLanes][33], s2[kStatLanes][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  double a = 0.0, b = 0.0;
-  if (training && c < C) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float rm = 0.f, rv = 0.f;
+  const bool owner = threadIdx.y == 0 && c < C;
+  if (owner && rmean) {
+    rm = rmean[c];
+    rv = rvar[c];
+  }
+  for (int sg = 0; sg < sgroups; ++sg) {
+    const float* part = partial + (size_t)sg * rows * 2 * C;
+    double a = 0.0, b = 0.0;
+    if (training && c < C) {
 #pragma unroll 4
-    for (int g = threadIdx.y; g < groups; g += kStatLanes) {
-      for (int k = 0; k < sub; ++k) {
-        const int r = g * row_stride + k;
-        if (r < rows) {
-          a += (double)partial[((size_t)r * 2 + 0) * C + c];
-          b += (double)partial[((size_t)r * 2 + 1) * C + c];
+      for (int g = threadIdx.y; g < groups; g += kStatLanes) {
+        for (int k = 0; k < sub; ++k) {
+          const int r = g * row_stride + k;
+          if (r < rows) {
+            a += (double)part[((size_t)r * 2 + 0) * C + c];
+            b += (double)part[((size_t)r * 2 + 1) * C + c];
+          }
         }
       }
     }
-  }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y != 0 || c >= C) return;
-  float mean, var;
-  if (training) {
-    double sa = 0.0, sb = 0.0;
+    __syncthreads();                      // previous group's owner is done reading s1/s2
+    s1[threadIdx.y][threadIdx.x] = a;
+    s2[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    if (!owner) continue;
+    float mean, var;
+    if (training) {
+      double sa = 0.0, sb = 0.0;
 #pragma unroll
-    for (int k = 0; k < kStatLanes; ++k) {
-      sa += s1[k][threadIdx.x];
-      sb += s2[k][threadIdx.x];
+      for (int k = 0; k < kStatLanes; ++k) {
+        sa += s1[k][threadIdx.x];
+        sb += s2[k][threadIdx.x];
+      }
+      double m = sa / count;
+      double v = sb / count - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      if (rmean) {
+        double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
+        rm = (1.f - momentum) * rm + momentum * mean;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+    } else {
+      mean = rm;
+      var = rv;
     }
-    double m = sa / count;
-    double v = sb / count - m * m;
-    if (v < 0.0) v = 0.0;
-    mean = (float)m;
-    var = (float)v;
-    if (rmean) {
-      double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
-      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
-      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    float rstd = 1.0f / sqrtf(var + eps);
+    float sc = gamma[c] * rstd;
+    float* ss = scale_shift + (size_t)sg * 2 * C;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - mean * sc;
+    if (mean_rstd) {
+      float* mr = mean_rstd + (size_t)sg * 2 * C;
+      mr[c] = mean;
+      mr[C + c] = rstd;
     }
-  } else {
-    mean = rmean[c];
-    var = rvar[c];
   }
-  float rstd = 1.0f / sqrtf(var + eps);
-  float sc = gamma[c] * rstd;
-  scale_shift[c] = sc;
-  scale_shift[C + c] = beta[c] - mean * sc;
-  if (mean_rstd) {
-    mean_rstd[c] = mean;
-    mean_rstd[C + c] = rstd;
+  if (owner && training && rmean) {
+    rmean[c] = rm;
+    rvar[c] = rv;
   }
 }
 
@@ -133,15 +152,19 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 
 template <int FMT, bool POOL>
 __global__ void bn_relu_apply_kernel(const float* __restrict__ z, int N, int H, int W, int C,
-                                     const float* __restrict__ scale_shift, View dst, View pa, View pb) {
+                                     const float* __restrict__ scale_shift, View dst, View pa, View pb,
+                                     int imgs_per_group) {
+  // scale_shift: [groups][2][C]; image n uses group n / imgs_per_group (one group = plain forward)
   const int C4 = C >> 2;
   if constexpr (!POOL) {
     size_t total = (size_t)N * H * W * C4;
+    const size_t pix_per_group = (size_t)imgs_per_group * H * W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
       int c = (int)(i % C4) * 4;
       size_t pix = i / C4;
-      float4 sc = __ldg(reinterpret_cast<const float4*>(scale_shift + c));
-      float4 sh = __ldg(reinterpret_cast<const float4*>(scale_shift + C + c));
+      const float* ss = scale_shift + (pix / pix_per_group) * 2 * C;
+      float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+      float4 sh = __ldg(reinterpret_cast<const float4*>(ss + C + c));
       float4 v = *reinterpret_cast<const float4*>(z + pix * C + c);
       st4<FMT>(dst.p0, dst.p1, pix * dst.ctot + dst.coff + c, bn_relu4(v, sc, sh));
     }
@@ -154,8 +177,9 @@ __global__ void bn_relu_apply_kernel(const float* __restrict__ z, int N, int H, 
       int wx = (int)(win % Wh);
       int hy = (int)((win / Wh) % Hh);
       int n = (int)(win / ((size_t)Wh * Hh));
-      float4 sc = __ldg(reinterpret_cast<const float4*>(scale_shift + c));
-      float4 sh = __ldg(reinterpret_cast<const float4*>(scale_shift + C + c));
+      const float* ss = scale_shift + (size_t)(n / imgs_per_group) * 2 * C;
+      float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+      float4 sh = __ldg(reinterpret_cast<const float4*>(ss + C + c));
       size_t p00 = ((size_t)n * H + 2 * hy) * W + 2 * wx;
       size_t p01 = p00 + 1, p10 = p00 + W, p11 = p10 + 1;
       float4 y00 = bn_relu4(*reinterpret_cast<const float4*>(z + p00 * C + c), sc, sh);
@@ -417,21 +441,30 @@ using namespace aide;
 extern "C" int aide_bn_finalize(float* stat_partial, int rows, int C, double count, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, float momentum,
                                 float eps, int training, float* scale_shift, float* mean_rstd, void* stream) {
-  AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift, "bn_finalize: bad arguments");
+  return aide_bn_finalize_grouped(stat_partial, rows, 1, C, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                  training, scale_shift, mean_rstd, stream);
+}
+
+extern "C" int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgroups, int C, double count,
+                                        const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                        float momentum, float eps, int training, float* scale_shift, float* mean_rstd,
+                                        void* stream) {
+  AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift && sgroups >= 1, "bn_finalize: bad arguments");
   AIDE_REQUIRE(training ? (stat_partial && rows > 0 && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics input");
   dim3 block(32, kStatLanes), grid(ceil_div(C, 32));
   int groups = rows, row_stride = 1, sub = 1;
   if (training && rows > 2 * kStatChunk) {   // many tiles: fold chunks in parallel first (in place)
     groups = ceil_div(rows, kStatChunk);
-    bn_stat_fold_kernel<<<dim3(ceil_div(2 * C, 32), groups), block, 0, as_stream(stream)>>>(stat_partial, rows, 2 * C);
+    bn_stat_fold_kernel<<<dim3(ceil_div(2 * C, 32), groups, sgroups), block, 0, as_stream(stream)>>>(stat_partial, rows,
+                                                                                                      2 * C);
     AIDE_CHECK_LAUNCH();
     row_stride = kStatChunk;
     sub = 2;
   }
   bn_finalize_kernel<<<grid, block, 0, as_stream(stream)>>>(stat_partial, groups, row_stride, sub, rows, C, count,
                                                             gamma, beta, running_mean, running_var, momentum, eps,
-                                                            training, scale_shift, mean_rstd);
+                                                            training, scale_shift, mean_rstd, sgroups);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -440,7 +473,16 @@ extern "C" int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, 
                                   void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff, void* poolA_p0,
                                   void* poolA_p1, int poolA_ctot, int poolA_coff, void* poolB_p0, void* poolB_p1,
                                   int poolB_ctot, int poolB_coff, void* stream) {
-  AIDE_REQUIRE(z && scale_shift && C % 4 == 0 && N > 0, "bn_relu_apply: bad arguments (C %% 4 must be 0)");
+  return aide_bn_relu_apply_grouped(fmt, z, N, N, H, W, C, scale_shift, dst_p0, dst_p1, dst_ctot, dst_coff, poolA_p0,
+                                    poolA_p1, poolA_ctot, poolA_coff, poolB_p0, poolB_p1, poolB_ctot, poolB_coff, stream);
+}
+
+extern "C" int aide_bn_relu_apply_grouped(int fmt, const float* z, int N, int imgs_per_group, int H, int W, int C,
+                                          const float* scale_shift, void* dst_p0, void* dst_p1, int dst_ctot,
+                                          int dst_coff, void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                                          void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream) {
+  AIDE_REQUIRE(z && scale_shift && C % 4 == 0 && N > 0 && imgs_per_group > 0 && N % imgs_per_group == 0,
+               "bn_relu_apply: bad arguments (C %% 4 must be 0, N a multiple of the group size)");
   const bool pool = poolA_p0 || poolB_p0;
   AIDE_REQUIRE(pool || dst_p0, "bn_relu_apply: no destination");
   AIDE_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "bn_relu_apply: pooling needs even H, W");
@@ -454,10 +496,10 @@ extern "C" int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, 
   if (blocks > cap) blocks = cap;
   if (pool) {
     AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, true><<<blocks, 256, 0, as_stream(stream)>>>(
-                               z, N, H, W, C, scale_shift, dst, pa, pb)));
+                               z, N, H, W, C, scale_shift, dst, pa, pb, imgs_per_group)));
   } else {
     AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, false><<<blocks, 256, 0, as_stream(stream)>>>(
-                               z, N, H, W, C, scale_shift, dst, pa, pb)));
+                               z, N, H, W, C, scale_shift, dst, pa, pb, imgs_per_group)));
   }
   AIDE_CHECK_LAUNCH();
   return 0;

@@ -183,7 +183,8 @@ def plan_unet(num_classes: int = 2) -> Plan:
 class Layout:
     """Byte offsets of every buffer of a plan for a given (N, H, W, fmt) inside one arena."""
 
-    def __init__(self, plan: Plan, N: int, H: int, W: int, fmt: int):
+    def __init__(self, plan: Plan, N: int, H: int, W: int, fmt: int, groups: int = 1):
+        self.groups = groups
         if H % 16 or W % 16:
             raise ValueError(f"input height/width must be multiples of 16 (got {H}x{W}); the nets pool 4 times")
         self.plan, self.N, self.H, self.W, self.fmt = plan, N, H, W, fmt
@@ -207,8 +208,8 @@ class Layout:
             cur += _align(N * h * w * u.cout * 4)
             self.off["st:" + u.name] = cur
             cur += _align(rows * 2 * u.cout * 4)
-            self.off["ss:" + u.name] = cur            # scale_shift [2][C] then mean_rstd [2][C]
-            cur += _align(4 * u.cout * 4)
+            self.off["ss:" + u.name] = cur            # scale_shift [G][2][C] then mean_rstd [G][2][C]
+            cur += _align(groups * 4 * u.cout * 4)
         self.total = cur
 
     def buf_fmt(self, name: str) -> int:
@@ -319,15 +320,14 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             call("aide_conv3x3_fwd", ufmt, x0, x1, xct, xco, u.cin, w0, w1, params[u.conv + ".bias"].data_ptr(),
                  z, u.cout, 0, u.cout, N, h, w, stp if training else None, st)
             rows_g = layout.stat_rows[u.name] // G
-            for g in range(G):
-                call("aide_bn_finalize", stp + g * rows_g * 2 * u.cout * 4, rows_g, u.cout, float(Ng * h * w),
-                     params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
-                     params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
-                     BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + 2 * u.cout * 4, st)
-                d = gview(u.dst[0], u.dst[1], u.level, g) if u.dst else (None, None, 0, 0)
-                pa = gview(u.pools[0][0], u.pools[0][1], u.level + 1, g) if len(u.pools) > 0 else (None, None, 0, 0)
-                pb = gview(u.pools[1][0], u.pools[1][1], u.level + 1, g) if len(u.pools) > 1 else (None, None, 0, 0)
-                call("aide_bn_relu_apply", fmt, z + g * Ng * h * w * u.cout * 4, Ng, h, w, u.cout, ss, *d, *pa, *pb, st)
+            call("aide_bn_finalize_grouped", stp, rows_g, G, u.cout, float(Ng * h * w),
+                 params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
+                 params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
+                 BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * u.cout * 4, st)
+            d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
+            pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
+            pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
+            call("aide_bn_relu_apply_grouped", fmt, z, N, Ng, h, w, u.cout, ss, *d, *pa, *pb, st)
         elif isinstance(op, Upsample):
             h, w = H >> op.level, W >> op.level
             s = _view(layout, base, op.src, 0)

@@ -146,10 +146,10 @@ class _EngineNet(nn.Module):
         first = inputs[0][0] if groups > 1 else inputs[0]
         N, _, H, W = first.shape
         N *= groups
-        key = (N, H, W, fmt)
+        key = (N, H, W, fmt, groups)
         layout = self._layouts.get(key)
         if layout is None:
-            layout = self._layouts[key] = E.Layout(plan, N, H, W, fmt)
+            layout = self._layouts[key] = E.Layout(plan, N, H, W, fmt, groups)
         named = self._named()
         training = self.training
         wkey = tuple((named[u.conv + ".weight"].data_ptr(), named[u.conv + ".weight"]._version) for u in plan.units)

@@ -98,12 +98,24 @@ int aide_bn_finalize(float* stat_partial /* folded in place: consumed */, int ro
                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                      float momentum, float eps, int training,
                      float* scale_shift, float* mean_rstd, void* stream);
+/* The same for `sgroups` statistics groups at once (a stacked-batch forward whose views keep their own BatchNorm
+ * statistics -- the 4 augmented forwards of trainchaos_proposed_30cases1labeled.py:265-269 run as one batch):
+ * stat_partial holds sgroups consecutive blocks of `rows` rows, scale_shift / mean_rstd are [sgroups][2][C], and the
+ * running statistics are updated once per group, in group order, exactly like sgroups separate forward calls. */
+int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgroups, int C, double count, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                             int training, float* scale_shift, float* mean_rstd, void* stream);
 /* y = relu(scale*z+shift) written to `dst` (full resolution) and, when given, the 2x2 max-pooled y to
  * up to two half-resolution views (the fused-encoder concat and the modal-2 branch, fuseunet.py:51-56). */
 int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, int C, const float* scale_shift,
                        void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
                        void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
                        void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream);
+/* Stacked-batch form: image n is normalised with scale_shift[n / imgs_per_group] ([groups][2][C]). */
+int aide_bn_relu_apply_grouped(int fmt, const float* z, int N, int imgs_per_group, int H, int W, int C,
+                               const float* scale_shift, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                               void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                               void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream);
 /* backward, stage 1: g = relu'(y) * (sum of upstream gradients).  Upstream sources (all fp32 NHWC):
  * up to 3 same-resolution slices and up to 3 half-resolution slices routed through the max-pool
  * arg-max (first maximum in window scan order wins, like ATen max_pool2d_with_indices).  y is
