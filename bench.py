@@ -390,14 +390,18 @@ def main():
     if rank == 0:
         from aide_b200 import engine as E
         fmt_inf, fmt_train = E.mode_format(args.mode, False), E.mode_format(args.mode, True)
-        rl = conv_roofline(fmt_inf, B, S, device, peaks)      # 4 of the 5 forwards per net run in this format
-        layers = {FMT_NAMES[fmt_inf]: rl.pop("layers")}
+        # The dominant kernel launches of the step are the convolutions of the stacked pseudo-label forward (4 views x B
+        # images per launch, 4/7 of the step's conv FLOPs); the train forward / dgrad run the same kernel at batch B.
+        Ba = 4 * B if tr.group_augs else B
+        rl = conv_roofline(fmt_inf, Ba, S, device, peaks)
+        layers = {f"{FMT_NAMES[fmt_inf]}:B{Ba}": rl.pop("layers")}
+        rl["batch_per_launch"] = Ba
         out["roofline"] = rl
-        if fmt_train != fmt_inf:
-            rl2 = conv_roofline(fmt_train, B, S, device, peaks)   # train forward + dgrad
-            layers[FMT_NAMES[fmt_train]] = rl2.pop("layers")
-            out["roofline_train_format"] = {k: rl2[k] for k in ("kernel", "achieved", "frac", "frac_of_format_ceiling",
-                                                                "operand_format", "mma_passes")}
+        rl2 = conv_roofline(fmt_train, B, S, device, peaks)       # train forward + dgrad
+        layers[f"{FMT_NAMES[fmt_train]}:B{B}"] = rl2.pop("layers")
+        out["roofline_train_batch"] = {k: rl2[k] for k in ("kernel", "achieved", "frac", "frac_of_format_ceiling",
+                                                           "operand_format", "mma_passes", "traffic")}
+        out["roofline_train_batch"]["batch_per_launch"] = B
         if args.roofline_json:
             with open(args.roofline_json, "w") as f:
                 json.dump(dict(mode=args.mode, batch=B, size=S, summary=rl, layers=layers), f, indent=1)
@@ -435,8 +439,14 @@ def main():
                                            sample=f"failed: {type(e).__name__}: {e}")
         print(json.dumps(out), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: the captured CUDA graphs of the step still hold the communicator's kernels,
+        # and destroying the process group under them can block forever (seen on 2 x B200).  Every rank has finished
+        # its work at the barrier; flush and exit with status 0.
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize(device)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

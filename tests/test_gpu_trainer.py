@@ -102,5 +102,5 @@ def test_two_rank_step_equals_mean_of_shard_gradients(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29631",
-                          os.path.join(root, "tools", "ddp_check.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(root, "tools", "ddp_check.py")], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

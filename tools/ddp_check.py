@@ -58,6 +58,10 @@ for graph in (False, True):
         assert frac_same > 0.99, frac_same
         assert not torch.equal(mine, p0)
     dist.barrier()
+    print(f"[rank {rank}] graph={graph} ok", flush=True)
+torch.cuda.synchronize()
 if rank == 0:
-    print("DDP_CHECK_OK")
-dist.destroy_process_group()
+    print("DDP_CHECK_OK", flush=True)
+# no destroy_process_group(): captured CUDA graphs still reference the communicator (see bench.py)
+sys.stdout.flush()
+os._exit(0)
