@@ -25,6 +25,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import augment as AUG
 from . import engine as E
 from . import losses as L
 from ._lib import call, lib
@@ -80,6 +81,7 @@ class AideTrainer:
             cuda_graph = os.environ.get("AIDE_B200_GRAPH", "1") != "0"
         self.cuda_graph = bool(cuda_graph)
         self._graphs: Dict[tuple, tuple] = {}
+        self._aug_dev = None             # (matrices, modes, flips) of the current step's reverse augmentation, or None
         self.graph_launches = 0          # kernels launched through graph replays (aide_launch_count() sees eager ones)
 
     # ------------------------------------------------------------------------------------------
@@ -141,6 +143,30 @@ class AideTrainer:
     def _inputs(self, x):
         return tuple(x) if isinstance(x, (tuple, list)) else (x,)
 
+    # ---- reverse augmentation parameters (host builds PIL's matrices, the kernel does the resampling) -----------
+    @staticmethod
+    def _aug_host(augset, n_views: int, B: int, H: int, W: int):
+        mats = torch.empty((n_views, B, 6), dtype=torch.float64)
+        modes = torch.empty((n_views, B), dtype=torch.int32)
+        flips = torch.empty((n_views, B), dtype=torch.int32)
+        for v in range(n_views):
+            for b in range(B):
+                mode, m = AUG.rotate_matrix(0 - float(augset[f"degree{v + 1}"][b]), W, H)
+                if int(augset["augno"][b]) <= v:          # this sample has fewer views: leave the plane untouched
+                    mode, m = 1, [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+                mats[v, b] = torch.tensor(m, dtype=torch.float64)
+                modes[v, b] = mode
+                flips[v, b] = int(augset[f"hflip{v + 1}"][b]) if int(augset["augno"][b]) > v else 0
+        return mats, modes, flips
+
+    def _reverse(self, t: torch.Tensor, v: int) -> torch.Tensor:
+        mats, modes, flips = self._aug_dev
+        B, K, H, W = t.shape
+        out = torch.empty_like(t)
+        call("aide_reverse_aug", t.data_ptr(), out.data_ptr(), mats[v].data_ptr(), modes[v].data_ptr(),
+             flips[v].data_ptr(), B, K, H, W, torch.cuda.current_stream().cuda_stream)
+        return out
+
     def _half(self, net, opt, xs, augs, other: Dict, me: Dict, stage: int, t_other, rate: float):
         """One network's share of the step, split in three stages around the two joins."""
         if stage == 0:
@@ -153,6 +179,8 @@ class AideTrainer:
                     a = net._engine_forward_grouped([self._inputs(v) for v in augs])
                 else:
                     a = [net._engine_forward(self._inputs(v), keep_tape=False)[0] for v in augs]
+                if self._aug_dev is not None:      # undo the views' flip / rotation (reference :271-272 -> :81-95)
+                    a = [self._reverse(t, v) for v, t in enumerate(a)]
             net.train(was_training)
             if a:
                 me["q"], me["w"] = L.pseudo_label(a, self.temperature, self.flavour)
@@ -187,23 +215,44 @@ class AideTrainer:
             me["loss"], me["idx"] = loss, idx
             me["tape"] = None
 
-    def step(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float) -> Dict[str, torch.Tensor]:
+    def step(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float,
+             augset: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
         """x / augs[i]: a tensor [B,3,H,W] (unet) or a pair of them (fuseunet), on the device OR in (pinned) host
         memory.  t1, t2: [B,H,W] int64.  Returns device scalars loss1, loss2, dice1, dice2 (Dice_fn batch sums), the
         index vectors and both logits; no host sync.  With cuda_graph=True the returned tensors are the graph's
-        static outputs: they are overwritten by the next step()."""
+        static outputs: they are overwritten by the next step().  augset: the reference's dict of the views' forward
+        augmentation (``augno``, ``degree{k}``, ``hflip{k}`` per sample); the views' logits are flipped / rotated back
+        on the GPU before the pseudo label is built (None = identity, as in the synthetic benchmark)."""
         xs = self._inputs(x)
         augs = [self._inputs(a) for a in augs]
+        host_aug = None
+        if augset is not None and len(augs) > 0:
+            B, _, H, W = xs[0].shape
+            host_aug = self._aug_host(augset, len(augs), B, H, W)
         if not self.cuda_graph:
             dev = self.device
             mv = lambda t: t if t.is_cuda else t.to(dev, non_blocking=True)
-            return self._step_eager(tuple(mv(t) for t in xs), mv(t1), mv(t2), [tuple(mv(t) for t in a) for a in augs], rate)
-        key = (tuple(xs[0].shape), len(xs), len(augs), float(rate), self.flavour, self.world)
+            self._aug_dev = tuple(t.to(dev) for t in host_aug) if host_aug is not None else None
+            try:
+                return self._step_eager(tuple(mv(t) for t in xs), mv(t1), mv(t2), [tuple(mv(t) for t in a) for a in augs],
+                                        rate)
+            finally:
+                self._aug_dev = None
+        key = (tuple(xs[0].shape), len(xs), len(augs), float(rate), self.flavour, self.world, host_aug is not None)
         entry = self._graphs.get(key)
         if entry is None:
-            entry = self._capture(key, xs, t1, t2, augs, rate)
+            if host_aug is not None:                           # static device buffers the captured kernels read
+                self._aug_dev = tuple(t.to(self.device) for t in host_aug)
+            try:
+                entry = self._capture(key, xs, t1, t2, augs, rate)
+                entry[1]["aug"] = self._aug_dev
+            finally:
+                self._aug_dev = None
         graph, static, out, n_kernels = entry
         self._fill_static(static, xs, t1, t2, augs)            # D2D, or H2D straight into the graph's inputs
+        if host_aug is not None:
+            for d, s_ in zip(static["aug"], host_aug):
+                d.copy_(s_, non_blocking=True)
         graph.replay()
         self.graph_launches += n_kernels
         self.steps += 1

@@ -184,6 +184,13 @@ int aide_loss_bwd(const float* logits, const int64_t* targets, const float* q, c
  * (trainchaos_proposed_30cases1labeled.py:274-292,97-101). */
 int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo,
                       float* q /*[N,2,H,W]*/, float* wm /*[N,1,H,W]*/, void* stream);
+/* Reverse augmentation of augmented-forward outputs (trainchaos_proposed_30cases1labeled.py:81-95, which round-trips
+ * every plane through PIL on the CPU): optional horizontal flip, then PIL's Image.rotate(-degree, BILINEAR) about the
+ * centre with fill 0, reproduced bit for bit.  src/dst: [n_img,K,H,W] fp32 (different buffers); per image a row-major
+ * inverse affine matrix (6 doubles, as PIL builds it), a mode (0 affine, 1 copy, 2 rotate-180, 3 / 4 PIL's ROTATE_90 /
+ * ROTATE_270 fast paths on square images) and a flip flag -- all device arrays. */
+int aide_reverse_aug(const float* src, float* dst, const double* matrices, const int* modes, const int* hflips,
+                     int n_img, int K, int H, int W, void* stream);
 /* Small-loss selection (trainchaos_proposed_30cases1labeled.py:305-321): ascending argsort of
  * `pre_other` (the OTHER net's per-image loss) -> idx[N]; the first n_clean images are "clean".
  * Emits this net's per-image coefficients and its scalar loss

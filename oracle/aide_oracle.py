@@ -308,7 +308,7 @@ def adam_amsgrad_step(params: Params, grads: Dict[str, torch.Tensor], state: Dic
 def aide_step(fwd, p1: Params, p2: Params, inputs: Tuple[torch.Tensor, ...],
               aug_inputs: Sequence[Tuple[torch.Tensor, ...]], targets1: torch.Tensor, targets2: torch.Tensor,
               rate: float, temperature: float = 1.0, flavour: str = "chaos", n_clean: int = 2,
-              segcor_weight: Sequence[float] = (1.0, 10.0)):
+              segcor_weight: Sequence[float] = (1.0, 10.0), augset: Optional[Dict] = None):
     """One AIDE iteration up to (not including) the optimiser step.
 
     chaos flavour: augmented forwards in train mode (BN buffers updated 4 extra times), sharpen pow(T)
@@ -321,6 +321,9 @@ def aide_step(fwd, p1: Params, p2: Params, inputs: Tuple[torch.Tensor, ...],
     with torch.no_grad():
         aug1 = [fwd(p1, *a, training=aug_train) for a in aug_inputs]
         aug2 = [fwd(p2, *a, training=aug_train) for a in aug_inputs]
+    if augset is not None:
+        aug1 = reverseaug_pil(augset, aug1, aug1[0].shape[1])
+        aug2 = reverseaug_pil(augset, aug2, aug2[0].shape[1])
     q1, w1 = pseudo_label(aug1, temperature, flavour)
     q2, w2 = pseudo_label(aug2, temperature, flavour)
     out1 = fwd(p1, *inputs, training=True)
@@ -347,3 +350,85 @@ def synthetic_batch(b: int, h: int, w: Optional[int] = None, seed: int = 1234, n
     t2 = (torch.rand(b, h, w, generator=g) < 0.08).long()
     augs = [tuple(torch.randn(b, 3, h, w, generator=g) for _ in range(n_modal)) for _ in range(n_aug)]
     return imgs, t1, t2, augs
+
+
+# --------------------------------------------------------------------------------------
+# reverse augmentation of the augmented forwards' outputs ("next" row f2 of SURVEY.md section 8)
+# --------------------------------------------------------------------------------------
+def reverseaug_pil(augset: Dict, augoutput: List[torch.Tensor], classno: int) -> List[torch.Tensor]:
+    """train_files/trainchaos_proposed_30cases1labeled.py:81-95, verbatim semantics: every (sample, view, class) plane goes
+    through PIL (mode 'F'): optional FLIP_LEFT_RIGHT, then rotate(-degree, BILINEAR) about the image centre, fill 0.
+    Pillow is the reference's third-party dependency for this step (unpinned in requirements.txt; 12.2.0 here)."""
+    import numpy as np
+    from PIL import Image
+    out = [t.clone() for t in augoutput]
+    for batch_idx in range(len(augset["augno"])):
+        for aug_idx in range(int(augset["augno"][batch_idx])):
+            imgflip = augset["hflip{}".format(aug_idx + 1)][batch_idx]
+            rotation = 0 - augset["degree{}".format(aug_idx + 1)][batch_idx]
+            for classidx in range(classno):
+                mask = out[aug_idx][batch_idx, classidx, :, :].cpu().numpy()
+                mask = Image.fromarray(mask, mode="F")
+                if imgflip:
+                    mask = mask.transpose(Image.FLIP_LEFT_RIGHT)
+                mask = mask.rotate(float(rotation), Image.BILINEAR)
+                out[aug_idx][batch_idx, classidx, :, :] = torch.from_numpy(np.array(mask))
+    return out
+
+
+def rotate_matrix(angle_deg: float, w: int, h: int):
+    """PIL.Image.Image.rotate's inverse affine matrix (output pixel -> source position), PIL/Image.py `rotate`:
+    returns (mode, matrix) with mode 0 = affine, 1 = copy (angle % 360 == 0), 2 = ROTATE_180, 3 = ROTATE_90,
+    4 = ROTATE_270 (PIL's exact fast paths)."""
+    angle = angle_deg % 360.0
+    if angle == 0:
+        return 1, [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    if angle == 180:
+        return 2, [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    if angle in (90, 270) and w == h:
+        return (3 if angle == 90 else 4), [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    cx, cy = w / 2, h / 2
+    a = -math.radians(angle)
+    m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+    m[2] = m[0] * -cx + m[1] * -cy + m[2]
+    m[5] = m[3] * -cx + m[4] * -cy + m[5]
+    m[2] += cx
+    m[5] += cy
+    return 0, m
+
+
+def reverseaug_plane(src, hflip: bool, angle_deg: float):
+    """numpy restatement of what PIL does to one float32 plane (Pillow src/libImaging/Geometry.c: affine_transform +
+    bilinear_filter32F, double arithmetic, clamped neighbours, out-of-image source -> 0).  Checked bit for bit against
+    reverseaug_pil in tests/test_oracle_golden.py."""
+    import numpy as np
+    h, w = src.shape
+    s = src[:, ::-1] if hflip else src
+    mode, m = rotate_matrix(angle_deg, w, h)
+    if mode == 1:
+        return s.copy()
+    if mode == 2:
+        return s[::-1, ::-1].copy()
+    if mode == 3:                                  # Transpose.ROTATE_90: counter-clockwise
+        return np.ascontiguousarray(np.rot90(s, 1))
+    if mode == 4:
+        return np.ascontiguousarray(np.rot90(s, 3))
+    ys, xs = np.mgrid[0:h, 0:w]
+    xin = m[0] * (xs + 0.5) + m[1] * (ys + 0.5) + m[2]
+    yin = m[3] * (xs + 0.5) + m[4] * (ys + 0.5) + m[5]
+    inside = (xin >= 0.0) & (xin < w) & (yin >= 0.0) & (yin < h)
+    xin = xin - 0.5
+    yin = yin - 0.5
+    x = np.floor(xin).astype(np.int64)
+    y = np.floor(yin).astype(np.int64)
+    dx, dy = xin - x, yin - y
+    x0, x1 = np.clip(x, 0, w - 1), np.clip(x + 1, 0, w - 1)
+    yc = np.clip(y, 0, h - 1)
+    # BILINEAR(v, a, b, d): v = a + (b - a) * d with a, b FLOAT32 -> the difference is rounded to float32 first
+    f64 = np.float64
+    v1 = s[yc, x0].astype(f64) + (s[yc, x1] - s[yc, x0]).astype(f64) * dx
+    has2 = (y + 1 >= 0) & (y + 1 < h)
+    y2 = np.clip(y + 1, 0, h - 1)
+    v2 = np.where(has2, s[y2, x0].astype(f64) + (s[y2, x1] - s[y2, x0]).astype(f64) * dx, v1)
+    out = (v1 + (v2 - v1) * dy).astype(np.float32)
+    return np.where(inside, out, np.float32(0.0))

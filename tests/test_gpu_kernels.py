@@ -370,3 +370,28 @@ def test_adam_amsgrad_matches_torch(dev):
         opt.step()
     for p, r in zip(dps, ref):
         assert torch.allclose(p.detach().cpu(), r.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_reverse_augmentation_matches_pil_bit_for_bit(dev, oracle):
+    """GPU un-flip / un-rotate of the augmented views' logits vs the reference's PIL round trip
+    (trainchaos_proposed_30cases1labeled.py:81-95): bit-exact, including PIL's fast paths and samples with fewer views."""
+    import random
+    import aide_b200 as A
+    rnd = random.Random(3)
+    for (B, K, H, W) in [(4, 2, 64, 64), (3, 2, 48, 80), (2, 3, 33, 17)]:
+        n_views = 4
+        augset = {"augno": [rnd.choice([4, 4, 2]) for _ in range(B)]}
+        for v in range(1, n_views + 1):
+            augset[f"hflip{v}"] = [int(rnd.random() < 0.5) for _ in range(B)]
+            augset[f"degree{v}"] = [rnd.choice([0, 0.0, 90, 180, -90, 30]) if rnd.random() < 0.3 else rnd.uniform(-60, 60)
+                                    for _ in range(B)]
+        outs = [rnd_t for rnd_t in (rnd_tensor(B, K, H, W, seed=10 + v) for v in range(n_views))]
+        ref = oracle.reverseaug_pil(augset, [t.clone() for t in outs], K)
+        got = A.reverseaug(augset, [t.clone().to(dev) for t in outs], K)
+        torch.cuda.synchronize()
+        for v in range(n_views):
+            assert torch.equal(got[v].cpu(), ref[v]), (B, K, H, W, v)
+
+
+def rnd_tensor(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))

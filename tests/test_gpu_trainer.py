@@ -104,3 +104,35 @@ def test_two_rank_step_equals_mean_of_shard_gradients(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29631",
                           os.path.join(root, "tools", "ddp_check.py")], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_step_with_reverse_augmentation(oracle, graph):
+    """The step with flipped / rotated views: the engine un-augments the views' logits on the GPU (aide_reverse_aug),
+    the oracle through PIL as the reference does (trainchaos_proposed_30cases1labeled.py:271-272 -> :81-95)."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+    torch.manual_seed(2)
+    p1 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
+    p2 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
+    x, t1, t2, augs = batch(oracle, B, S, 900)
+    d = lambda t: t.to(dev)
+    saved = [t.clone() for t in tr._state_tensors()]
+    for rep, degs in enumerate(([17.5, -42.0, 0.0, 60.0], [-5.25, 33.0, 90.0, -60.0])):
+        augset = {"augno": [4, 4, 3, 4]}
+        for v in range(1, 5):
+            augset[f"degree{v}"] = [g * (1 if v % 2 else -1) + v for g in degs]
+            augset[f"hflip{v}"] = [(b + v + rep) % 2 for b in range(B)]
+        r = oracle.aide_step(oracle.fuseunet_forward, oracle.clone_params(p1, True), oracle.clone_params(p2, True), x, augs,
+                             t1, t2, 0.25, augset=augset)
+        # same trainer, state rewound: the second repetition REPLAYS the captured graph with other augmentation
+        # parameters (they live in static device buffers the captured kernels read)
+        with torch.no_grad():
+            for t, s_ in zip(tr._state_tensors(), saved):
+                t.copy_(s_)
+        m = tr.step(tuple(d(t) for t in x), d(t1), d(t2), [tuple(d(t) for t in a) for a in augs], 0.25, augset=augset)
+        assert abs(m["loss1"].item() - r["loss1"].item()) < 2e-5 * max(1, abs(r["loss1"].item())), rep
+        assert abs(m["loss2"].item() - r["loss2"].item()) < 2e-5 * max(1, abs(r["loss2"].item())), rep
+        assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"]), rep

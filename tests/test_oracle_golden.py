@@ -109,3 +109,24 @@ def test_known_answers_256(golden, oracle):
     packed = torch.from_numpy(np.packbits((yf.argmax(1) == 1).numpy().reshape(-1)))
     flips = int(np.unpackbits((packed ^ g["fuse_argmax_packed"]).numpy()).sum())
     assert flips <= 2, flips                                              # numerical ties only (min margin 1.5e-6)
+
+
+def test_reverseaug_restatement_matches_pil_bit_for_bit(oracle):
+    """The numpy restatement of Pillow's flip + rotate(BILINEAR) (oracle.reverseaug_plane) against the reference's own
+    code path through PIL (oracle.reverseaug_pil = trainchaos_proposed_30cases1labeled.py:81-95), including PIL's
+    exact fast paths; the host-side matrix builder of the product must agree with the oracle's."""
+    import random
+    import numpy as np
+    from aide_b200.augment import rotate_matrix
+    rnd = random.Random(0)
+    rs = np.random.RandomState(0)
+    for (H, W) in [(32, 32), (48, 64), (17, 23)]:
+        for trial in range(24):
+            deg = rnd.choice([0, 90, 180, 270, -90, 360]) if trial < 6 else rnd.uniform(-60, 60)
+            flip = rnd.random() < 0.5
+            x = rs.randn(H, W).astype(np.float32)
+            augset = {"augno": [1], "hflip1": [int(flip)], "degree1": [deg]}
+            ref = oracle.reverseaug_pil(augset, [torch.from_numpy(x)[None, None].clone()], 1)[0][0, 0].numpy()
+            got = oracle.reverseaug_plane(np.ascontiguousarray(x), flip, 0 - deg)
+            assert np.array_equal(ref, got), (H, W, deg, flip)
+            assert rotate_matrix(0 - deg, W, H) == oracle.rotate_matrix(0 - deg, W, H)
