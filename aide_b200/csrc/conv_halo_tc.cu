@@ -56,6 +56,7 @@ struct HaloParams {
   int tiles_w, tiles_h, m_tiles, n_tiles, total_items;
   int BN, kc, n_cchunks, row_bytes;
   int MB, nacc, nbuf, tmem_cols;
+  int stack, acc_w;                              // hi/lo weight planes stacked along N (see the MMA issuer); columns per accumulator
   int a_slot_bytes, a_stage_bytes, a_stages;
   int b_plane_bytes, b_stage_bytes, b_stages;
   int b_off, bar_off;
@@ -188,6 +189,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
     // lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced with 64-bit adds on the start-address
     // field (16-byte units): +2 per 32-byte K step, +row offset per tap, +slot per pixel tile.
     const uint32_t idesc = make_idesc(TF32 ? 2u : (KIND == K_BF16 ? 1u : 0u), 0u, 0u, 128u, (uint32_t)p.BN);
+    // Stacked split-precision step: the weight stage holds the hi plane followed by the lo plane, i.e. ONE K-major
+    // operand of 2*BN rows, so  A_hi x [W_hi; W_lo]  is a single MMA of width 2*BN writing hi*hi to columns [0, BN) and
+    // hi*lo to [BN, 2*BN); A_lo x W_hi follows into [0, BN) and the epilogue adds the two halves.  Two MMAs instead of
+    // three, the first of them wide -- narrow cout tiles are bound by operand fetch per MMA, not by tensor work.
+    const uint32_t idesc2 = make_idesc(TF32 ? 2u : (KIND == K_BF16 ? 1u : 0u), 0u, 0u, 128u, (uint32_t)(2 * p.BN));
+    const bool stack = NPL == 2 && p.stack != 0;
     const uint32_t layout = NKS == 4 ? 2u : 4u;
     const uint64_t a_desc0 = make_smem_desc(base, 16, kHW * p.row_bytes, layout);
     const uint64_t b_desc0 = make_smem_desc(base + p.b_off, 16, 8 * p.row_bytes, layout);
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
     const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t row16 = (uint32_t)p.row_bytes >> 4;
-    const uint32_t acc_tile = (uint32_t)(p.nacc * p.BN);
+    const uint32_t acc_tile = (uint32_t)(p.nacc * p.acc_w);
     const bool leader = elect_one();
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0, tcount = 0;
@@ -224,12 +231,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
               const uint64_t b_hi = b_desc0 + (uint64_t)(sb * b_stage16);
               const uint32_t flag0 = (first >> ai) & 1u;
               uint64_t a_hi = a_tap;
-              uint32_t acc = acc_item + (uint32_t)ai * p.BN;
+              uint32_t acc = acc_item + (uint32_t)ai * p.acc_w;
               for (int m = 0; m < mbv; ++m, a_hi += (uint64_t)a_slot16, acc += acc_tile) {
 #pragma unroll
                 for (int ks = 0; ks < NKS; ++ks) {
                   const uint32_t flag = ks == 0 ? flag0 : 1u;
-                  if (NPL == 2) {
+                  if (NPL == 2 && stack) {
+                    umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(2 * ks), idesc2, flag);
+                    umma<TF32>(acc, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, 1u);
+                  } else if (NPL == 2) {
                     umma<TF32>(acc, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, flag);
                     umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(b_plane16 + 2 * ks), idesc, 1u);
                     umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(2 * ks), idesc, 1u);
@@ -274,7 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
         const int hh = (r / p.tiles_w) * kTH + ty, ww = (r % p.tiles_w) * kTW + tx;
         const bool valid = hh < p.H && ww < p.W;
         float* zrow = p.z + (((size_t)n_img * p.H + hh) * p.W + ww) * p.z_ctot + p.z_coff + n0;
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MB + m) * p.nacc * p.BN);
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MB + m) * p.nacc * p.acc_w);
+        const int nparts = p.nacc * (p.stack ? 2 : 1);           // BN-wide column blocks to add up per accumulator set
         for (int ch = 0; ch < p.BN / 32; ++ch) {
           uint32_t rr[32];
           tmem_ld_32x32(tbase + (uint32_t)(ch * 32), rr);
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-          for (int a = 1; a < p.nacc; ++a) {
+          for (int a = 1; a < nparts; ++a) {
             tmem_ld_32x32(tbase + (uint32_t)(a * p.BN + ch * 32), rr);
             tmem_ld_wait();
 #pragma unroll
@@ -334,7 +345,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct HaloPlan {
-  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages;
+  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack;
   int a_slot, a_stage, b_plane, b_stage, smem;
   double cost;
 };
@@ -367,14 +378,17 @@ double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks,
   const long long items = (m_tiles + c.MB - 1) / c.MB * (cout / c.BN);
   const long long waves = (items + kNumSMs - 1) / kNumSMs;
   // an MMA of 128 x BN x 32 B: tensor rate (BN/2 clk) vs operand fetch from shared memory, plus issue overhead
-  const double fetch = (m.sm_a + c.BN) / m.sm_d;
-  const double per_mma = (c.BN / 2.0 > fetch ? c.BN / 2.0 : fetch) + m.issue;
-  const double mma = (double)c.MB * 9 * n_cchunks * nks * (npl == 2 ? 3 : 1) * per_mma + 9.0 * n_cchunks * m.stage_ovh;
+  auto mma_clk = [&](double n) {
+    const double fetch = (m.sm_a + n) / m.sm_d;
+    return (n / 2.0 > fetch ? n / 2.0 : fetch) + m.issue;
+  };
+  const double per_step = npl == 1 ? mma_clk(c.BN) : c.stack ? mma_clk(2.0 * c.BN) + mma_clk(c.BN) : 3.0 * mma_clk(c.BN);
+  const double mma = (double)c.MB * 9 * n_cchunks * nks * per_step + 9.0 * n_cchunks * m.stage_ovh;
   const double bytes = (double)n_cchunks * npl * c.row_bytes * (c.MB * kHaloPix + 9.0 * c.BN);
-  const double epi = (double)c.MB * (c.BN / 32) * m.epi * c.nacc;
+  const double epi = (double)c.MB * (c.BN / 32) * m.epi * c.nacc * (c.stack ? 1.5 : 1.0);
   double t = mma > bytes / m.bw ? mma : bytes / m.bw;
   t *= 1.0 + m.pb / c.b_stages + m.pa / c.a_stages;            // shallow rings expose L2 latency
-  if (c.nbuf == 1) t += epi;
+  if (c.nbuf == 1) t += 3.0 * epi;      // single TMEM buffer: the tensor pipe drains while the epilogue runs (measured)
   else if (epi > t) t = epi;
   return (double)waves * t;
 }
@@ -382,6 +396,7 @@ double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks,
 bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
   const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
   const int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
+  const int force_stack = env_int("AIDE_CONV_STACK", -1);
   best->cost = -1;
   for (int bn = 256; bn >= 32; bn >>= 1) {
     if (cout % bn) continue;
@@ -395,12 +410,17 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
         if (cin % kc) continue;
         const int n_cchunks = cin / kc;
         const int nks = rb / 32;
-        const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? 3 : 1);
+       for (int stack = 0; stack <= 1; ++stack) {
+        if (stack && (npl != 2 || 2 * bn > 256)) continue;
+        if (force_stack >= 0 && stack != force_stack && !(stack == 0 && (npl != 2 || 2 * bn > 256))) continue;
+        // accumulation chain per TMEM column: 3 MMAs per 32-byte K step, 2 when the weight planes are stacked
+        const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? (stack ? 2 : 3) : 1);
         const int nacc = wanted_nacc(fmt, chain);
-        if (mb * nacc * bn > 512) continue;
+        const int acc_w = bn * (1 + stack);
+        if (mb * nacc * acc_w > 512) continue;
         HaloPlan c{};
-        c.BN = bn; c.MB = mb; c.nacc = nacc; c.row_bytes = rb;
-        c.nbuf = (2 * mb * nacc * bn <= 512) ? 2 : 1;
+        c.BN = bn; c.MB = mb; c.nacc = nacc; c.row_bytes = rb; c.stack = stack;
+        c.nbuf = (2 * mb * nacc * acc_w <= 512) ? 2 : 1;
         c.a_slot = (kHaloPix * rb + 1023) / 1024 * 1024;
         c.a_stage = npl * mb * c.a_slot;
         c.b_plane = bn * rb;
@@ -427,6 +447,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
           pick = c;
           pick.cost = model_cost(kSel, c, npl, n_cchunks, nks, m_tiles, cout);
         }
+       }
       }
       if (pick_row_cost < 0) continue;
       if (best->cost < 0 || pick.cost < best->cost * 0.999) *best = pick;
@@ -483,6 +504,7 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
   HaloPlan pl;
   AIDE_REQUIRE(make_plan(fmt, cin, cout, p.m_tiles, &pl), "conv3x3(halo): no tiling fits (cin=%d cout=%d)", cin, cout);
   p.BN = pl.BN; p.MB = pl.MB; p.nacc = pl.nacc; p.nbuf = pl.nbuf;
+  p.stack = pl.stack; p.acc_w = pl.BN * (1 + pl.stack);
   p.row_bytes = pl.row_bytes;
   p.kc = pl.row_bytes / es;
   p.n_cchunks = cin / p.kc;
@@ -492,7 +514,7 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
   p.b_plane_bytes = pl.b_plane; p.b_stage_bytes = pl.b_stage; p.b_stages = pl.b_stages;
   p.b_off = pl.a_stages * pl.a_stage;
   p.bar_off = p.b_off + pl.b_stages * pl.b_stage;
-  int cols = p.nbuf * p.MB * p.nacc * p.BN;
+  int cols = p.nbuf * p.MB * p.nacc * p.acc_w;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   p.z = z; p.bias = bias; p.stat_partial = stat_partial;
@@ -513,12 +535,12 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
 }
 
 // for tools/ and bench.py: the tiling chosen for a layer
-extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out /*[8]*/) {
+extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out /*[9]*/) {
   if (!halo_shape_ok(fmt, cin, cout, N, H, W)) return 1;
   HaloPlan pl;
   make_plan(fmt, cin, cout, (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH), &pl);
   out[0] = pl.BN; out[1] = pl.MB; out[2] = pl.nacc; out[3] = pl.nbuf; out[4] = pl.row_bytes; out[5] = pl.a_stages;
-  out[6] = pl.b_stages; out[7] = pl.smem;
+  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack;
   return 0;
 }
 

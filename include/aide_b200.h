@@ -70,9 +70,9 @@ int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
                      const void* w_p0, const void* w_p1, const float* bias,
                      float* z, int z_ctot, int z_coff, int cout, int N, int H, int W,
                      float* stat_partial, void* stream);
-/* Tiling the tcgen05 forward/dgrad kernel picks for a layer (diagnostics for bench.py / tools): out[8] =
+/* Tiling the tcgen05 forward/dgrad kernel picks for a layer (diagnostics for bench.py / tools): out[9] =
  * {cout tile, pixel tiles per CTA iteration, accumulators per tile, TMEM buffers, smem row bytes, halo stages,
- *  weight stages, dynamic smem bytes}.  Returns non-zero when the layer runs on the first-generation kernel. */
+ *  weight stages, dynamic smem bytes, hi/lo weight planes stacked along N}.  Returns non-zero when the layer runs on the first-generation kernel. */
 int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out);
 /* dX[n,h,w,ci] = sum_{tap,co} dz[n,h+dy,w+dx,co] * w[co][ci][flipped tap]  (ATen conv backward-data): the forward
  * kernel on dgrad-prepared weights (aide_weight_prep).  dz is a plain [N,H,W,cout] operand-format buffer, dx an fp32

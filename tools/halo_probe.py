@@ -41,10 +41,10 @@ def rel(a, b):
 
 
 def plan(fmt, cin, cout, N, H, W):
-    out = (C.c_int * 8)()
+    out = (C.c_int * 9)()
     if A.lib.aide_conv3x3_plan_info(fmt, cin, cout, N, H, W, out):
         return None
-    return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6])
+    return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6], stack=out[8])
 
 
 def check(fmt, N, H, W, cin, cout):
