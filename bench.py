@@ -39,6 +39,17 @@ FUSEUNET_FWD_GFLOP_256 = 116.207          # per slice per net, conv FLOPs only (
 METRIC = "dual-FuseUNet train slices/sec @256x256x2 (AIDE proposed step)"
 
 
+def workload_config(B, S, world, mode, **extra):
+    """The `config` object both arms print: the same workload, named the same way."""
+    cfg = {"workload": "AIDE proposed step: 2x fuseunet, 4 augmented forwards + train forward + backward per net, "
+                       "co-teaching selection, Adam-amsgrad (BASELINE.json configs[2]; configs[3] for N>1)",
+           "mode": mode, "per_gpu_batch": B, "global_batch": B * world, "img_size": S, "modalities": 2,
+           "aug_views": 4, "rate": 0.25, "parallelism": f"dp{world}",
+           "algorithmic_gflop_per_slice": round((3 + 4) * 2 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2, 1)}
+    cfg.update(extra)
+    return cfg
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,8 +309,8 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "slices/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "AIDE proposed step, 2x fuseunet, CPU reference path (BASELINE.json configs[2])",
-                   "per_gpu_batch": B, "sample_batch": b, "img_size": S, "modalities": 2, "aug_views": 4},
+        "config": workload_config(B, S, max(args.gpus, 1), "cpu-reference (oracle port of the reference step, fp32)",
+                                  sample_batch=b),
         "cpu_baseline": {"value": round(v, 4), "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
@@ -373,14 +384,10 @@ def main():
                   "parity_mixed": "tf32x2 for the train forward/backward, f16x2 for the pseudo-label forwards",
                   "fast": "bf16 operands, fp32 accumulate (NOT a parity mode)", "exact": "f32 CUDA cores"}[args.mode],
         "data": "synthetic",
-        "config": {"workload": "AIDE proposed step: 2x fuseunet, 4 augmented forwards + train forward + backward per net, "
-                               "co-teaching selection, Adam-amsgrad (BASELINE.json configs[2]; configs[3] for N>1)",
-                   "mode": args.mode, "per_gpu_batch": B, "global_batch": B * world, "img_size": S, "modalities": 2,
-                   "aug_views": 4, "rate": 0.25, "parallelism": f"dp{world}",
-                   "cuda_graph": bool(tr.cuda_graph),
-                   "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; "
-                         f"{n_pool} distinct resident batches alternate",
-                   "algorithmic_gflop_per_slice": round((3 + 4) * 2 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2, 1)},
+        "config": workload_config(B, S, world, args.mode, cuda_graph=bool(tr.cuda_graph),
+                                  stacked_aug_forward=bool(tr.group_augs),
+                                  l2="per-step working set (activations + weights, several GB) exceeds the 126 MB L2; "
+                                     f"{n_pool} distinct resident batches alternate"),
         "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
         "clocks": clocks, "e2e": e2e,
