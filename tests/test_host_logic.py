@@ -103,3 +103,50 @@ def test_polylr_matches_formula():
         opt.step()
         sch.step()
         assert abs(opt.param_groups[0]["lr"] - 0.1 * (1 - e / 10) ** 0.9) < 1e-12
+
+
+def test_conv_planner_returns_valid_tilings_for_every_layer():
+    """Host-only: the tile planner of the tcgen05 conv kernel (aide_conv3x3_plan_info) must return a feasible tiling
+    for every tensor-core layer of both networks at the batches the step uses (B and 4B) and at 256 / 320 inputs:
+    TMEM columns <= 512, dynamic shared memory <= 227 KB, cout tile divides cout, at least two weight stages."""
+    import ctypes as C
+    from aide_b200 import engine as E, lib
+    out = (C.c_int * 9)()
+    checked = 0
+    for plan in (E.plan_fuseunet(2), E.plan_unet(2)):
+        for S in (256, 320):
+            for B in (4, 8, 32):
+                for u in plan.units:
+                    if u.first:
+                        continue
+                    h = S >> u.level
+                    for fmt in (1, 2, 3):
+                        for cin, cout in ((u.cin, u.cout), (u.cout, u.cin)):          # forward and dgrad roles
+                            if cin % 32 or cout % 32:
+                                continue
+                            rc = lib.aide_conv3x3_plan_info(fmt, cin, cout, B, h, h, out)
+                            assert rc == 0, (plan.kind, S, B, u.name, fmt)
+                            bn, mb, nacc, nbuf, rb, a_st, b_st, smem, stack = list(out)
+                            assert cout % bn == 0 and bn in (32, 64, 128, 256) and mb in (1, 2, 4)
+                            assert nbuf * mb * nacc * bn * (1 + stack) <= 512
+                            assert smem <= 227 * 1024 and a_st >= 1 and b_st >= 2 and rb in (64, 128)
+                            assert not stack or (fmt != 2 and 2 * bn <= 256)
+                            # same answer when asked again (the launch and the workspace query must agree)
+                            again = (C.c_int * 9)()
+                            lib.aide_conv3x3_plan_info(fmt, cin, cout, B, h, h, again)
+                            assert list(again) == list(out)
+                            checked += 1
+    assert checked > 1000
+
+
+def test_stat_rows_scale_with_batch_groups():
+    """The stacked pseudo-label forward slices the conv's BatchNorm partial-statistics rows per view: the row count
+    must be an exact multiple of the batch (rows are image-major for every conv kernel)."""
+    from aide_b200 import lib
+    for fmt in (0, 1, 2, 3):
+        for (cin, cout, h) in ((3, 32, 256), (64, 64, 128), (512, 256, 64), (512, 512, 16), (256, 512, 4)):
+            if fmt != 0 and cin == 3:
+                continue
+            r8 = lib.aide_conv3x3_stat_rows(fmt, cin, cout, 8, h, h)
+            r32 = lib.aide_conv3x3_stat_rows(fmt, cin, cout, 32, h, h)
+            assert r8 > 0 and r32 == 4 * r8, (fmt, cin, cout, h, r8, r32)
