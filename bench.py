@@ -60,6 +60,9 @@ def parse():
                     choices=["parity", "parity_tf32", "parity_mixed", "fast", "exact"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (slices per network per step)")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--model", default="fuseunet", choices=["fuseunet", "unet"],
+                    help="unet = BASELINE.json configs[4] shape (single-modal UNet pair, kidney flavour: eval-mode "
+                         "pseudo-label forwards); the default is the metric's configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fast-mode / train-only side measurements")
     ap.add_argument("--roofline-json", default="", help="also write the per-layer conv table to this file")
@@ -69,9 +72,16 @@ def parse():
 # ---------------------------------------------------------------------------------------------------------
 # synthetic workload: randn images, Bernoulli(0.08) masks, 4 augmented views, rate 0.25
 # ---------------------------------------------------------------------------------------------------------
-def make_batch(B, S, seed, device=None, pin=False):
+def make_batch(B, S, seed, device=None, pin=False, modalities=2):
     g = torch.Generator().manual_seed(seed)
     img = lambda: torch.randn(B, 3, S, S, generator=g)
+    if modalities == 1:
+        x = img()
+        t1 = (torch.rand(B, S, S, generator=g) < 0.08).long()
+        t2 = (torch.rand(B, S, S, generator=g) < 0.08).long()
+        augs = [img() for _ in range(4)]
+        mv = (lambda t: t.pin_memory()) if pin else ((lambda t: t.to(device)) if device is not None else (lambda t: t))
+        return dict(x=mv(x), t1=mv(t1), t2=mv(t2), augs=[mv(a) for a in augs])
     x = (img(), img())
     t1 = (torch.rand(B, S, S, generator=g) < 0.08).long()
     t2 = (torch.rand(B, S, S, generator=g) < 0.08).long()
@@ -336,14 +346,17 @@ def main():
     except OSError:
         pass
 
+    unet = args.model == "unet"
+    nmod = 1 if unet else 2
+
     def build(mode):
-        tr = AideTrainer("fuseunet", mode=mode, device=device, seed=2 + 0)
+        tr = AideTrainer(args.model, mode=mode, device=device, seed=2 + 0, flavour="kidney" if unet else "chaos")
         tr.broadcast_parameters(0)
         return tr
 
     tr = build(args.mode)
     n_pool = 2
-    dev_batches = [make_batch(B, S, 1234 + 97 * rank + i, device=device) for i in range(n_pool)]
+    dev_batches = [make_batch(B, S, 1234 + 97 * rank + i, device=device, modalities=nmod) for i in range(n_pool)]
 
     def dev_step(i):
         b = dev_batches[i % n_pool]
@@ -362,7 +375,7 @@ def main():
     value = world * B * K / (ms / 1e3)
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of losses / Dice
-    host_batches = [make_batch(B, S, 4321 + 97 * rank + i, pin=True) for i in range(n_pool)]
+    host_batches = [make_batch(B, S, 4321 + 97 * rank + i, pin=True, modalities=nmod) for i in range(n_pool)]
     io = {}
 
     def host_step(i):
@@ -394,7 +407,17 @@ def main():
     }
     out["algorithmic_tflops"] = round(value * out["config"]["algorithmic_gflop_per_slice"] / 1e3, 1)
 
-    if rank == 0:
+    if unet:
+        # side configuration: report the step rate only (the roofline / CPU legs describe the metric's fuseunet workload)
+        fwd = {256: 130.703, 320: 204.223, 512: 522.812}.get(S)
+        out["config"]["workload"] = ("AIDE proposed step, kidney flavour: 2x UNet (single modality), eval-mode pseudo-label "
+                                     "forwards (BASELINE.json configs[4] shape)")
+        out["config"]["modalities"] = 1
+        out["config"]["algorithmic_gflop_per_slice"] = round(14 * fwd, 1) if fwd else None
+        out["algorithmic_tflops"] = round(value * 14 * fwd / 1e3, 1) if fwd else None
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    elif rank == 0:
         from aide_b200 import engine as E
         fmt_inf, fmt_train = E.mode_format(args.mode, False), E.mode_format(args.mode, True)
         # The dominant kernel launches of the step are the convolutions of the stacked pseudo-label forward (4 views x B
