@@ -45,6 +45,8 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_upsample2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_upsample2x_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "aide_zero_insert2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "aide_zero_insert2x_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_conv1x1_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "aide_conv1x1_bwd_rows": (_i, [_i, _i, _i, _i]),
     "aide_conv1x1_bwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -169,9 +169,80 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dhi, int ctot, i
   }
 }
 
+// ---------------------------------------------------------------- zero-insert x2 (ConvTranspose2d(k=2, s=2) front end)
+// nn.ConvTranspose2d(Cin, Cout, kernel_size=2, stride=2) (netblocks.py:12, learned_bilinear=True) equals a 3x3 / pad 1
+// convolution of the zero-inserted input X'[2h,2w] = x[h,w] (0 elsewhere) with K[co,ci,1-a,1-b] = W[ci,co,a,b]: the
+// engine reuses its conv3x3 unit (forward, dgrad, wgrad) and only needs this copy.  Raw 16-byte vectors per plane.
+__global__ void zero_insert2x_kernel(const uint4* __restrict__ s0, const uint4* __restrict__ s1, int s_ctot_v, int s_coff_v,
+                                     uint4* __restrict__ d0, uint4* __restrict__ d1, int d_ctot_v, int d_coff_v, int N,
+                                     int h, int w, int Cv) {
+  const int H = 2 * h, W = 2 * w;
+  const size_t total = (size_t)N * H * W * Cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv);
+    const size_t pix = i / Cv;
+    const int ox = (int)(pix % W), oy = (int)((pix / W) % H);
+    const size_t n = pix / ((size_t)W * H);
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (((ox | oy) & 1) == 0) {
+      const size_t sp = ((n * h + (oy >> 1)) * w + (ox >> 1)) * s_ctot_v + s_coff_v + c;
+      a = s0[sp];
+      if (s1) b = s1[sp];
+    }
+    const size_t dp = pix * d_ctot_v + d_coff_v + c;
+    d0[dp] = a;
+    if (d1) d1[dp] = b;
+  }
+}
+
+// transpose: d_lo[n,h,w,c] = d_hi[n,2h,2w,c]
+__global__ void zero_insert2x_bwd_kernel(const float* __restrict__ dhi, int ctot, int coff, float* __restrict__ dlo, int N,
+                                         int h, int w, int C) {
+  const int C4 = C >> 2;
+  const size_t total = (size_t)N * h * w * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const size_t pix = i / C4;
+    const int ix = (int)(pix % w), iy = (int)((pix / w) % h);
+    const size_t n = pix / ((size_t)w * h);
+    *reinterpret_cast<float4*>(dlo + pix * C + c) =
+        *reinterpret_cast<const float4*>(dhi + ((n * 2 * h + 2 * iy) * (size_t)(2 * w) + 2 * ix) * ctot + coff + c);
+  }
+}
+
 }  // namespace aide
 
 using namespace aide;
+
+extern "C" int aide_zero_insert2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,
+                                      void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff, int N, int h, int w, int C,
+                                      void* stream) {
+  AIDE_REQUIRE(fmt_valid(fmt) && src_p0 && dst_p0 && N > 0 && h > 0 && w > 0, "zero_insert2x_fwd: bad arguments");
+  const int vec = 16 / fmt_elem_bytes(fmt);            // channels per 16-byte vector
+  AIDE_REQUIRE(C % vec == 0 && src_ctot % vec == 0 && src_coff % vec == 0 && dst_ctot % vec == 0 && dst_coff % vec == 0,
+               "zero_insert2x_fwd: channel counts / offsets must be multiples of %d", vec);
+  AIDE_REQUIRE(fmt_planes(fmt) == 1 || (src_p1 && dst_p1), "zero_insert2x_fwd: two-plane format needs both planes");
+  const size_t total = (size_t)N * 4 * h * w * (C / vec);
+  long long blocks = (long long)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  zero_insert2x_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(src_p0), reinterpret_cast<const uint4*>(fmt_planes(fmt) == 2 ? src_p1 : nullptr),
+      src_ctot / vec, src_coff / vec, reinterpret_cast<uint4*>(dst_p0),
+      reinterpret_cast<uint4*>(fmt_planes(fmt) == 2 ? dst_p1 : nullptr), dst_ctot / vec, dst_coff / vec, N, h, w, C / vec);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_zero_insert2x_bwd(const float* dhi, int dhi_ctot, int dhi_coff, float* dlo, int N, int h, int w,
+                                      int C, void* stream) {
+  AIDE_REQUIRE(dhi && dlo && C % 4 == 0 && dhi_coff % 4 == 0 && dhi_ctot % 4 == 0, "zero_insert2x_bwd: bad arguments");
+  const size_t total = (size_t)N * h * w * (C / 4);
+  long long blocks = (long long)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  zero_insert2x_bwd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(dhi, dhi_ctot, dhi_coff, dlo, N, h, w, C);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
 
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 

@@ -78,6 +78,8 @@ class Unit:
     dst: Optional[Tuple[str, int]]   # full-resolution destination view of y
     pools: List[Tuple[str, int]] = field(default_factory=list)  # half-resolution destinations of maxpool(y)
     first: bool = False              # input is a network input (fp32 NHWC, 3 channels): CUDA-core path
+    transposed: bool = False         # the parameter is a ConvTranspose2d(k=2, s=2) weight [Cin,Cout,2,2] (netblocks.py:12):
+                                     # run as conv3x3 on the zero-inserted input with K[co,ci,1-a,1-b] = W[ci,co,a,b]
 
 
 @dataclass
@@ -86,6 +88,7 @@ class Upsample:
     dst: str
     c: int
     level: int           # level of the SOURCE (low resolution)
+    mode: str = "bilinear"   # "bilinear": nn.Upsample(2, bilinear, align_corners=True); "zero": zero insertion (ConvTranspose2d)
 
 
 @dataclass
@@ -107,18 +110,21 @@ def _block(ops, units, prefix, cin, cout, level, src, dst, pools, mid_buf, bufs,
     units += [u1, u2]
 
 
-def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes: int):
+def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes: int, learned_bilinear: bool = False):
     """Four UNet_basic_up_block (netblocks.py:137-147) + last_conv1.  Skip tensors already live in the
-    upper half of the cat buffers (cat((upsampled, skip)) -> channels [C, 2C))."""
+    upper half of the cat buffers (cat((upsampled, skip)) -> channels [C, 2C)).  learned_bilinear: the up path is
+    ConvTranspose2d(k=2,s=2) -> BN -> ReLU (netblocks.py:11-14; Sequential indices 0, 1) instead of
+    Upsample -> Conv2d(3x3) -> BN -> ReLU (indices 1, 2)."""
     x, cx = bottom, skips_c[0] * 2
     for i, c in enumerate(skips_c, 1):            # c = 512, 256, 128, 64 ; level = 4 - i
         lvl = 4 - i
         up, cat, mid, out = f"up{i}", f"cat{i}", f"u{i}m", f"u{i}o"
         bufs[up] = (lvl, cx)
         bufs[out] = (lvl, c)
-        ops.append(Upsample(x, up, cx, lvl + 1))
-        u = Unit(f"up_block{i}.up", f"up_block{i}.bilinear_up.1", f"up_block{i}.bilinear_up.2", cx, c, lvl,
-                 (up, 0), (cat, 0), [])
+        ops.append(Upsample(x, up, cx, lvl + 1, "zero" if learned_bilinear else "bilinear"))
+        ci, bi = (0, 1) if learned_bilinear else (1, 2)
+        u = Unit(f"up_block{i}.up", f"up_block{i}.bilinear_up.{ci}", f"up_block{i}.bilinear_up.{bi}", cx, c, lvl,
+                 (up, 0), (cat, 0), [], transposed=learned_bilinear)
         ops.append(u)
         units.append(u)
         _block(ops, units, f"up_block{i}.block", 2 * c, c, lvl, (cat, 0), (out, 0), [], mid, bufs)
@@ -126,7 +132,7 @@ def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes:
     ops.append(("head", x, cx))
 
 
-def plan_fuseunet(num_classes: int = 2) -> Plan:
+def plan_fuseunet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
     """fuseunet.forward (fuseunet.py:43-91): modal-1 encoder consumes the fused concat, modal-2 is independent."""
     bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3), "in1": (0, 3)}
     ops: list = [("input", 0, "in0"), ("input", 1, "in1")]
@@ -150,11 +156,11 @@ def plan_fuseunet(num_classes: int = 2) -> Plan:
                f"a{lvl + 1}m", bufs, first=lvl == 0)
         _block(ops, units, f"modal2_downblock{lvl + 1}.block", cin_b, c, lvl, src_b, (fused[0], fused[1] + c), pool_b,
                f"b{lvl + 1}m", bufs, first=lvl == 0)
-    _decoder(ops, units, bufs, "y5", [512, 256, 128, 64], num_classes)
+    _decoder(ops, units, bufs, "y5", [512, 256, 128, 64], num_classes, learned_bilinear)
     return Plan("fuseunet", 2, num_classes, bufs, ops, units)
 
 
-def plan_unet(num_classes: int = 2) -> Plan:
+def plan_unet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
     """UNet.forward (UNet.py:152-165); max-pool inside down blocks 2..5 (UNet.py:117-121)."""
     bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3)}
     ops: list = [("input", 0, "in0")]
@@ -173,7 +179,7 @@ def plan_unet(num_classes: int = 2) -> Plan:
         cin = 3 if lvl == 0 else width[lvl - 1]
         _block(ops, units, f"down_block{lvl + 1}.block", cin, c, lvl, src, dst, pools, f"d{lvl + 1}m", bufs,
                first=lvl == 0)
-    _decoder(ops, units, bufs, "x5", [512, 256, 128, 64], num_classes)
+    _decoder(ops, units, bufs, "x5", [512, 256, 128, 64], num_classes, learned_bilinear)
     return Plan("unet", 1, num_classes, bufs, ops, units)
 
 
@@ -223,6 +229,22 @@ def _stream() -> int:
 # ------------------------------------------------------------------------------------------------
 # weights in operand format (re-derived when a parameter's version changes)
 # ------------------------------------------------------------------------------------------------
+def conv_weight_oihw(u: Unit, params: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """The unit's 3x3 weight in nn.Conv2d layout [Cout,Cin,3,3].  For a ConvTranspose2d(k=2,s=2) parameter
+    W [Cin,Cout,2,2] this is K[co,ci,1-a,1-b] = W[ci,co,a,b] with the other five taps zero (tensor re-indexing only)."""
+    w = params[u.conv + ".weight"]
+    if not u.transposed:
+        return w
+    k = w.new_zeros((u.cout, u.cin, 3, 3))
+    k[:, :, 0:2, 0:2] = w.detach().permute(1, 0, 2, 3).flip(2, 3)
+    return k
+
+
+def transposed_weight_grad(gk: torch.Tensor) -> torch.Tensor:
+    """dW [Cin,Cout,2,2] of a ConvTranspose2d weight from the gradient of its 3x3 stand-in K [Cout,Cin,3,3]."""
+    return gk[:, :, 0:2, 0:2].flip(2, 3).permute(1, 0, 2, 3).contiguous()
+
+
 class PreparedWeights:
     """Operand-format copies of every conv3x3 weight: forward [Cout][9][Cin] and dgrad [Cin][9][Cout]
     planes (aide_weight_prep).  One instance per parameter *version*; tapes hold a reference so a later
@@ -252,7 +274,7 @@ class PreparedWeights:
             f = FMT_F32 if u.first else fmt
             fwd, dg, pb = self.off[u.name]
             two = _planes(f) == 2
-            w = params[u.conv + ".weight"]
+            w = conv_weight_oihw(u, params)
             call("aide_weight_prep", f, w.data_ptr(), u.cout, u.cin, base + fwd, base + fwd + pb if two else None,
                  base + dg if dg >= 0 else None, base + dg + pb if (dg >= 0 and two) else None, st)
 
@@ -332,7 +354,7 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             h, w = H >> op.level, W >> op.level
             s = _view(layout, base, op.src, 0)
             d = _view(layout, base, op.dst, 0)
-            call("aide_upsample2x_fwd", fmt, *s, *d, N, h, w, op.c, st)
+            call("aide_upsample2x_fwd" if op.mode == "bilinear" else "aide_zero_insert2x_fwd", fmt, *s, *d, N, h, w, op.c, st)
         else:
             _, name, cin = op
             x0, x1, xct, xco = _view(layout, base, name, 0)
@@ -483,8 +505,8 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             # the (single) consumer of op.dst is the up-conv unit; its dX is the high-resolution gradient
             consumer = next(u for u in plan.units if u.src[0] == op.dst)
             h, w = H >> op.level, W >> op.level
-            call("aide_upsample2x_bwd", bb + off["dx:" + consumer.name], consumer.cin, 0, bb + off["dlo:" + op.dst],
-                 N, h, w, op.c, st)
+            call("aide_upsample2x_bwd" if op.mode == "bilinear" else "aide_zero_insert2x_bwd",
+                 bb + off["dx:" + consumer.name], consumer.cin, 0, bb + off["dlo:" + op.dst], N, h, w, op.c, st)
         elif isinstance(op, Unit):
             u = op
             h, w = H >> u.level, W >> u.level

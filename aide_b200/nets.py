@@ -31,10 +31,10 @@ class basic_block(nn.Module):
 
 
 def UNet_up_conv_bn_relu(input_channel: int, output_channel: int, learned_bilinear: bool = False) -> nn.Sequential:
-    if learned_bilinear:
-        raise NotImplementedError(
-            "learned_bilinear=True (ConvTranspose2d decoder, netblocks.py:11-14) is not built yet; no reference "
-            "script enables it (SURVEY.md section 0, item 2)")
+    if learned_bilinear:                              # netblocks.py:11-14 / UNet.py:6-9
+        return nn.Sequential(nn.ConvTranspose2d(input_channel, output_channel, kernel_size=2, stride=2),
+                             nn.BatchNorm2d(output_channel),
+                             nn.ReLU())
     return nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
                          nn.Conv2d(input_channel, output_channel, kernel_size=3, padding=1),
                          nn.BatchNorm2d(output_channel),
@@ -191,7 +191,9 @@ class _EngineNet(nn.Module):
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
                        dlogits.contiguous(), flat)
         self.last_grad_flat = flat
-        return [self._glayout.view(flat, n) for n, _ in self.named_parameters()]
+        tw = {u.conv + ".weight" for u in self._plan.units if u.transposed}
+        return [E.transposed_weight_grad(self._glayout.view(flat, n)) if n in tw else self._glayout.view(flat, n)
+                for n, _ in self.named_parameters()]
 
     def _run(self, *inputs):
         self._check_inputs(inputs)
@@ -224,7 +226,7 @@ class fuseunet(_EngineNet):
         self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
         self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
         self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
-        self._engine_setup(E.plan_fuseunet(num_classes), mode)
+        self._engine_setup(E.plan_fuseunet(num_classes, learned_bilinear), mode)
 
     def forward(self, modal1_inputs, modal2_inputs):
         return self._run(modal1_inputs, modal2_inputs)
@@ -245,7 +247,7 @@ class UNet(_EngineNet):
         self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
         self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
         self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
-        self._engine_setup(E.plan_unet(num_classes), mode)
+        self._engine_setup(E.plan_unet(num_classes, learned_bilinear), mode)
 
     def forward(self, x):
         return self._run(x)

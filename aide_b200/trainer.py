@@ -58,6 +58,9 @@ class AideTrainer:
         ctor = fuseunet if kind == "fuseunet" else UNet
         self.net1 = ctor(num_classes=2, mode=mode).to(self.device).train()
         self.net2 = ctor(num_classes=2, mode=mode).to(self.device).train()
+        if any(u.transposed for u in self.net1._plan.units):
+            raise NotImplementedError("AideTrainer keeps parameters in the flat gradient layout; ConvTranspose2d decoders "
+                                      "(learned_bilinear=True) run through the nn.Module / torch.optim path")
         self.opt1 = FlatAdamAMSGrad(grad_order_params(self.net1), lr=lr)
         self.opt2 = FlatAdamAMSGrad(grad_order_params(self.net2), lr=lr)
         for net, opt in ((self.net1, self.opt1), (self.net2, self.opt2)):

@@ -147,6 +147,16 @@ int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src
 int aide_upsample2x_bwd(const float* dhi, int dhi_ctot, int dhi_coff, float* dlo, int N, int h, int w, int C,
                         void* stream);
 
+/* ---- nn.ConvTranspose2d(Cin, Cout, kernel_size=2, stride=2) (netblocks.py:12, learned_bilinear=True) ------------- */
+/* The transposed convolution equals conv3x3(pad 1) of the zero-inserted input X'[2h,2w] = x[h,w] (0 elsewhere) with
+ * K[co,ci,1-a,1-b] = W[ci,co,a,b]; these two entry points are the zero insertion and its transpose, the GEMM work runs
+ * on aide_conv3x3_fwd / _dgrad / _wgrad.  src/dst are operand-format views, dhi/dlo fp32. */
+int aide_zero_insert2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,
+                           void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff, int N, int h, int w, int C,
+                           void* stream);
+int aide_zero_insert2x_bwd(const float* dhi, int dhi_ctot, int dhi_coff, float* dlo, int N, int h, int w, int C,
+                           void* stream);
+
 /* ---- last_conv1: 1x1 conv C -> K + bias (fuseunet.py:41,89; UNet.py:150,164) --------------------- */
 int aide_conv1x1_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int C,
                      const float* w /*[K][C]*/, const float* bias, float* logits_nchw, int K,

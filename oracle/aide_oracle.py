@@ -71,10 +71,22 @@ def _add_basic_block(p: Params, name: str, cin: int, cout: int) -> None:
     _add_bn(p, name + ".bn2", cout)
 
 
-def _add_up_block(p: Params, name: str, cin: int, cprev: int, cout: int) -> None:
-    # bilinear_up = Sequential(Upsample, Conv2d, BatchNorm2d, ReLU) -> indices 1, 2 hold tensors
-    _add_conv(p, name + ".bilinear_up.1", cin, cprev)
-    _add_bn(p, name + ".bilinear_up.2", cprev)
+def _add_up_block(p: Params, name: str, cin: int, cprev: int, cout: int, learned_bilinear: bool = False) -> None:
+    if learned_bilinear:
+        # bilinear_up = Sequential(ConvTranspose2d(k=2,s=2), BatchNorm2d, ReLU) (netblocks.py:11-14) -> indices 0, 1.
+        # nn.ConvTranspose2d default init: kaiming_uniform(a=sqrt 5) on [Cin,Cout,2,2]; torch computes fan_in from
+        # dim 1, i.e. Cout * 4, for the bias bound as well
+        w = torch.empty(cin, cprev, 2, 2)
+        torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        b = torch.empty(cprev)
+        bound = 1.0 / math.sqrt(cprev * 4)
+        torch.nn.init.uniform_(b, -bound, bound)
+        p[name + ".bilinear_up.0.weight"], p[name + ".bilinear_up.0.bias"] = w, b
+        _add_bn(p, name + ".bilinear_up.1", cprev)
+    else:
+        # bilinear_up = Sequential(Upsample, Conv2d, BatchNorm2d, ReLU) -> indices 1, 2 hold tensors
+        _add_conv(p, name + ".bilinear_up.1", cin, cprev)
+        _add_bn(p, name + ".bilinear_up.2", cprev)
     _add_basic_block(p, name + ".block", cprev * 2, cout)
 
 
@@ -84,7 +96,7 @@ UNET_ENC = [(3, 64), (64, 128), (128, 256), (256, 512), (512, 1024)]  # UNet.py:
 DECODER = [(1024, 512, 512), (512, 256, 256), (256, 128, 128), (128, 64, 64)]
 
 
-def init_fuseunet(num_classes: int = 2) -> Params:
+def init_fuseunet(num_classes: int = 2, learned_bilinear: bool = False) -> Params:
     """Same state_dict (keys, shapes, values under the same torch seed) as fuseunet()."""
     p: Params = {}
     for lvl, (c1, _, co) in enumerate(FUSE_ENC, 1):
@@ -92,17 +104,17 @@ def init_fuseunet(num_classes: int = 2) -> Params:
     for lvl, (_, c2, co) in enumerate(FUSE_ENC, 1):
         _add_basic_block(p, f"modal2_downblock{lvl}.block", c2, co)
     for i, (ci, cp, co) in enumerate(DECODER, 1):
-        _add_up_block(p, f"up_block{i}", ci, cp, co)
+        _add_up_block(p, f"up_block{i}", ci, cp, co, learned_bilinear)
     _add_conv(p, "last_conv1", 64, num_classes, k=1)
     return p
 
 
-def init_unet(num_classes: int = 2) -> Params:
+def init_unet(num_classes: int = 2, learned_bilinear: bool = False) -> Params:
     p: Params = {}
     for lvl, (ci, co) in enumerate(UNET_ENC, 1):
         _add_basic_block(p, f"down_block{lvl}.block", ci, co)
     for i, (ci, cp, co) in enumerate(DECODER, 1):
-        _add_up_block(p, f"up_block{i}", ci, cp, co)
+        _add_up_block(p, f"up_block{i}", ci, cp, co, learned_bilinear)
     _add_conv(p, "last_conv1", 64, num_classes, k=1)
     return p
 
@@ -141,6 +153,15 @@ def _basic_block(p: Params, name: str, x: torch.Tensor, training: bool) -> torch
 
 def _up_block(p: Params, name: str, skip: torch.Tensor, x: torch.Tensor, training: bool) -> torch.Tensor:
     # netblocks.py:137-147 : up -> conv/bn/relu -> cat((x, skip)) -> basic_block
+    if name + ".bilinear_up.0.weight" in p:        # learned_bilinear=True (netblocks.py:11-14): ConvTranspose2d -> BN -> ReLU
+        bn = name + ".bilinear_up.1"
+        x = F.conv_transpose2d(x, p[name + ".bilinear_up.0.weight"], p[name + ".bilinear_up.0.bias"], stride=2)
+        if training:
+            p[bn + ".num_batches_tracked"] += 1
+        x = F.relu(F.batch_norm(x, p[bn + ".running_mean"], p[bn + ".running_var"], p[bn + ".weight"], p[bn + ".bias"],
+                                training, BN_MOMENTUM, BN_EPS))
+        x = torch.cat((x, skip), dim=1)
+        return _basic_block(p, name + ".block", x, training)
     x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
     x = _conv_bn_relu(p, name + ".bilinear_up.1", name + ".bilinear_up.2", x, training)
     x = torch.cat((x, skip), dim=1)

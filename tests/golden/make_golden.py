@@ -261,5 +261,58 @@ def main():
             print("  ka256", k, v)
 
 
+def main_learned_bilinear():
+    """learned_bilinear=True (ConvTranspose2d decoder, netblocks.py:11-14 / UNet.py:6-9): the oracle against the
+    unmodified reference, frozen into golden_lb.pt.   python tests/golden/make_golden.py lb"""
+    out = {}
+    torch.set_num_threads(8)
+    crit_mean = refutils.CEMDiceLoss(cediceweight=[1.0, 1.0], ceclassweight=torch.tensor([1.0, 1.0]),
+                                     diceclassweight=[1.0, 1.0])
+    torch.manual_seed(2)
+    rf, ru = RefFuse(num_classes=2, learned_bilinear=True), RefUNet(num_classes=2, learned_bilinear=True)
+    torch.manual_seed(2)
+    check_state(rf, O.init_fuseunet(2, True), "fuseunet(learned_bilinear)")
+    check_state(ru, O.init_unet(2, True), "UNet(learned_bilinear)")
+    out["fuse_keys"], out["unet_keys"] = list(rf.state_dict().keys()), list(ru.state_dict().keys())
+    for tag, (b, h, w) in {"s32": (2, 32, 32), "s48x64": (3, 48, 64)}.items():
+        (x1, x2), t1, t2, _ = O.synthetic_batch(b, h, w, seed=1234)
+        case = {}
+        for kind, Ref, fwd, xs in (("fuse", RefFuse, O.fuseunet_forward, (x1, x2)), ("unet", RefUNet, O.unet_forward, (x1,))):
+            torch.manual_seed(2)
+            net = Ref(num_classes=2, learned_bilinear=True)
+            p = O.clone_params(dict(net.state_dict()), requires_grad=True)
+            net.train()
+            y_ref = net(*xs)
+            y_or = fwd(p, *xs, training=True)
+            same(y_ref, y_or, f"{tag} {kind} lb logits")
+            check_state(net, {k: v.detach() for k, v in p.items()}, f"{tag} {kind} lb post-fwd buffers")
+            l_ref = crit_mean(y_ref, t2)
+            same(l_ref, O.ce_dice_mean(y_or, t2), f"{tag} {kind} lb CEMDiceLoss")
+            names = [k for k, _ in net.named_parameters()]
+            g_ref = grads_of(l_ref, [q for _, q in net.named_parameters()])
+            g_or = grads_of(O.ce_dice_mean(y_or, t2), [p[k] for k in names])
+            for k, a, c in zip(names, g_ref, g_or):
+                same(a, c, f"{tag} {kind} lb grad {k}")
+            net.eval()
+            with torch.no_grad():
+                ye = net(*xs)
+                same(ye, fwd({k: v.detach() for k, v in p.items()}, *xs, training=False), f"{tag} {kind} lb eval logits")
+            case[kind] = dict(logits=y_ref.detach().clone(), loss_mean=l_ref.item(), logits_eval=ye.clone(),
+                              grad_last_w=g_ref[names.index("last_conv1.weight")].clone(),
+                              grad_up1_w_sub=g_ref[names.index("up_block1.bilinear_up.0.weight")][::16, ::16].clone(),
+                              grad_up1_w_sum=g_ref[names.index("up_block1.bilinear_up.0.weight")].double().sum().item(),
+                              grad_up4_w=g_ref[names.index("up_block4.bilinear_up.0.weight")].clone(),
+                              grad_up4_b=g_ref[names.index("up_block4.bilinear_up.0.bias")].clone(),
+                              grad_absmax={k: g.abs().max().item() for k, g in zip(names, g_ref)},
+                              rv_up=net.up_block2.bilinear_up[1].running_var.clone())
+        out[tag] = case
+    torch.save(out, os.path.join(HERE, "golden_lb.pt"))
+    print("oracle == reference (learned_bilinear) on every check; wrote golden_lb.pt (%.1f KB)"
+          % (os.path.getsize(os.path.join(HERE, "golden_lb.pt")) / 1024))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "lb":
+        main_learned_bilinear()
+    else:
+        main()

@@ -336,3 +336,51 @@ def test_grouped_augmented_forward_equals_sequential_forwards(oracle, kind, trai
             assert int(sa[k]) == int(sb[k]) == (G if training else 0)
         elif "running" in k:
             assert relmax(sb[k], sa[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("mode", ["exact", "parity"])
+@pytest.mark.parametrize("kind", ["fuse", "unet"])
+def test_learned_bilinear_decoder_vs_reference_vectors(oracle, kind, mode):
+    """learned_bilinear=True: ConvTranspose2d(k=2,s=2) -> BN -> ReLU up path (netblocks.py:11-14, UNet.py:6-9), run
+    by the engine as conv3x3 on the zero-inserted input.  Forward vs vectors frozen from the unmodified reference,
+    gradients vs the oracle (robust measures at this tiny size, see oracle_sensitivity_band), state_dict layout of
+    the reference (bilinear_up.0 = ConvTranspose2d [Cin,Cout,2,2], bilinear_up.1 = BatchNorm)."""
+    import os
+    import aide_b200
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_lb.pt"), weights_only=False)
+    b, h, w = 3, 48, 64
+    (x1, x2), t1, t2, _ = oracle.synthetic_batch(b, h, w, seed=1234)
+    xs = (x1, x2) if kind == "fuse" else (x1,)
+    torch.manual_seed(2)
+    net = (aide_b200.fuseunet if kind == "fuse" else aide_b200.UNet)(num_classes=2, learned_bilinear=True, mode=mode).to(dev)
+    assert list(net.state_dict().keys()) == g["fuse_keys" if kind == "fuse" else "unet_keys"]
+    assert tuple(net.up_block1.bilinear_up[0].weight.shape) == (1024, 512, 2, 2)
+    net.train()
+    y = net(*[x.to(dev) for x in xs])
+    c = g["s48x64"][kind]
+    assert relmax(y, c["logits"]) < LOGIT_TOL[mode]
+    loss = aide_b200.CEMDiceLoss([1., 1.], [1., 1.], [1., 1.])(y, t2.to(dev))
+    assert abs(loss.item() - c["loss_mean"]) < 2e-5
+    loss.backward()
+    torch.manual_seed(2)
+    p = oracle.clone_params((oracle.init_fuseunet if kind == "fuse" else oracle.init_unet)(2, True), requires_grad=True)
+    yo = (oracle.fuseunet_forward if kind == "fuse" else oracle.unet_forward)(p, *xs, training=True)
+    names = [k for k in p if not oracle.is_buffer(k) and not is_prebn_bias(k) and not k.endswith("bilinear_up.0.bias")]
+    go = dict(zip(names, torch.autograd.grad(oracle.ce_dice_mean(yo, t2), [p[k] for k in names])))
+    eng = dict(net.named_parameters())
+    for k in names:
+        assert eng[k].grad is not None and eng[k].grad.shape == go[k].shape, k
+    assert relmax(eng["last_conv1.weight"].grad, c["grad_last_w"]) < 2e-3
+    fa = torch.cat([eng[k].grad.detach().cpu().double().flatten() for k in names])
+    fb = torch.cat([go[k].detach().double().flatten() for k in names])
+    assert 1.0 - torch.nn.functional.cosine_similarity(fa, fb, dim=0).item() < 1e-3
+    up = [k for k in names if k.endswith("bilinear_up.0.weight")]
+    fa = torch.cat([eng[k].grad.detach().cpu().double().flatten() for k in up])
+    fb = torch.cat([go[k].detach().double().flatten() for k in up])
+    assert 1.0 - torch.nn.functional.cosine_similarity(fa, fb, dim=0).item() < 1e-3       # the transposed-conv weights
+    assert relmax(net.up_block2.bilinear_up[1].running_var, c["rv_up"]) < 1e-4
+    net.eval()
+    with torch.no_grad():
+        ye = net(*[x.to(dev) for x in xs])
+    assert relmax(ye, c["logits_eval"]) < 1e-3

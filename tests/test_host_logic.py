@@ -69,8 +69,12 @@ def test_no_cpu_fallback():
         net(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError, match="CUDA only"):
         aide_b200.CEMDiceLossImage()(torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long))
-    with pytest.raises(NotImplementedError):
-        aide_b200.fuseunet(learned_bilinear=True)
+    # learned_bilinear=True keeps the reference's module tree: ConvTranspose2d at index 0, BatchNorm at index 1
+    lb = aide_b200.fuseunet(learned_bilinear=True)
+    assert isinstance(lb.up_block1.bilinear_up[0], torch.nn.ConvTranspose2d)
+    assert tuple(lb.up_block1.bilinear_up[0].weight.shape) == (1024, 512, 2, 2)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        lb(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32))
 
 
 def test_dropin_packages_import():

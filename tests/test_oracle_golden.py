@@ -130,3 +130,33 @@ def test_reverseaug_restatement_matches_pil_bit_for_bit(oracle):
             got = oracle.reverseaug_plane(np.ascontiguousarray(x), flip, 0 - deg)
             assert np.array_equal(ref, got), (H, W, deg, flip)
             assert rotate_matrix(0 - deg, W, H) == oracle.rotate_matrix(0 - deg, W, H)
+
+
+@pytest.mark.parametrize("tag,shape", [("s32", (2, 32, 32)), ("s48x64", (3, 48, 64))])
+def test_learned_bilinear_networks(oracle, tag, shape):
+    """learned_bilinear=True (ConvTranspose2d(k=2,s=2) -> BN -> ReLU up path, netblocks.py:11-14 / UNet.py:6-9): the
+    oracle against vectors frozen from the unmodified reference (tests/golden/make_golden.py lb)."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_lb.pt"), weights_only=False)
+    b, h, w = shape
+    (x1, x2), t1, t2, _ = oracle.synthetic_batch(b, h, w, seed=1234)
+    for kind, init, fwd, xs, keys in (("fuse", oracle.init_fuseunet, oracle.fuseunet_forward, (x1, x2), "fuse_keys"),
+                                      ("unet", oracle.init_unet, oracle.unet_forward, (x1,), "unet_keys")):
+        torch.manual_seed(2)
+        p = oracle.clone_params(init(2, True), requires_grad=True)
+        assert list(p.keys()) == g[keys]
+        y = fwd(p, *xs, training=True)
+        c = g[tag][kind]
+        assert torch.allclose(y, c["logits"], rtol=0, atol=2e-5 * c["logits"].abs().max().item())
+        loss = oracle.ce_dice_mean(y, t2)
+        assert abs(loss.item() - c["loss_mean"]) < 2e-6
+        names = ["last_conv1.weight", "up_block4.bilinear_up.0.weight", "up_block4.bilinear_up.0.bias",
+                 "up_block1.bilinear_up.0.weight"]
+        gl, g4w, g4b, g1w = torch.autograd.grad(loss, [p[k] for k in names])
+        for got, want in ((gl, c["grad_last_w"]), (g4w, c["grad_up4_w"]), (g4b, c["grad_up4_b"]),
+                          (g1w[::16, ::16], c["grad_up1_w_sub"])):
+            assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-9
+        assert torch.allclose(p["up_block2.bilinear_up.1.running_var"], c["rv_up"], rtol=1e-5)
+        with torch.no_grad():
+            ye = fwd({k: v.detach() for k, v in p.items()}, *xs, training=False)
+        assert torch.allclose(ye, c["logits_eval"], rtol=0, atol=1e-4 * c["logits_eval"].abs().max().item())
