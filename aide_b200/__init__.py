@@ -15,7 +15,7 @@ from ._lib import AideError, FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, LIB_PATH,
 from .engine import MODES, default_mode  # noqa: F401
 from .nets import UNet, fuseunet  # noqa: F401
 from .losses import (CEDiceLoss, CEMDiceLoss, CEMDiceLossImage, CrossEntropyLoss2d, Dice_Loss, DiceLoss,  # noqa: F401
-                     Dice_fn, MulticlassDiceLoss, MulticlassMSELoss, coteach_step, pseudo_label)
+                     Dice_fn, MulticlassDiceLoss, MulticlassMSELoss, coteach_step, predict_mask, pseudo_label)
 from .coteach_loss import (Coteachingloss_dropimage, Coteachingloss_dropimagedroppixel,  # noqa: F401
                            Coteachingloss_dropregionce, Coteachingloss_weightimage)
 from .optim import FlatAdamAMSGrad, PolyLR  # noqa: F401

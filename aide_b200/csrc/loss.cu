@@ -272,6 +272,43 @@ extern "C" int aide_loss_bwd(const float* logits, const int64_t* targets, const 
   return 0;
 }
 
+// ---------------------------------------------------------------- hard mask: argmax(softmax(logits, 1), 1) as uint8
+// (trainchaos_proposed_30cases1labeled.py:407-409, evalchaos_comparison_1cases.py:208-214).  The softmax is evaluated
+// like the reference does (exp(z - max) / sum, fp32) and the FIRST maximum wins, as in torch.argmax.
+namespace aide {
+__global__ void argmax_mask_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int N, int K, size_t HW) {
+  const size_t total = (size_t)N * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i - n * HW;
+    const float* z = logits + n * K * HW + hw;
+    float m = z[0];
+    for (int k = 1; k < K; ++k) m = fmaxf(m, z[k * HW]);
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) sum += expf(z[k * HW] - m);
+    int best = 0;
+    float pb = expf(z[0] - m) / sum;
+    for (int k = 1; k < K; ++k) {
+      const float p = expf(z[k * HW] - m) / sum;
+      if (p > pb) {
+        pb = p;
+        best = k;
+      }
+    }
+    mask[i] = (uint8_t)best;
+  }
+}
+}  // namespace aide
+
+extern "C" int aide_argmax_mask(const float* logits, uint8_t* mask, int N, int K, int H, int W, void* stream) {
+  AIDE_REQUIRE(logits && mask && N > 0 && K >= 1 && K <= 255 && H > 0 && W > 0, "argmax_mask: bad arguments");
+  const size_t total = (size_t)N * H * W;
+  long long blocks = (long long)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  aide::argmax_mask_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(logits, mask, N, K, (size_t)H * W);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo, float* q,
                                  float* wm, void* stream) {
   AIDE_REQUIRE(aug_logits && n_aug >= 1 && n_aug <= 8 && q && wm, "pseudo_label: 1..8 augmented logit tensors");

@@ -259,6 +259,18 @@ def Dice_fn(inputs, targets, threshold=0.5):
     return dfn
 
 
+def predict_mask(logits: torch.Tensor) -> torch.Tensor:
+    """uint8 [N,H,W] hard mask = argmax(softmax(logits, 1), 1) in one kernel (the per-slice mask emission of the
+    pseudo-label rewrite and evaluation passes, trainchaos_proposed_30cases1labeled.py:407-409)."""
+    if not logits.is_cuda:
+        raise RuntimeError("aide_b200 runs on CUDA only (there is no CPU fallback)")
+    x = logits.detach().contiguous().float()
+    N, K, H, W = x.shape
+    mask = torch.empty((N, H, W), dtype=torch.uint8, device=x.device)
+    call("aide_argmax_mask", x.data_ptr(), mask.data_ptr(), N, K, H, W, _stream())
+    return mask
+
+
 # -------------------------------------------------------------------------------------------------
 # pseudo labels + fused co-teaching step
 # -------------------------------------------------------------------------------------------------

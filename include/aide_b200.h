@@ -194,6 +194,9 @@ int aide_loss_bwd(const float* logits, const int64_t* targets, const float* q, c
  * (trainchaos_proposed_30cases1labeled.py:274-292,97-101). */
 int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo,
                       float* q /*[N,2,H,W]*/, float* wm /*[N,1,H,W]*/, void* stream);
+/* Hard segmentation mask argmax(softmax(logits, 1), 1) as uint8 [N,H,W] (pseudo-label / evaluation passes,
+ * trainchaos_proposed_30cases1labeled.py:407-409, evalchaos_comparison_1cases.py:208-214); first maximum wins. */
+int aide_argmax_mask(const float* logits, uint8_t* mask, int N, int K, int H, int W, void* stream);
 /* Reverse augmentation of augmented-forward outputs (trainchaos_proposed_30cases1labeled.py:81-95, which round-trips
  * every plane through PIL on the CPU): optional horizontal flip, then PIL's Image.rotate(-degree, BILINEAR) about the
  * centre with fill 0, reproduced bit for bit.  src/dst: [n_img,K,H,W] fp32 (different buffers); per image a row-major

@@ -395,3 +395,14 @@ def test_reverse_augmentation_matches_pil_bit_for_bit(dev, oracle):
 
 def rnd_tensor(*shape, seed=0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_predict_mask_equals_reference_argmax(dev, golden):
+    """argmax(softmax(logits,1),1) as uint8 in one kernel vs the reference's two torch calls on the CPU
+    (trainchaos_proposed_30cases1labeled.py:407-409), on golden logits, on multi-class logits and on exact ties."""
+    import aide_b200 as A
+    lg = golden["loss"]["logits"] if "loss" in golden and "logits" in golden["loss"] else rnd(4, 2, 24, 40, seed=3)
+    for t in (lg, rnd(2, 5, 17, 9, seed=4), torch.zeros(1, 3, 4, 4), rnd(3, 2, 32, 32, seed=5).round()):
+        ref = torch.argmax(F.softmax(t, dim=1), dim=1).to(torch.uint8)
+        got = A.predict_mask(t.to(dev))
+        assert got.dtype == torch.uint8 and torch.equal(got.cpu(), ref)
