@@ -150,51 +150,51 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
+// blockDim = (cx, ty), grid = (row blocks, channel groups).  threadIdx.x owns 4 channels; whole rows of pixels (or of
+// 2x2 windows) are dealt to blocks and threadIdx.y walks along the row, so the inner loop has no integer division
+// (the 1-D version spent most of its instruction budget on 64-bit index arithmetic: 0.63 of the HBM roofline).
 template <int FMT, bool POOL>
 __global__ void bn_relu_apply_kernel(const float* __restrict__ z, int N, int H, int W, int C,
                                      const float* __restrict__ scale_shift, View dst, View pa, View pb,
                                      int imgs_per_group) {
   // scale_shift: [groups][2][C]; image n uses group n / imgs_per_group (one group = plain forward)
-  const int C4 = C >> 2;
-  if constexpr (!POOL) {
-    size_t total = (size_t)N * H * W * C4;
-    const size_t pix_per_group = (size_t)imgs_per_group * H * W;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-      int c = (int)(i % C4) * 4;
-      size_t pix = i / C4;
-      const float* ss = scale_shift + (pix / pix_per_group) * 2 * C;
-      float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-      float4 sh = __ldg(reinterpret_cast<const float4*>(ss + C + c));
-      float4 v = *reinterpret_cast<const float4*>(z + pix * C + c);
-      st4<FMT>(dst.p0, dst.p1, pix * dst.ctot + dst.coff + c, bn_relu4(v, sc, sh));
-    }
-  } else {
-    const int Hh = H >> 1, Wh = W >> 1;
-    size_t total = (size_t)N * Hh * Wh * C4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-      int c = (int)(i % C4) * 4;
-      size_t win = i / C4;
-      int wx = (int)(win % Wh);
-      int hy = (int)((win / Wh) % Hh);
-      int n = (int)(win / ((size_t)Wh * Hh));
-      const float* ss = scale_shift + (size_t)(n / imgs_per_group) * 2 * C;
-      float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
-      float4 sh = __ldg(reinterpret_cast<const float4*>(ss + C + c));
-      size_t p00 = ((size_t)n * H + 2 * hy) * W + 2 * wx;
-      size_t p01 = p00 + 1, p10 = p00 + W, p11 = p10 + 1;
-      float4 y00 = bn_relu4(*reinterpret_cast<const float4*>(z + p00 * C + c), sc, sh);
-      float4 y01 = bn_relu4(*reinterpret_cast<const float4*>(z + p01 * C + c), sc, sh);
-      float4 y10 = bn_relu4(*reinterpret_cast<const float4*>(z + p10 * C + c), sc, sh);
-      float4 y11 = bn_relu4(*reinterpret_cast<const float4*>(z + p11 * C + c), sc, sh);
-      if (dst.p0) {
-        st4<FMT>(dst.p0, dst.p1, p00 * dst.ctot + dst.coff + c, y00);
-        st4<FMT>(dst.p0, dst.p1, p01 * dst.ctot + dst.coff + c, y01);
-        st4<FMT>(dst.p0, dst.p1, p10 * dst.ctot + dst.coff + c, y10);
-        st4<FMT>(dst.p0, dst.p1, p11 * dst.ctot + dst.coff + c, y11);
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int rows_per_img = POOL ? (H >> 1) : H;
+  const int total_rows = N * rows_per_img;
+  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
+    const int n = row / rows_per_img, y = row - n * rows_per_img;          // block-uniform
+    const float* ss = scale_shift + (size_t)(n / imgs_per_group) * 2 * C;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(ss + C + c));
+    if constexpr (!POOL) {
+      const size_t p0 = ((size_t)n * H + y) * W;
+      for (int x = threadIdx.y; x < W; x += blockDim.y) {
+        const size_t pix = p0 + x;
+        const float4 v = *reinterpret_cast<const float4*>(z + pix * C + c);
+        st4<FMT>(dst.p0, dst.p1, pix * dst.ctot + dst.coff + c, bn_relu4(v, sc, sh));
       }
-      float4 m = max4(max4(y00, y01), max4(y10, y11));
-      if (pa.p0) st4<FMT>(pa.p0, pa.p1, win * pa.ctot + pa.coff + c, m);
-      if (pb.p0) st4<FMT>(pb.p0, pb.p1, win * pb.ctot + pb.coff + c, m);
+    } else {
+      const int Wh = W >> 1;
+      const size_t prow = ((size_t)n * H + 2 * y) * W;
+      const size_t wrow = ((size_t)n * rows_per_img + y) * Wh;
+      for (int wx = threadIdx.y; wx < Wh; wx += blockDim.y) {
+        const size_t p00 = prow + 2 * wx, p01 = p00 + 1, p10 = p00 + W, p11 = p10 + 1;
+        const size_t win = wrow + wx;
+        float4 y00 = bn_relu4(*reinterpret_cast<const float4*>(z + p00 * C + c), sc, sh);
+        float4 y01 = bn_relu4(*reinterpret_cast<const float4*>(z + p01 * C + c), sc, sh);
+        float4 y10 = bn_relu4(*reinterpret_cast<const float4*>(z + p10 * C + c), sc, sh);
+        float4 y11 = bn_relu4(*reinterpret_cast<const float4*>(z + p11 * C + c), sc, sh);
+        if (dst.p0) {
+          st4<FMT>(dst.p0, dst.p1, p00 * dst.ctot + dst.coff + c, y00);
+          st4<FMT>(dst.p0, dst.p1, p01 * dst.ctot + dst.coff + c, y01);
+          st4<FMT>(dst.p0, dst.p1, p10 * dst.ctot + dst.coff + c, y10);
+          st4<FMT>(dst.p0, dst.p1, p11 * dst.ctot + dst.coff + c, y11);
+        }
+        float4 m = max4(max4(y00, y01), max4(y10, y11));
+        if (pa.p0) st4<FMT>(pa.p0, pa.p1, win * pa.ctot + pa.coff + c, m);
+        if (pb.p0) st4<FMT>(pb.p0, pb.p1, win * pb.ctot + pb.coff + c, m);
+      }
     }
   }
 }
@@ -490,15 +490,21 @@ extern "C" int aide_bn_relu_apply_grouped(int fmt, const float* z, int N, int im
                "bn_relu_apply: channel offsets must be multiples of 4");
   View dst{dst_p0, dst_p1, dst_ctot, dst_coff}, pa{poolA_p0, poolA_p1, poolA_ctot, poolA_coff},
       pb{poolB_p0, poolB_p1, poolB_ctot, poolB_coff};
-  size_t total = (size_t)N * H * W * (C / 4) / (pool ? 4 : 1);
-  int blocks = (int)((total + 255) / 256);
-  int cap = kNumSMs * 16;
-  if (blocks > cap) blocks = cap;
+  const int c4 = C / 4;
+  int cx = c4 < 32 ? c4 : 32;                     // threads across channels (x 4 channels each)
+  while (cx & (cx - 1)) cx &= cx - 1;             // power of two
+  const dim3 block(cx, 256 / cx);
+  const int total_rows = N * (pool ? H / 2 : H);
+  int rb = total_rows;
+  const int cgroups = ceil_div(c4, cx);
+  const int cap = kNumSMs * 16 / cgroups > 0 ? kNumSMs * 16 / cgroups : 1;
+  if (rb > cap) rb = cap;
+  const dim3 grid(rb, cgroups);
   if (pool) {
-    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, true><<<blocks, 256, 0, as_stream(stream)>>>(
+    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, true><<<grid, block, 0, as_stream(stream)>>>(
                                z, N, H, W, C, scale_shift, dst, pa, pb, imgs_per_group)));
   } else {
-    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, false><<<blocks, 256, 0, as_stream(stream)>>>(
+    AIDE_DISPATCH_FMT(fmt, (bn_relu_apply_kernel<FMT, false><<<grid, block, 0, as_stream(stream)>>>(
                                z, N, H, W, C, scale_shift, dst, pa, pb, imgs_per_group)));
   }
   AIDE_CHECK_LAUNCH();

@@ -88,37 +88,41 @@ __device__ __forceinline__ void st8(void* p0, void* p1, size_t e, const float (&
   }
 }
 
-// one thread = one output pixel x 8 channels; blockDim.x walks the channels of a pixel, blockIdx / threadIdx.y the
-// pixels, so the source-index arithmetic is done once per pixel row of threads and all accesses are 128-bit
+// blockDim = (cx, ty): threadIdx.x walks the channels of a pixel in 8-channel (128-bit) vectors, whole OUTPUT rows are
+// dealt to blocks and threadIdx.y walks along the row -- the vertical source rows / weights are block-uniform and the
+// inner loop has no integer division.
 template <int FMT>
 __global__ void upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w, int C, float sh, float sw) {
   const int H = 2 * h, W = 2 * w;
-  const size_t npix = (size_t)N * H * W;
-  for (size_t pix = (size_t)blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += (size_t)gridDim.x * blockDim.y) {
-    const int ox = (int)(pix % W);
-    const int oy = (int)((pix / W) % H);
-    const int n = (int)(pix / ((size_t)W * H));
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
+  const int total_rows = N * H;
+  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
+    const int n = row / H, oy = row - n * H;
+    int y0, y1;
+    float ly0, ly1;
     src_index(sh, oy, h, y0, y1, ly0, ly1);
-    src_index(sw, ox, w, x0, x1, lx0, lx1);
     const size_t r0 = ((size_t)n * h + y0) * w, r1 = ((size_t)n * h + y1) * w;
-    const size_t s00 = (r0 + x0) * src.ctot + src.coff, s01 = (r0 + x1) * src.ctot + src.coff;
-    const size_t s10 = (r1 + x0) * src.ctot + src.coff, s11 = (r1 + x1) * src.ctot + src.coff;
-    const size_t d0 = pix * dst.ctot + dst.coff;
-    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
-      float a[8], b[8], d[8], e[8], o[8];
-      ld8<FMT>(src.p0, src.p1, s00 + c, a);
-      ld8<FMT>(src.p0, src.p1, s01 + c, b);
-      ld8<FMT>(src.p0, src.p1, s10 + c, d);
-      ld8<FMT>(src.p0, src.p1, s11 + c, e);
+    const size_t drow = (size_t)row * W;
+    for (int ox = threadIdx.y; ox < W; ox += blockDim.y) {
+      int x0, x1;
+      float lx0, lx1;
+      src_index(sw, ox, w, x0, x1, lx0, lx1);
+      const size_t s00 = (r0 + x0) * src.ctot + src.coff, s01 = (r0 + x1) * src.ctot + src.coff;
+      const size_t s10 = (r1 + x0) * src.ctot + src.coff, s11 = (r1 + x1) * src.ctot + src.coff;
+      const size_t d0 = (drow + ox) * dst.ctot + dst.coff;
+      for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+        float a[8], b[8], d[8], e[8], o[8];
+        ld8<FMT>(src.p0, src.p1, s00 + c, a);
+        ld8<FMT>(src.p0, src.p1, s01 + c, b);
+        ld8<FMT>(src.p0, src.p1, s10 + c, d);
+        ld8<FMT>(src.p0, src.p1, s11 + c, e);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        // same operation order as the 4-channel kernel: along W first, then along H
-        const float t0 = lx0 * a[k] + lx1 * b[k], t1 = lx0 * d[k] + lx1 * e[k];
-        o[k] = ly0 * t0 + ly1 * t1;
+        for (int k = 0; k < 8; ++k) {
+          // same operation order as the 4-channel kernel: along W first, then along H
+          const float t0 = lx0 * a[k] + lx1 * b[k], t1 = lx0 * d[k] + lx1 * e[k];
+          o[k] = ly0 * t0 + ly1 * t1;
+        }
+        st8<FMT>(dst.p0, dst.p1, d0 + c, o);
       }
-      st8<FMT>(dst.p0, dst.p1, d0 + c, o);
     }
   }
 }
@@ -258,8 +262,7 @@ extern "C" int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_
     int cx = C / 8 < 32 ? C / 8 : 32;                   // threads across the channels of one pixel
     while (cx & (cx - 1)) cx &= cx - 1;                 // power of two
     const dim3 block(cx, 256 / cx);
-    const size_t npix = (size_t)N * 4 * h * w;
-    long long blocks = (long long)((npix + block.y - 1) / block.y);
+    long long blocks = (long long)N * 2 * h;            // one output row per block iteration
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     const float sh = ac_scale(h, 2 * h), sw = ac_scale(w, 2 * w);
     if (fmt == AIDE_FMT_F16X2)
