@@ -77,6 +77,39 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// Tiled version for cout % 32 == 0 and cin % 32 == 0 (every tensor-core layer): a block stages a [32 co][32 ci][9]
+// tile through shared memory so that the OIHW read (288 contiguous floats per output channel) and both operand-plane
+// writes (32 consecutive ci per (co, tap) row of the forward layout, 32 consecutive co per (ci, tap) row of the dgrad
+// layout) are coalesced; the one-thread-per-element kernel above strides every access.
+template <int FMT>
+__global__ void __launch_bounds__(256) weight_prep_tiled_kernel(const float* __restrict__ w, int cout, int cin, void* f0,
+                                                                void* f1, void* d0, void* d1) {
+  constexpr int CO_STRIDE = 32 * 9 + 1;                 // +1: lanes across co hit different banks
+  __shared__ float tile[32 * CO_STRIDE];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int co = i / 288, r = i - co * 288;           // r = ci_local * 9 + tap: contiguous in OIHW
+    tile[co * CO_STRIDE + r] = w[((size_t)(co0 + co) * cin + ci0) * 9 + r];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr float ws = FMT == AIDE_FMT_F16X2 ? kF16WScale / kF16ActScale : 1.0f;   // st1 applies 2^8; weights carry 2^12
+  if (f0) {
+    for (int row = wid; row < 32 * 9; row += 8) {       // row = co_local * 9 + tap, lanes = ci
+      const int co = row / 9, tap = row - co * 9;
+      const float v = tile[co * CO_STRIDE + lane * 9 + tap] * ws;
+      st1<FMT>(f0, f1, ((size_t)(co0 + co) * 9 + tap) * cin + ci0 + lane, v);
+    }
+  }
+  if (d0) {
+    for (int row = wid; row < 32 * 9; row += 8) {       // row = ci_local * 9 + tap, lanes = co
+      const int ci = row / 9, tap = row - ci * 9;
+      const float v = tile[lane * CO_STRIDE + ci * 9 + tap] * ws;
+      st1<FMT>(d0, d1, ((size_t)(ci0 + ci) * 9 + (8 - tap)) * cout + co0 + lane, v);
+    }
+  }
+}
+
 }  // namespace aide
 
 using namespace aide;
@@ -111,6 +144,12 @@ extern "C" int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
   AIDE_REQUIRE(w_oihw && cout > 0 && cin > 0 && (fwd_p0 || dgrad_p0), "weight_prep: bad arguments");
   AIDE_REQUIRE(fmt_planes(fmt) == 1 || ((!fwd_p0 || fwd_p1) && (!dgrad_p0 || dgrad_p1)),
                "weight_prep: TF32X2 / F16X2 need two planes");
+  if (cout % 32 == 0 && cin % 32 == 0) {
+    AIDE_DISPATCH_FMT(fmt, (weight_prep_tiled_kernel<FMT><<<dim3(cout / 32, cin / 32), 256, 0, as_stream(stream)>>>(
+                               w_oihw, cout, cin, fwd_p0, fwd_p1, dgrad_p0, dgrad_p1)));
+    AIDE_CHECK_LAUNCH();
+    return 0;
+  }
   size_t total = (size_t)cout * cin * 9;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
