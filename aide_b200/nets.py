@@ -140,7 +140,15 @@ class _EngineNet(nn.Module):
         logits, _ = self._engine_forward(views, keep_tape=False, groups=G)
         return list(logits.chunk(G, dim=0))
 
-    def _engine_forward(self, inputs, keep_tape: bool, groups: int = 1):
+    def graphed_eval(self, *example_inputs):
+        """A CUDA-graph replay of the eval-mode forward for inputs shaped like `example_inputs` ("next" row f3 of
+        SURVEY.md section 8: the per-epoch case loops of trainchaos_proposed_30cases1labeled.py:373-496 and
+        evalchaos_comparison_1cases.py:203-214 run thousands of single-slice forwards; eagerly each one is ~100
+        launches of ~50 us host time).  Returns a callable `f(*inputs) -> logits`; the logits tensor is the graph's
+        static output (overwritten by the next call).  The graph is re-captured when a weight changes."""
+        return _GraphedEval(self, example_inputs)
+
+    def _engine_forward(self, inputs, keep_tape: bool, groups: int = 1, arena: Optional[torch.Tensor] = None):
         plan = self._plan
         fmt = E.mode_format(self.engine_mode, keep_tape)
         first = inputs[0][0] if groups > 1 else inputs[0]
@@ -161,7 +169,10 @@ class _EngineNet(nn.Module):
         if wts is None or wts.key != wkey or (need_dgrad and not wts.has_dgrad):
             wts = self._weights[fmt] = E.PreparedWeights(plan, named, fmt, need_dgrad)
         dev = first.device
-        if keep_tape:
+        if arena is not None:
+            if arena.numel() < layout.total:
+                raise ValueError("arena too small for this forward")
+        elif keep_tape:
             arena = torch.empty(layout.total, dtype=torch.uint8, device=dev)
         else:
             if self._scratch is None or self._scratch.numel() < layout.total or self._scratch.device != dev:
@@ -202,6 +213,51 @@ class _EngineNet(nn.Module):
             return _NetFunction.apply(self, len(inputs), *inputs, *params)
         logits, _ = self._engine_forward(inputs, keep_tape=False)
         return logits
+
+
+class _GraphedEval:
+    """Captured eval-mode forward of one network for one input shape (see _EngineNet.graphed_eval)."""
+
+    def __init__(self, net: "_EngineNet", example_inputs):
+        if net.training:
+            raise RuntimeError("graphed_eval() is for eval mode: call net.eval() first")
+        net._check_inputs(example_inputs)
+        self.net = net
+        self.static_in = [torch.empty_like(x) for x in example_inputs]
+        self.graph = None
+        self.out = None
+        self._wkey = None
+        self._arena = None
+
+    def _weights_key(self):
+        named = self.net._named()
+        return tuple((named[u.conv + ".weight"].data_ptr(), named[u.conv + ".weight"]._version)
+                     for u in self.net._plan.units)
+
+    def _capture(self):
+        net = self.net
+        with torch.no_grad():
+            out, _ = net._engine_forward(self.static_in, keep_tape=False)      # warm-up: weight planes, layouts
+            torch.cuda.synchronize()
+            N, _, H, W = self.static_in[0].shape
+            fmt = E.mode_format(net.engine_mode, False)
+            total = net._layouts[(N, H, W, fmt, 1)].total
+            self._arena = torch.empty(total, dtype=torch.uint8, device=self.static_in[0].device)   # owned by the graph
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out, _ = net._engine_forward(self.static_in, keep_tape=False, arena=self._arena)
+        self._wkey = self._weights_key()
+        self._weights = net._weights.get(fmt)          # keep the operand planes the captured kernels read alive
+
+    def __call__(self, *inputs):
+        if self.net.training:
+            raise RuntimeError("the captured forward is an eval-mode forward")
+        if self.graph is None or self._weights_key() != self._wkey:
+            self._capture()
+        for d, s_ in zip(self.static_in, inputs):
+            d.copy_(s_, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 # -------------------------------------------------------------------------------------------------

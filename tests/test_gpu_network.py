@@ -384,3 +384,39 @@ def test_learned_bilinear_decoder_vs_reference_vectors(oracle, kind, mode):
     with torch.no_grad():
         ye = net(*[x.to(dev) for x in xs])
     assert relmax(ye, c["logits_eval"]) < 1e-3
+
+
+def test_graphed_eval_forward_equals_eager_and_is_faster(oracle):
+    """Single-slice evaluation forwards (trainchaos_proposed_30cases1labeled.py:403-409) replayed as one CUDA graph:
+    bit-identical to the eager launch sequence, re-captured when the weights change."""
+    import time
+    import aide_b200 as A
+    dev = torch.device("cuda:0")
+    net = build("fuse", "parity", dev).eval()
+    g = torch.Generator().manual_seed(5)
+    xs = [tuple(torch.randn(1, 3, 256, 256, generator=g).to(dev) for _ in range(2)) for _ in range(3)]
+    f = net.graphed_eval(*xs[0])
+    with torch.no_grad():
+        for x in xs:
+            eager = net(*x).clone()
+            assert torch.equal(f(*x), eager)
+        mask = A.predict_mask(f(*xs[0]))
+        assert mask.shape == (1, 256, 256) and mask.dtype == torch.uint8
+        # weights change -> the captured operand planes are stale -> re-capture
+        net.last_conv1.bias.add_(0.25)
+        net.up_block4.block.conv2.weight.mul_(1.5)
+        assert torch.equal(f(*xs[1]), net(*xs[1]))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            f(*xs[2])
+        torch.cuda.synchronize()
+        t_graph = (time.perf_counter() - t0) / 20
+        t0 = time.perf_counter()
+        for _ in range(20):
+            net(*xs[2])
+        torch.cuda.synchronize()
+        t_eager = (time.perf_counter() - t0) / 20
+    print(f"single-slice eval forward 256x256: graph {t_graph * 1e3:.2f} ms ({1 / t_graph:.0f} slices/s), "
+          f"eager {t_eager * 1e3:.2f} ms")
+    assert t_graph < t_eager
