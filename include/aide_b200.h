@@ -18,9 +18,11 @@
  *       AIDE_FMT_TF32X2 two fp32 planes hi = rn_tf32(x), lo = x - hi ("parity mode": 3 tcgen05
  *                       kind::tf32 MMAs hi*hi + hi*lo + lo*hi reproduce fp32 products)
  *       AIDE_FMT_BF16   one bf16 plane ("fast mode": single kind::f16 MMA)
- *       AIDE_FMT_F16X2  two fp16 planes hi = fp16(x*2^s), lo = fp16(x*2^s - hi), s a per-tensor-class power of
- *                       two (activations 2^8, weights 2^12): three kind::f16 MMAs hi*hi + hi*lo + lo*hi give the
- *                       same 22-bit products as TF32X2 at twice the tensor-core rate and half the operand bytes
+ *       AIDE_FMT_F16X2  two fp16 planes hi = fp16(x*2^s), lo = fp16(x*2^s - hi), s a power of two (activations 2^8,
+ *                       weights 2^12, gradients: chosen per tensor ON THE DEVICE by aide_bn_relu_bwd_apply): the
+ *                       products hi*hi + hi*lo + lo*hi give the same 22-bit mantissas as TF32X2 at twice the
+ *                       tensor-core rate and half the operand bytes.  This is the default "parity" format for
+ *                       forward, dgrad and wgrad.
  *     Raw convolution outputs (z), gradients w.r.t. activations and all reductions are fp32.
  */
 #ifndef AIDE_B200_H_
@@ -61,10 +63,10 @@ int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
 /* z[n,h,w,co] = bias[co] + sum_{tap,ci} x[n,h+dy,w+dx,ci] * w[co][tap][ci].
  * Also emits per-tile BatchNorm partial statistics (sum z, sum z^2 per channel) when stat_partial
  * != NULL: layout [rows][2][cout] fp32 with rows = aide_conv3x3_stat_rows(...).
- * The same entry point computes dgrad when given dgrad-prepared weights (bias = stats = NULL).
  * F32 -> CUDA-core kernels (a dedicated HBM-bound kernel for the networks' first layer, cin == 3 and cout in
- * {32, 64}; a generic tiled kernel otherwise); TF32X2/BF16 -> tcgen05 implicit GEMM fed by TMA (needs cin%32==0
- * (TF32X2) or cin%32==0 (BF16), cout%32==0; other shapes -> error). */
+ * {32, 64}; a generic tiled kernel otherwise); TF32X2 / BF16 / F16X2 -> tcgen05 implicit GEMM fed by TMA (needs
+ * cin % 32 == 0 and cout % 32 == 0; other shapes -> error): the halo-reuse kernel (conv_halo_tc.cu) for maps of at
+ * least 8x8 pixels, the first-generation kernel (conv_fwd_tc.cu) below that. */
 int aide_conv3x3_stat_rows(int fmt, int cin, int cout, int N, int H, int W);
 int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
                      const void* w_p0, const void* w_p1, const float* bias,
