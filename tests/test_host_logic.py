@@ -154,3 +154,51 @@ def test_stat_rows_scale_with_batch_groups():
             r8 = lib.aide_conv3x3_stat_rows(fmt, cin, cout, 8, h, h)
             r32 = lib.aide_conv3x3_stat_rows(fmt, cin, cout, 32, h, h)
             assert r8 > 0 and r32 == 4 * r8, (fmt, cin, cout, h, r8, r32)
+
+
+def test_transposed_conv_is_conv3x3_on_zero_inserted_input():
+    """Host-side algebra behind learned_bilinear=True (netblocks.py:11-14): ConvTranspose2d(k=2,s=2)(x) equals
+    conv3x3(pad 1) of the zero-inserted input with K[co,ci,1-a,1-b] = W[ci,co,a,b] (engine.conv_weight_oihw), and the
+    gradient of W is the re-indexed gradient of K (engine.transposed_weight_grad)."""
+    import torch.nn.functional as F
+    from aide_b200 import engine as E
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 5, 6, generator=g)
+    W = torch.randn(8, 4, 2, 2, generator=g)
+    b = torch.randn(4, generator=g)
+    u = E.Unit("t", "c", "bn", 8, 4, 0, ("a", 0), None, [], False, True)
+    K = E.conv_weight_oihw(u, {"c.weight": W})
+    xz = torch.zeros(2, 8, 10, 12)
+    xz[:, :, ::2, ::2] = x
+    assert torch.equal(F.conv2d(xz, K, b, padding=1), F.conv_transpose2d(x, W, b, stride=2))
+    gK = torch.randn(4, 8, 3, 3, generator=g)
+    W2 = W.clone().requires_grad_(True)
+    K2 = torch.zeros(4, 8, 3, 3)
+    K2[:, :, 0:2, 0:2] = W2.permute(1, 0, 2, 3).flip(2, 3)
+    (K2 * gK).sum().backward()
+    assert torch.equal(W2.grad, E.transposed_weight_grad(gK))
+    # plans: the ConvTranspose parameter names / indices of the reference's Sequential
+    p = E.plan_fuseunet(2, learned_bilinear=True)
+    ups = [v for v in p.units if v.transposed]
+    assert [v.conv for v in ups] == [f"up_block{i}.bilinear_up.0" for i in range(1, 5)]
+    assert [v.bn for v in ups] == [f"up_block{i}.bilinear_up.1" for i in range(1, 5)]
+    assert all(op.mode == "zero" for op in p.ops if isinstance(op, E.Upsample))
+
+
+def test_trainer_reverse_aug_parameters_follow_pil(oracle):
+    """AideTrainer._aug_host builds, per (view, sample), the inverse affine matrix / fast-path mode / flip flag the
+    reverse-augmentation kernel consumes; they must be PIL's (oracle.rotate_matrix restates PIL.Image.rotate), with
+    views beyond a sample's `augno` left as the identity."""
+    from aide_b200.trainer import AideTrainer
+    augset = {"augno": [4, 2, 4], "degree1": [10.0, -33.5, 0.0], "degree2": [90.0, 45.0, 180.0],
+              "degree3": [-60.0, 12.0, 7.25], "degree4": [0.0, 5.0, -90.0],
+              "hflip1": [1, 0, 1], "hflip2": [0, 1, 0], "hflip3": [1, 1, 0], "hflip4": [0, 1, 1]}
+    mats, modes, flips = AideTrainer._aug_host(augset, 4, 3, 64, 64)
+    for v in range(4):
+        for b in range(3):
+            if augset["augno"][b] <= v:
+                assert int(modes[v, b]) == 1 and int(flips[v, b]) == 0
+                continue
+            mode, m = oracle.rotate_matrix(0 - augset[f"degree{v + 1}"][b], 64, 64)
+            assert int(modes[v, b]) == mode and mats[v, b].tolist() == m
+            assert int(flips[v, b]) == augset[f"hflip{v + 1}"][b]
