@@ -59,7 +59,9 @@ SIGNATURES = {
     "aide_reverse_aug": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "aide_coteach_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_adam_amsgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
-    "aide_adam_amsgrad_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp, _vp, _f, _vp]),
+    "aide_coteach_select_ex": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp,
+                                    _vp, _vp]),
+    "aide_adam_amsgrad_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp, _vp, _f, _vp, _vp]),
 }
 
 

@@ -9,11 +9,12 @@ namespace aide {
 __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, float* __restrict__ vmax, size_t n, float lr, float b1,
                                     float b2, float eps, float bc1, float bc2_sqrt, float gscale,
-                                    const float* __restrict__ bc_dev) {
+                                    const float* __restrict__ bc_dev, const float* __restrict__ lr_dev) {
   if (bc_dev) {               // bias corrections computed on the device (CUDA-graph friendly step counter)
     bc1 = bc_dev[0];
     bc2_sqrt = bc_dev[1];
   }
+  if (lr_dev) lr = *lr_dev;   // learning rate read from device memory: a scheduler can change it under a captured graph
   const float step_size = lr / bc1;
   size_t n4 = n >> 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -67,12 +68,12 @@ using namespace aide;
 
 static int adam_launch(float* p, const float* g, float* m, float* v, float* vmax, size_t n, float lr, float beta1,
                        float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale, const float* bc_dev,
-                       cudaStream_t st) {
+                       const float* lr_dev, cudaStream_t st) {
   int blocks = (int)(((n >> 2) + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   if (blocks < 1) blocks = 1;
   adam_amsgrad_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, vmax, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale,
-                                              bc_dev);
+                                              bc_dev, lr_dev);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -85,17 +86,18 @@ extern "C" int aide_adam_amsgrad(float* p, const float* g, float* m, float* v, f
   if (n == 0) return 0;
   double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   return adam_launch(p, g, m, v, vmax, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, nullptr,
-                     as_stream(stream));
+                     nullptr, as_stream(stream));
 }
 
 extern "C" int aide_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, size_t n, float lr,
                                      float beta1, float beta2, float eps, int* step_counter, float* bc_scratch,
-                                     float grad_scale, void* stream) {
+                                     float grad_scale, const float* lr_dev, void* stream) {
   AIDE_REQUIRE(p && g && m && v && vmax && step_counter && bc_scratch, "adam_amsgrad_dev: bad arguments");
   AIDE_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vmax) % 16 == 0,
                "adam_amsgrad_dev: buffers must be 16-byte aligned");
   adam_prelude_kernel<<<1, 1, 0, as_stream(stream)>>>(step_counter, bc_scratch, (double)beta1, (double)beta2);
   AIDE_CHECK_LAUNCH();
   if (n == 0) return 0;
-  return adam_launch(p, g, m, v, vmax, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, bc_scratch, as_stream(stream));
+  return adam_launch(p, g, m, v, vmax, n, lr, beta1, beta2, eps, 1.f, 1.f, grad_scale, bc_scratch, lr_dev,
+                     as_stream(stream));
 }

@@ -57,6 +57,7 @@ struct HaloParams {
   int BN, kc, n_cchunks, row_bytes;
   int MB, nacc, nbuf, tmem_cols;
   int stack, acc_w;                              // hi/lo weight planes stacked along N (see the MMA issuer); columns per accumulator
+  int lo_col;                                    // stacked mode: column offset of the A_lo x W_hi product (BN = with hi*lo, 0 = with hi*hi)
   int a_slot_bytes, a_stage_bytes, a_stages;
   int b_plane_bytes, b_stage_bytes, b_stages;
   int b_off, bar_off;
@@ -191,8 +192,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
     const uint32_t idesc = make_idesc(TF32 ? 2u : (KIND == K_BF16 ? 1u : 0u), 0u, 0u, 128u, (uint32_t)p.BN);
     // Stacked split-precision step: the weight stage holds the hi plane followed by the lo plane, i.e. ONE K-major
     // operand of 2*BN rows, so  A_hi x [W_hi; W_lo]  is a single MMA of width 2*BN writing hi*hi to columns [0, BN) and
-    // hi*lo to [BN, 2*BN); A_lo x W_hi follows into [0, BN) and the epilogue adds the two halves.  Two MMAs instead of
-    // three, the first of them wide -- narrow cout tiles are bound by operand fetch per MMA, not by tensor work.
+    // hi*lo to [BN, 2*BN); A_lo x W_hi follows into [BN, 2*BN) as well (lo_col) and the epilogue adds the two halves.
+    // Two MMAs instead of three, the first of them wide -- narrow cout tiles are bound by operand fetch per MMA, not by
+    // tensor work.  Keeping BOTH small cross terms out of the hi*hi columns halves the number of truncating
+    // accumulations into the large partial sum (tcgen05 truncates when it adds into TMEM): the cross terms are 2^-11
+    // smaller, so is the truncation error of their own chain.
     const uint32_t idesc2 = make_idesc(TF32 ? 2u : (KIND == K_BF16 ? 1u : 0u), 0u, 0u, 128u, (uint32_t)(2 * p.BN));
     const bool stack = NPL == 2 && p.stack != 0;
     const uint32_t layout = NKS == 4 ? 2u : 4u;
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
                   const uint32_t flag = ks == 0 ? flag0 : 1u;
                   if (NPL == 2 && stack) {
                     umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(2 * ks), idesc2, flag);
-                    umma<TF32>(acc, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, 1u);
+                    umma<TF32>(acc + (uint32_t)p.lo_col, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, 1u);
                   } else if (NPL == 2) {
                     umma<TF32>(acc, a_hi + (uint64_t)(a_plane16 + 2 * ks), b_hi + (uint64_t)(2 * ks), idesc, flag);
                     umma<TF32>(acc, a_hi + (uint64_t)(2 * ks), b_hi + (uint64_t)(b_plane16 + 2 * ks), idesc, 1u);
@@ -505,6 +509,7 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
   AIDE_REQUIRE(make_plan(fmt, cin, cout, p.m_tiles, &pl), "conv3x3(halo): no tiling fits (cin=%d cout=%d)", cin, cout);
   p.BN = pl.BN; p.MB = pl.MB; p.nacc = pl.nacc; p.nbuf = pl.nbuf;
   p.stack = pl.stack; p.acc_w = pl.BN * (1 + pl.stack);
+  p.lo_col = (pl.stack && env_int("AIDE_CONV_LOSEP", 1)) ? pl.BN : 0;
   p.row_bytes = pl.row_bytes;
   p.kc = pl.row_bytes / es;
   p.n_cchunks = cin / p.kc;

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <unordered_map>
+
 namespace aide {
 
 using namespace ptx;
@@ -58,11 +60,46 @@ static int encode_tmap(CUtensorMap* m, int dtype, int rank, const void* base, co
   const CUtensorMapDataType dt = dtype == 1   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // Encoded maps are cached per host thread, keyed on everything that defines them (the module path of
+  // an unmodified training script re-issues the same ~100 conv calls per forward on the same arena addresses).
+  struct Key {
+    const void* base;
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4];
+    int dtype, rank, swizzle;
+    bool operator==(const Key& o) const { return std::memcmp(this, &o, sizeof(Key)) == 0; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+      uint64_t h = 1469598103934665603ull;
+      for (size_t i = 0; i < sizeof(Key) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+      return (size_t)h;
+    }
+  };
+  static_assert(sizeof(Key) % 8 == 0, "Key is hashed as 64-bit words");
+  static thread_local std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  Key key;
+  std::memset(&key, 0, sizeof(key));
+  key.base = base;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i + 1 < rank) key.strides[i] = strides_bytes[i];
+  }
+  key.dtype = dtype; key.rank = rank; key.swizzle = swizzle_bytes;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *m = it->second;
+    return 0;
+  }
   CUresult r = fn(m, dt, (cuuint32_t)rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AIDE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d box %u,%u swizzle %d)", (int)r,
                rank, box[0], box[1], swizzle_bytes);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *m);
   return 0;
 }
 

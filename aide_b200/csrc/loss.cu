@@ -174,44 +174,55 @@ __global__ void pseudo_label_kernel(AugPtrs aug, int n_aug, int HW, size_t total
   }
 }
 
-// single block, N <= 1024 threads
-__global__ void coteach_select_kernel(const float* __restrict__ pre_other, const float* __restrict__ loss_img,
-                                      const double* __restrict__ sums, int N, double hw, int n_clean, float rate,
-                                      float seg_w, float cor_w, float w_ce, float w_dice, int64_t* __restrict__ idx,
+// single block, n_total <= 1024 threads.  `pre_other` holds the OTHER net's per-image losses of the whole (global) batch of
+// n_total images; this rank's N images are entries [first, first + N).  NaN losses sort last (like torch.sort) and ties
+// break on the global index, so the ranks are always a permutation.
+__device__ __forceinline__ bool sorts_before(float o, int j, float mine, int i) {
+  const bool on = o != o, mn = mine != mine;
+  if (on || mn) return on == mn ? j < i : mn;
+  return o < mine || (o == mine && j < i);
+}
+__global__ void coteach_select_kernel(const float* __restrict__ pre_other, int n_total, int first,
+                                      const float* __restrict__ loss_img, const double* __restrict__ sums, int N,
+                                      double hw, int n_clean, float rate, const float* __restrict__ rate_dev, float seg_w,
+                                      float cor_w, float w_ce, float w_dice, int64_t* __restrict__ idx,
                                       float* __restrict__ a_ce, float* __restrict__ a_dice, float* __restrict__ a_mse,
                                       float* __restrict__ loss_out) {
   __shared__ float v[1024];
   __shared__ int order[1024];
   const int i = threadIdx.x;
-  if (i < N) v[i] = pre_other[i];
+  if (rate_dev) rate = *rate_dev;            // read from device memory: the warm-up schedule moves under a captured graph
+  if (i < n_total) v[i] = pre_other[i];
   __syncthreads();
   int rank = 0;
-  if (i < N) {
-    float mine = v[i];
-    for (int j = 0; j < N; ++j) {
-      float o = v[j];
-      rank += (o < mine) || (o == mine && j < i);  // stable ascending
-    }
+  if (i < n_total) {
+    const float mine = v[i];
+    for (int j = 0; j < n_total; ++j) rank += sorts_before(v[j], j, mine, i) ? 1 : 0;   // stable ascending
     order[rank] = i;
   }
   __syncthreads();
-  const int n_rest = N - n_clean;
-  if (i < N) {
+  const int n_rest = n_total - n_clean;
+  if (i < n_total) {
     idx[i] = order[i];
-    bool clean = rank < n_clean;
-    // loss = seg_w * (mean_clean L + (1-rate) mean_rest L) + cor_w * rate * sum_rest(mse) / (n_rest*2*HW)
-    float cseg = clean ? seg_w / (float)n_clean : (n_rest > 0 ? seg_w * (1.0f - rate) / (float)n_rest : 0.f);
-    a_ce[i] = cseg * w_ce / (float)hw;
-    a_dice[i] = cseg * w_dice;
-    a_mse[i] = (!clean && n_rest > 0) ? cor_w * rate / (float)((double)n_rest * 2.0 * hw) : 0.f;
+    const int l = i - first;                 // local image index
+    if (l >= 0 && l < N) {
+      const bool clean = rank < n_clean;
+      // loss = seg_w * (mean_clean L + (1-rate) mean_rest L) + cor_w * rate * sum_rest(mse) / (n_rest*2*HW)
+      const float cseg = clean ? seg_w / (float)n_clean : (n_rest > 0 ? seg_w * (1.0f - rate) / (float)n_rest : 0.f);
+      a_ce[l] = cseg * w_ce / (float)hw;
+      a_dice[l] = cseg * w_dice;
+      a_mse[l] = (!clean && n_rest > 0) ? cor_w * rate / (float)((double)n_rest * 2.0 * hw) : 0.f;
+    }
   }
   __syncthreads();
   if (i == 0 && loss_out) {
-    // fixed-order scalar assembly following the reference expression order
+    // fixed-order scalar assembly following the reference expression order; with n_total > N this is the rank's
+    // share of the global loss (the shares of all ranks add up to it)
     float seg1 = 0.f, seg2 = 0.f;
     double mse = 0.0;
-    for (int r = 0; r < N; ++r) {
-      int k = order[r];
+    for (int r = 0; r < n_total; ++r) {
+      const int k = order[r] - first;
+      if (k < 0 || k >= N) continue;
       if (r < n_clean) seg1 += loss_img[k];
       else {
         seg2 += loss_img[k];
@@ -325,16 +336,27 @@ extern "C" int aide_pseudo_label(const float* const* aug_logits, int n_aug, int 
   return 0;
 }
 
+extern "C" int aide_coteach_select_ex(const float* pre_other_all, int n_total, int first, const float* loss_img,
+                                      const double* sums, int N, int H, int W, int n_clean, float rate,
+                                      const float* rate_dev, float seg_w, float cor_w, float w_ce, float w_dice,
+                                      int64_t* idx, float* a_ce, float* a_dice, float* a_mse, float* loss_out,
+                                      void* stream) {
+  AIDE_REQUIRE(pre_other_all && loss_img && sums && idx && a_ce && a_dice && a_mse, "coteach_select: null argument");
+  AIDE_REQUIRE(N >= 1 && n_total >= N && n_total <= 1024 && first >= 0 && first + N <= n_total && n_clean >= 1 &&
+                   n_clean <= n_total,
+               "coteach_select: need 1 <= n_clean <= n_total <= 1024 and [first, first+N) inside the global batch");
+  int threads = ((n_total + 31) / 32) * 32;
+  coteach_select_kernel<<<1, threads, 0, as_stream(stream)>>>(pre_other_all, n_total, first, loss_img, sums, N,
+                                                              (double)H * W, n_clean, rate, rate_dev, seg_w, cor_w, w_ce,
+                                                              w_dice, idx, a_ce, a_dice, a_mse, loss_out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int aide_coteach_select(const float* pre_other, const float* loss_img, const double* sums, int N, int H,
                                    int W, int n_clean, float rate, float seg_w, float cor_w, float w_ce, float w_dice,
                                    int64_t* idx, float* a_ce, float* a_dice, float* a_mse, float* loss_out,
                                    void* stream) {
-  AIDE_REQUIRE(pre_other && loss_img && sums && idx && a_ce && a_dice && a_mse, "coteach_select: null argument");
-  AIDE_REQUIRE(N >= 1 && N <= 1024 && n_clean >= 1 && n_clean <= N, "coteach_select: need 1 <= n_clean <= N <= 1024");
-  int threads = ((N + 31) / 32) * 32;
-  coteach_select_kernel<<<1, threads, 0, as_stream(stream)>>>(pre_other, loss_img, sums, N, (double)H * W, n_clean,
-                                                              rate, seg_w, cor_w, w_ce, w_dice, idx, a_ce, a_dice,
-                                                              a_mse, loss_out);
-  AIDE_CHECK_LAUNCH();
-  return 0;
+  return aide_coteach_select_ex(pre_other, N, 0, loss_img, sums, N, H, W, n_clean, rate, nullptr, seg_w, cor_w, w_ce,
+                                w_dice, idx, a_ce, a_dice, a_mse, loss_out, stream);
 }

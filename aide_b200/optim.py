@@ -2,7 +2,10 @@
 
 FlatAdamAMSGrad = torch.optim.Adam(lr, amsgrad=True) (reference:
 train_files/trainchaos_proposed_30cases1labeled.py:231-232,323,325) applied by ONE kernel to flat fp32
-parameter / gradient / state buffers (aide_adam_amsgrad).  PolyLR mirrors utils/poly_lr_scheduler.py:31-51.
+parameter / gradient / state buffers (aide_adam_amsgrad).  It is a torch.optim.Optimizer, so the reference's
+schedulers (StepLR :236-237, PolyLR :239-240 -> utils/poly_lr_scheduler.py:31-51) wrap it unchanged: they write
+``param_groups[0]['lr']``, which is mirrored into a one-element DEVICE buffer the kernel reads -- a learning-rate
+change therefore also reaches a captured CUDA graph of the training step.
 """
 from __future__ import annotations
 
@@ -14,15 +17,19 @@ from torch.optim.lr_scheduler import _LRScheduler
 from ._lib import call
 
 
-class FlatAdamAMSGrad:
+class FlatAdamAMSGrad(torch.optim.Optimizer):
     """Keeps a flat copy-free view of the parameters: on construction the parameters are re-pointed into
     one contiguous fp32 buffer (so ``module.parameters()`` keep working) and the three Adam states are
     flat buffers of the same size.  ``step(grad_flat)`` consumes a flat gradient laid out in the same
     parameter order (see flatten_grads) -- or the per-parameter ``.grad`` fields when called without."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
-        self.params: List[torch.nn.Parameter] = [p for p in params]
-        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        plist: List[torch.nn.Parameter] = [p for p in params]
+        super().__init__(plist, dict(lr=lr, betas=betas, eps=eps))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdamAMSGrad keeps ONE flat buffer: pass a flat list of parameters, not groups")
+        self.params = plist
+        self.betas, self.eps, self.t = betas, eps, 0
         self.offsets, cur = [], 0
         for p in self.params:
             self.offsets.append(cur)
@@ -36,10 +43,32 @@ class FlatAdamAMSGrad:
         self.v = torch.zeros_like(self.flat)
         self.vmax = torch.zeros_like(self.flat)
         self.gbuf = torch.zeros_like(self.flat)
-        # device-resident step counter + bias-correction scratch: nothing host-side changes between steps, so a
-        # captured CUDA graph of the training step replays correctly
+        # device-resident step counter, bias-correction scratch and learning rate: nothing host-side changes between
+        # steps, so a captured CUDA graph of the training step replays correctly
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_uploaded = float(lr)
+
+    # the learning rate lives in param_groups[0]['lr'] (what torch's schedulers read and write)
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.param_groups[0]["lr"] = float(value)
+
+    def set_lr(self, value: float) -> None:
+        self.lr = value
+        self.sync_lr()
+
+    def sync_lr(self) -> None:
+        """Mirror param_groups[0]['lr'] into the device scalar (no-op while it is unchanged)."""
+        lr = self.lr
+        if lr != self._lr_uploaded:
+            self.lr_dev.fill_(lr)
+            self._lr_uploaded = lr
 
     def flatten_grads(self) -> torch.Tensor:
         for p, o in zip(self.params, self.offsets):
@@ -49,7 +78,7 @@ class FlatAdamAMSGrad:
                 self.gbuf[o:o + p.numel()].zero_()
         return self.gbuf
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None
 
@@ -59,11 +88,17 @@ class FlatAdamAMSGrad:
         if g.numel() != self.flat.numel():
             raise ValueError("flat gradient does not match the flat parameter buffer")
         self.t += 1                      # host mirror (informational; the kernel uses the device counter)
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()               # under capture the caller syncs before the replay (AideTrainer.step)
         call("aide_adam_amsgrad_dev", self.flat.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
              self.vmax.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-             self.step_dev.data_ptr(), self.bc_dev.data_ptr(), grad_scale, torch.cuda.current_stream().cuda_stream)
+             self.step_dev.data_ptr(), self.bc_dev.data_ptr(), grad_scale, self.lr_dev.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that the
         # engine re-derives its operand-format weight planes (PreparedWeights is keyed on _version)
+        self.bump_versions()
+
+    def bump_versions(self) -> None:
         torch.autograd.graph.increment_version(self.params)
 
 

@@ -50,7 +50,7 @@ class AideTrainer:
     def __init__(self, kind: str = "fuseunet", mode: Optional[str] = None, device="cuda:0", seed: int = 2,
                  lr: float = 1e-4, n_clean: int = 2, segcor_weight=(1.0, 10.0), temperature: float = 1.0,
                  flavour: str = "chaos", two_streams: bool = True, process_group=None,
-                 cuda_graph: Optional[bool] = None):
+                 cuda_graph: Optional[bool] = None, global_select: bool = False, max_graphs: int = 4):
         self.device = torch.device(device)
         self.kind, self.flavour, self.temperature = kind, flavour, temperature
         self.n_clean, self.segcor_weight = n_clean, segcor_weight
@@ -69,9 +69,19 @@ class AideTrainer:
             net._tensors = None                       # parameters were re-pointed into the flat buffer
             net._prep_dgrad_always = True             # one weight preparation per step serves all 5 forwards + dgrad
         self.group = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        # Data-parallel selection semantics.  False (default): every rank selects n_clean "clean" images inside its
+        # local batch and the gradients are averaged.  True: the reference's nn.DataParallel behaviour
+        # (trainchaos_proposed_30cases1labeled.py:183-186,303-310): the per-image losses of all ranks are all-gathered,
+        # the sort and the n_clean / rest split are GLOBAL, loss means are over the global batch, gradients are summed.
+        self.global_select = bool(global_select) and self.world > 1
+        # warm-up rate (:248) as a device scalar: it changes every epoch of the warm-up and must not re-capture the graph
+        self.rate_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._rate_uploaded = None
+        self.max_graphs = max_graphs
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
         self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
         self.two_streams = two_streams
@@ -203,10 +213,17 @@ class AideTrainer:
             idx = torch.empty(N, dtype=torch.int64, device=dev)
             coef = torch.empty((3, N), dtype=torch.float32, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            call("aide_coteach_select", other["pre"].data_ptr(), me["pre"].data_ptr(), me["sums"].data_ptr(), N, H, W,
-                 min(self.n_clean, N), float(rate), float(self.segcor_weight[0]), float(self.segcor_weight[1]),
-                 1.0, 1.0, idx.data_ptr(), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
-                 loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            pre_all, n_total, first = other["pre"], N, 0
+            if self.global_select:                 # DataParallel semantics: rank the gathered global batch
+                n_total, first = N * self.world, N * self.rank
+                pre_all = torch.empty(n_total, dtype=torch.float32, device=dev)
+                torch.distributed.all_gather_into_tensor(pre_all, other["pre"].contiguous(), group=self.group)
+                idx = torch.empty(n_total, dtype=torch.int64, device=dev)
+            call("aide_coteach_select_ex", pre_all.data_ptr(), n_total, first, me["pre"].data_ptr(),
+                 me["sums"].data_ptr(), N, H, W, min(self.n_clean, n_total), float(rate), self.rate_dev.data_ptr(),
+                 float(self.segcor_weight[0]), float(self.segcor_weight[1]), 1.0, 1.0, idx.data_ptr(),
+                 coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(), loss.data_ptr(),
+                 torch.cuda.current_stream().cuda_stream)
             has_q = other["q"] is not None
             d = L.loss_backward(lg, t_other, me["sums"], coef[0], coef[1], coef[2] if has_q else None,
                                 other["q"], other["w"])
@@ -214,7 +231,11 @@ class AideTrainer:
             flat = net.last_grad_flat
             if self.world > 1:
                 torch.distributed.all_reduce(flat, group=self.group)
-            opt.step(flat, grad_scale=1.0 / self.world)
+                if self.global_select:             # the scalar was this rank's share of the global loss
+                    torch.distributed.all_reduce(loss, group=self.group)
+            # local selection: mean of the per-rank gradients; global selection: the coefficients already carry the
+            # global denominators, so the rank gradients add up to the reference's gradient
+            opt.step(flat, grad_scale=1.0 if self.global_select else 1.0 / self.world)
             me["loss"], me["idx"] = loss, idx
             me["tape"] = None
 
@@ -241,9 +262,16 @@ class AideTrainer:
                                         rate)
             finally:
                 self._aug_dev = None
-        key = (tuple(xs[0].shape), len(xs), len(augs), float(rate), self.flavour, self.world, host_aug is not None)
+        self._upload_scalars(rate)
+        key = (tuple(xs[0].shape), len(xs), len(augs), self.flavour, self.world, host_aug is not None,
+               self.global_select)
         entry = self._graphs.get(key)
+        if entry is not None:
+            self._graphs[key] = self._graphs.pop(key)          # most recently used last
         if entry is None:
+            while len(self._graphs) >= self.max_graphs:        # every graph owns a multi-GB private pool: evict the LRU
+                self._graphs.pop(next(iter(self._graphs)))
+                torch.cuda.empty_cache()
             if host_aug is not None:                           # static device buffers the captured kernels read
                 self._aug_dev = tuple(t.to(self.device) for t in host_aug)
             try:
@@ -263,10 +291,28 @@ class AideTrainer:
         self.opt2.t += 1
         for net in (self.net1, self.net2):                      # operand-format weight planes live in the graph's pool
             net._weights = None
+        # the replayed Adam kernels rewrote the parameters: bump their versions so that everything keyed on
+        # (data_ptr, _version) -- PreparedWeights, net.graphed_eval() -- re-derives its weight planes
+        self.opt1.bump_versions()
+        self.opt2.bump_versions()
         return out
+
+    def _upload_scalars(self, rate: float) -> None:
+        """Mirror the host scalars a captured step reads from device memory (rate, both learning rates)."""
+        if rate != self._rate_uploaded:
+            self.rate_dev.fill_(float(rate))
+            self._rate_uploaded = rate
+        self.opt1.sync_lr()
+        self.opt2.sync_lr()
+
+    def set_lr(self, lr: float) -> None:
+        self.opt1.set_lr(lr)
+        self.opt2.set_lr(lr)
 
     def _step_eager(self, x, t1: torch.Tensor, t2: torch.Tensor, augs: Sequence, rate: float) -> Dict[str, torch.Tensor]:
         xs = self._inputs(x)
+        if not torch.cuda.is_current_stream_capturing():
+            self._upload_scalars(rate)
         m1: Dict = {}
         m2: Dict = {}
         cur = torch.cuda.current_stream(self.device)

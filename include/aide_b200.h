@@ -215,16 +215,28 @@ int aide_reverse_aug(const float* src, float* dst, const double* matrices, const
 int aide_coteach_select(const float* pre_other, const float* loss_img, const double* sums, int N, int H, int W,
                         int n_clean, float rate, float seg_w, float cor_w, float w_ce, float w_dice,
                         int64_t* idx, float* a_ce, float* a_dice, float* a_mse, float* loss_out, void* stream);
+/* The same for a batch that is sharded over data-parallel ranks (the reference's nn.DataParallel sorts the GATHERED
+ * per-image losses on GPU 0, trainchaos_proposed_30cases1labeled.py:183-186,303-310): pre_other_all holds the other net's
+ * per-image losses of all n_total images (all-gathered, rank-major), this rank owns images [first, first+N).  idx
+ * [n_total] is the global argsort; the coefficients cover the N local images with the GLOBAL counts as denominators,
+ * and loss_out is this rank's share of the global loss (summing the shares / the gradients over ranks gives the
+ * reference's loss / gradient).  NaN losses sort last.  rate_dev (nullable): device scalar that overrides `rate`, so the
+ * warm-up schedule (:248) can move under a captured CUDA graph. */
+int aide_coteach_select_ex(const float* pre_other_all, int n_total, int first, const float* loss_img,
+                           const double* sums, int N, int H, int W, int n_clean, float rate, const float* rate_dev,
+                           float seg_w, float cor_w, float w_ce, float w_dice, int64_t* idx, float* a_ce,
+                           float* a_dice, float* a_mse, float* loss_out, void* stream);
 
 /* ---- optimiser ("next" row f1): torch.optim.Adam(amsgrad=True) on a flat fp32 buffer ------------- */
 int aide_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, size_t n,
                       float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 /* Same update with the step count kept ON THE DEVICE: *step_counter is incremented and the two bias corrections are
  * written to bc_scratch[2] by a one-thread prelude kernel -- no host scalar changes between steps, so a captured
- * CUDA graph of the whole training step can be replayed. */
+ * CUDA graph of the whole training step can be replayed.  lr_dev (nullable): device scalar that overrides `lr`, so
+ * StepLR / PolyLR (trainchaos_proposed_30cases1labeled.py:236-241) keep working under a captured graph. */
 int aide_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* vmax, size_t n,
                           float lr, float beta1, float beta2, float eps, int* step_counter, float* bc_scratch,
-                          float grad_scale, void* stream);
+                          float grad_scale, const float* lr_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -253,6 +253,33 @@ def main():
         fuse_argmax_packed=torch.from_numpy(__import__("numpy").packbits((yf.argmax(1) == 1).numpy().reshape(-1))),
         fuse_logits_sub=yf[:, :, ::8, ::8].clone(), unet_logits_sub=yu[:, :, ::8, ::8].clone(),
         fuse_margin_min=(yf[:, 1] - yf[:, 0]).abs().min().item())
+    # ---- argmax audit band: the SAME forward in fp64 (same weights, same inputs).  d = z1 - z0 is the argmax margin;
+    # |d32 - d64| is the reference's own fp32 rounding noise on it.  An engine pixel whose argmax differs from the
+    # reference's is a numerical tie iff its fp64 margin lies inside that noise band (tests/test_gpu_network.py).
+    p64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in pf0.items()}
+    with torch.no_grad():
+        y64 = O.fuseunet_forward(p64, x1.double(), x2.double(), True)
+    d64 = (y64[:, 1] - y64[:, 0]).reshape(-1)
+    d32 = (yf[:, 1] - yf[:, 0]).double().reshape(-1)
+    err = (d32 - d64).abs()
+    band = err.max().item()
+    cand = (d64.abs() < 64.0 * band).nonzero().flatten()
+    out["ka256"].update(
+        fp64_margin_band=band, fp64_logit_err_rel=((yf.double() - y64).abs().max() / y64.abs().max()).item(),
+        fp64_cand_idx=cand.to(torch.int32), fp64_cand_margin=d64[cand].float(), fp64_cand_err=err[cand].float(),
+        fp64_logits_sub=y64[:, :, ::8, ::8].clone(),
+        fp32_flips_vs_fp64=int(((d32 > 0) != (d64 > 0)).sum()))
+    # gradient of the scalar CE+Dice loss at this size (config 2: fuseunet forward+backward, batch 4, 256x256)
+    f.train()
+    yg = f(x1, x2)              # second train-mode forward of the same module: same logits, BN buffers move again
+    lg_ = crit_mean(yg, t)
+    names = [k for k, _ in f.named_parameters()]
+    gr = grads_of(lg_, [q_ for _, q_ in f.named_parameters()])
+    out["ka256"].update(
+        fuse_loss_mean=lg_.item(), fuse_grad_last_w=gr[names.index("last_conv1.weight")].clone(),
+        fuse_grad_last_b=gr[names.index("last_conv1.bias")].clone(),
+        fuse_grad_absmax={k: g_.abs().max().item() for k, g_ in zip(names, gr)},
+        fuse_grad_sum={k: g_.double().sum().item() for k, g_ in zip(names, gr)})
     torch.save(out, os.path.join(HERE, "golden.pt"))
     sz = os.path.getsize(os.path.join(HERE, "golden.pt"))
     print("oracle == reference on every check; wrote golden.pt (%.1f KB)" % (sz / 1024))

@@ -98,10 +98,16 @@ def test_forward_backward_vs_golden_and_oracle(golden, oracle, mode, kind, tag, 
     y = net(*[x.to(dev) for x in xs])
     assert y.shape == (b, 2, h, w) and y.requires_grad
     assert relmax(y, g["logits"]) < LOGIT_TOL[mode]
+    # argmax: a pixel may differ from the fp32 reference only where it is a numerical tie, i.e. where the margin of the
+    # SAME forward evaluated in fp64 lies inside the reference's own fp32-vs-fp64 noise band on that margin
     flips = y.argmax(1).cpu() != g["logits"].argmax(1)
-    margin = (g["logits"][:, 1] - g["logits"][:, 0]).abs()
-    tie = 2 * LOGIT_TOL[mode] * g["logits"].abs().max()        # a flip needs |margin| < 2 * logit error
-    assert (flips & (margin > tie)).sum() == 0 and int(flips.sum()) <= 2, int(flips.sum())
+    if mode != "fast":
+        p64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in oracle_params(oracle, kind).items()}
+        with torch.no_grad():
+            y64 = fwd_oracle(oracle, kind, {k: v.detach() for k, v in p64.items()}, tuple(x.double() for x in xs))
+        d64 = y64[:, 1] - y64[:, 0]
+        band = ((g["logits"][:, 1] - g["logits"][:, 0]).double() - d64).abs().max()
+        assert (flips & (d64.abs() > band)).sum() == 0 and int(flips.sum()) <= 2, (int(flips.sum()), band.item())
     # loss + gradients
     p = oracle_params(oracle, kind)
     yo = fwd_oracle(oracle, kind, p, xs)
@@ -237,11 +243,20 @@ def test_known_answers_256_parity_mode(golden):
     assert relmax(yf[:, :, ::8, ::8], g["fuse_logits_sub"]) < LOGIT_TOL["parity"]
     assert relmax(yu[:, :, ::8, ::8], g["unet_logits_sub"]) < LOGIT_TOL["parity"]
     packed = torch.from_numpy(np.packbits((yf.argmax(1) == 1).cpu().numpy().reshape(-1)))
-    flips = int(np.unpackbits((packed ^ g["fuse_argmax_packed"]).numpy()).sum())
-    # 262 144 pixels; a flip needs an oracle margin below twice the logit error (numerical tie).  Measured: 6
-    # (the fp32 CUDA-core 'exact' mode: 1; reference min margin 2e-6).  Bounded at 1 pixel in 10 000.
-    print(f"256x256 parity: {flips} argmax flips of 262144 (reference min margin {g['fuse_margin_min']:.2e})")
-    assert flips <= 26, flips
+    flipped = np.unpackbits((packed ^ g["fuse_argmax_packed"]).numpy()).nonzero()[0]
+    # Argmax audit (262 144 pixels).  The golden file holds the SAME forward evaluated in fp64 by the oracle: the fp64
+    # margin d = z1 - z0 of every pixel with |d| < 64 * band, where band = max |d_fp32 - d_fp64| is the reference's own
+    # fp32 rounding noise on the margin (4.1e-5; the fp32 reference itself flips 1 pixel against fp64).  EVERY pixel
+    # whose engine argmax differs from the fp32 reference's must be such a numerical tie: |d_fp64| inside the band.
+    band = g["fp64_margin_band"]
+    cand = {int(i): float(m) for i, m in zip(g["fp64_cand_idx"].tolist(), g["fp64_cand_margin"].tolist())}
+    margins = [abs(cand.get(int(i), float("inf"))) for i in flipped]
+    e64 = relmax(yf[:, :, ::8, ::8], g["fp64_logits_sub"])
+    print(f"256x256 parity: {len(flipped)} argmax flips of 262144 vs the fp32 reference; their fp64 margins "
+          f"{['%.2e' % m for m in margins]} (band {band:.2e}; the fp32 reference flips {g['fp32_flips_vs_fp64']} vs fp64); "
+          f"engine logits vs fp64 {e64:.2e} (fp32 reference vs fp64 {g['fp64_logit_err_rel']:.2e})")
+    assert all(m < band for m in margins), (margins, band)
+    assert len(flipped) <= 8, len(flipped)
     li = A.CEMDiceLossImage([1., 1.], [1., 1.], [1., 1.])(yf, t.to(dev))
     assert torch.allclose(li.cpu(), g["fuse_loss_img"], rtol=2e-5)
     assert li.sort()[1].tolist() == [1, 2, 0, 3]
@@ -272,13 +287,14 @@ def test_teacher_forced_training_steps(oracle):
     small-loss index sets; the oracle then advances with Adam-amsgrad.  The 1e-4 Dice bar of BASELINE.json is
     stated at 256x256, where one pixel at a numerical tie moves Dice_fn/B by ~2e-6; Dice_fn is a thresholded
     count, so at a smaller test size S the same pixel moves it (256/S)^2 times more and the bar scales with it
-    (1.6e-3 at 64).  AIDE_TF_STEPS (default 6; the 100-step run is recorded in profiles/) and AIDE_TF_SIZE
-    control the cost."""
+    (1.6e-3 at 64).  Default: 10 steps at the full 256x256 size, batch 4 (AIDE_TF_STEPS / AIDE_TF_SIZE change it; the
+    100-step run is recorded in profiles/)."""
     import aide_b200 as A
     dev = torch.device("cuda:0")
-    steps = int(os.environ.get("AIDE_TF_STEPS", "6"))
-    size = int(os.environ.get("AIDE_TF_SIZE", "64"))
+    steps = int(os.environ.get("AIDE_TF_STEPS", "10"))
+    size = int(os.environ.get("AIDE_TF_SIZE", "256"))
     B = 4
+    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(2)
     p1 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
     p2 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
