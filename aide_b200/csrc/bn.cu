@@ -141,6 +141,106 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups
   }
 }
 
+// Fold + finalize in ONE launch (the 112 separate fold launches of a step were pure launch latency): blocks fold their
+// chunk exactly like bn_stat_fold_kernel -- a block owns 16 channels x {sum, sum of squares} -- then take a ticket; the
+// LAST block of a channel group to arrive finalises those 16 channels for all statistics groups, reading the folded
+// (hi, lo) pairs of every chunk in fixed order (bit-reproducible whichever block happens to be last).  tickets: one
+// zero-initialised counter per channel group, left at zero again.
+__global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int rows, int C, int n_chunks, int sgroups,
+                                             double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                             float* __restrict__ scale_shift, float* __restrict__ mean_rstd,
+                                             unsigned int* __restrict__ tickets) {
+  __shared__ double sm[kStatLanes][33];
+  __shared__ unsigned int s_last;
+  const int cols = 2 * C;
+  const int cl = threadIdx.x & 15, stat = threadIdx.x >> 4;
+  const int c = blockIdx.x * 16 + cl;
+  const bool cvalid = c < C;
+  const int j = stat * C + c;                                 // column of this thread in a partial row
+  {
+    float* part = partial + (size_t)blockIdx.z * rows * cols;
+    const int r0 = blockIdx.y * kStatChunk;
+    const int r1 = min(rows, r0 + kStatChunk);
+    double acc = 0.0;
+    if (cvalid) {
+#pragma unroll 2
+      for (int r = r0 + threadIdx.y; r < r1; r += kStatLanes) acc += (double)part[(size_t)r * cols + j];
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && cvalid) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < kStatLanes; ++k) t += sm[k][threadIdx.x];
+      const float hi = (float)t;
+      part[(size_t)r0 * cols + j] = hi;
+      if (r0 + 1 < rows) part[(size_t)(r0 + 1) * cols + j] = (float)(t - (double)hi);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int total = (unsigned int)(n_chunks * sgroups);
+    s_last = atomicAdd(&tickets[blockIdx.x], 1u) == total - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- finalize the 16 channels of this block (thread (x, 0), x < 16, owns channel c)
+  float rm = 0.f, rv = 0.f;
+  const bool owner = threadIdx.y == 0 && stat == 0 && cvalid;
+  if (owner && rmean) {
+    rm = rmean[c];
+    rv = rvar[c];
+  }
+  for (int sg = 0; sg < sgroups; ++sg) {
+    const float* part = partial + (size_t)sg * rows * cols;
+    double a = 0.0;
+    if (cvalid) {
+      for (int g = threadIdx.y; g < n_chunks; g += kStatLanes) {
+        const int r = g * kStatChunk;
+        a += (double)__ldcg(part + (size_t)r * cols + j);
+        if (r + 1 < rows) a += (double)__ldcg(part + (size_t)(r + 1) * cols + j);
+      }
+    }
+    __syncthreads();
+    sm[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (!owner) continue;
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int k = 0; k < kStatLanes; ++k) {
+      sa += sm[k][cl];
+      sb += sm[k][cl + 16];
+    }
+    const double m = sa / count;
+    double v = sb / count - m * m;
+    if (v < 0.0) v = 0.0;
+    const float mean = (float)m, var = (float)v;
+    if (rmean) {
+      const double unbiased = count > 1.0 ? v * (count / (count - 1.0)) : v;
+      rm = (1.f - momentum) * rm + momentum * mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    }
+    const float rstd = 1.0f / sqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    float* ss = scale_shift + (size_t)sg * 2 * C;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - mean * sc;
+    if (mean_rstd) {
+      float* mr = mean_rstd + (size_t)sg * 2 * C;
+      mr[c] = mean;
+      mr[C + c] = rstd;
+    }
+  }
+  if (owner && rmean) {
+    rmean[c] = rm;
+    rvar[c] = rv;
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0u;     // ready for the next launch
+}
+
 // ------------------------------------------------------------------ forward apply
 __device__ __forceinline__ float4 bn_relu4(float4 z, float4 sc, float4 sh) {
   return make_float4(fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), fmaxf(fmaf(z.y, sc.y, sh.y), 0.f),
@@ -442,13 +542,15 @@ extern "C" int aide_bn_finalize(float* stat_partial, int rows, int C, double cou
                                 const float* beta, float* running_mean, float* running_var, float momentum,
                                 float eps, int training, float* scale_shift, float* mean_rstd, void* stream) {
   return aide_bn_finalize_grouped(stat_partial, rows, 1, C, count, gamma, beta, running_mean, running_var, momentum, eps,
-                                  training, scale_shift, mean_rstd, stream);
+                                  training, scale_shift, mean_rstd, nullptr, stream);
 }
+
+extern "C" int aide_bn_ticket_slots(int C) { return ceil_div(C, 16); }
 
 extern "C" int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgroups, int C, double count,
                                         const float* gamma, const float* beta, float* running_mean, float* running_var,
                                         float momentum, float eps, int training, float* scale_shift, float* mean_rstd,
-                                        void* stream) {
+                                        unsigned int* tickets, void* stream) {
   AIDE_REQUIRE(C > 0 && gamma && beta && scale_shift && sgroups >= 1, "bn_finalize: bad arguments");
   AIDE_REQUIRE(training ? (stat_partial && rows > 0 && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics input");
@@ -456,6 +558,13 @@ extern "C" int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgrou
   int groups = rows, row_stride = 1, sub = 1;
   if (training && rows > 2 * kStatChunk) {   // many tiles: fold chunks in parallel first (in place)
     groups = ceil_div(rows, kStatChunk);
+    if (tickets) {                           // ... and let the last block of each channel group finalize: one launch
+      bn_stat_fold_finalize_kernel<<<dim3(ceil_div(C, 16), groups, sgroups), block, 0, as_stream(stream)>>>(
+          stat_partial, rows, C, groups, sgroups, count, gamma, beta, running_mean, running_var, momentum, eps,
+          scale_shift, mean_rstd, tickets);
+      AIDE_CHECK_LAUNCH();
+      return 0;
+    }
     bn_stat_fold_kernel<<<dim3(ceil_div(2 * C, 32), groups, sgroups), block, 0, as_stream(stream)>>>(stat_partial, rows,
                                                                                                       2 * C);
     AIDE_CHECK_LAUNCH();

@@ -65,28 +65,34 @@ def test_config2_fuseunet_forward_backward_b4_256(golden, oracle, all_threads):
     e_last = relmax(net.last_conv1.weight.grad, g["fuse_grad_last_w"])
     assert e_last < 1e-3, e_last
     assert relmax(net.last_conv1.bias.grad, g["fuse_grad_last_b"]) < 1e-4
-    # live oracle on the same inputs: full logits, every gradient
+    # live oracle on the same inputs: full logits, every gradient.  Per-tensor gradient values are ill-conditioned in
+    # the fp32 reference itself (dW sums cancel heavily because train-mode BatchNorm makes every dz channel mean-free;
+    # ReLU / max-pool masks flip at rounding level): the bar is the oracle's OWN one-ulp sensitivity band measured on
+    # these inputs (as in tests/test_gpu_network.py), plus the well-conditioned shortest-path tensors above.
+    from test_gpu_network import assert_grads_inside_band, oracle_sensitivity_band
+    names = [k for k in oracle.init_fuseunet(2) if not oracle.is_buffer(k)]
+    live = [k for k in names if not is_prebn_bias(k)]
+
+    def grad_fn(xin):
+        torch.manual_seed(2)
+        pp = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
+        yy = oracle.fuseunet_forward(pp, *xin, training=True)
+        grad_fn.last = (pp, yy.detach())
+        return dict(zip(live, torch.autograd.grad(oracle.ce_dice_mean(yy, t), [pp[k] for k in live])))
+
+    go, band, band_cos = oracle_sensitivity_band(grad_fn, (x1, x2), live, n_draws=3)
     torch.manual_seed(2)
     p = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
     yo = oracle.fuseunet_forward(p, x1, x2, training=True)
-    names = [k for k in p if not oracle.is_buffer(k)]
-    go = dict(zip(names, torch.autograd.grad(oracle.ce_dice_mean(yo, t), [p[k] for k in names])))
     assert relmax(go["last_conv1.weight"], g["fuse_grad_last_w"]) < 1e-5          # the live oracle IS the reference
     e_logit = relmax(y, yo)
     assert e_logit < 2e-4, e_logit
     eng = {k: v.grad for k, v in net.named_parameters()}
-    live = [k for k in names if not is_prebn_bias(k)]
-    gap = cosine_gap(eng, go, live)
-    per = {k: relmax(eng[k], go[k]) for k in live}
-    worst = max(per, key=per.get)
     for k in names:
         if is_prebn_bias(k):
             assert eng[k].abs().max().item() < 1e-5, k                            # analytically zero
-    med = sorted(per.values())[len(per) // 2]
-    print(f"C2 fuseunet B=4 256x256: logits {e_logit:.2e}, last_conv1.weight grad {e_last:.2e}, 1-cos(all grads) {gap:.2e}, "
-          f"per-tensor grad max|d|/max|ref|: median {med:.2e}, worst {per[worst]:.2e} ({worst})")
-    assert gap < 1e-6, gap
-    assert med < 1e-3, med
+    print(f"C2 fuseunet B=4 256x256: logits {e_logit:.2e}, last_conv1.weight grad {e_last:.2e}")
+    assert_grads_inside_band({k: eng[k] for k in live}, go, band, band_cos, live, "C2 fuse/parity/256")
     # BatchNorm buffers after ONE train-mode forward
     sd = net.state_dict()
     for k, v in p.items():
