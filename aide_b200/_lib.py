@@ -25,6 +25,8 @@ SIGNATURES = {
     "aide_nchw_to_nhwc": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_nhwc_to_nchw": (_i, [_i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_weight_prep": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "aide_weight_prep_batch": (_i, [_i, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp),
+                                    C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "aide_conv3x3_stat_rows": (_i, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "aide_conv3x3_plan_info": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_i)]),
@@ -32,7 +34,8 @@ SIGNATURES = {
     "aide_conv3x3_dgrad": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "aide_bn_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
-    "aide_bn_finalize_grouped": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
+    "aide_bn_finalize_grouped": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "aide_bn_ticket_slots": (_i, [_i]),
     "aide_bn_relu_apply_grouped": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp,
                                         _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "aide_bn_relu_apply": (_i, [_i, _vp, _i, _i, _i, _i, _vp,
@@ -42,7 +45,7 @@ SIGNATURES = {
                                      C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i,
                                      C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     "aide_bn_relu_bwd_apply": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
-                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_upsample2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_upsample2x_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_zero_insert2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -328,7 +328,7 @@ __global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const flo
                                           const float* __restrict__ mean_rstd, int N, int H, int W, int C,
                                           BwdSrcs s, float* __restrict__ g, float* __restrict__ partial,
                                           unsigned int* __restrict__ gmax_bits) {
-  extern __shared__ float smem[];  // [ty][cx*8]
+  extern __shared__ __align__(16) float smem[];  // [ty][cx*8]
   float gmax = 0.f;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const bool cvalid = c < C;
@@ -432,23 +432,23 @@ __global__ void bn_relu_bwd_reduce_kernel(const float* __restrict__ z, const flo
 // F16X2 gradients: choose the power-of-two scale s of dZ from a bound on max|dz|,
 //   |dz| <= |gamma*rstd| * (|g| + |mean g| + |xhat| * |mean g*xhat|),  |xhat| taken as <= 16,
 // so that the bound lands at 2^10 (64x headroom to the fp16 maximum; conversions saturate beyond it, and the two
-// fp16 planes keep 22 significant bits down to 2^-24 of the bound).  scale_out = {s, 1/s}.
-__global__ void dz_scale_kernel(const unsigned int* __restrict__ gmax_bits, const float* __restrict__ mean_rstd,
-                                const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int C,
-                                float* __restrict__ scale_out) {
-  __shared__ float red[32];
-  const float gmax = __uint_as_float(*gmax_bits);
+// fp16 planes keep 22 significant bits down to 2^-24 of the bound).  scale_out = {s, 1/s}.  Resets *gmax_bits to 0
+// (the reduce stage of the next unit accumulates into it with atomicMax).
+__device__ __forceinline__ void dz_scale_block(unsigned int* gmax_bits, const float* mean_rstd, const float* gamma,
+                                               const float* sums, float inv_count, int C, float* scale_out, float* red) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const float gmax = __uint_as_float(__ldcg(gmax_bits));
   float b = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = tid; c < C; c += nthr) {
     const float k0 = fabsf(gamma[c] * mean_rstd[C + c]);
-    b = fmaxf(b, k0 * (gmax + fabsf(sums[c] * inv_count) + 16.f * fabsf(sums[C + c] * inv_count)));
+    b = fmaxf(b, k0 * (gmax + fabsf(__ldcg(sums + c) * inv_count) + 16.f * fabsf(__ldcg(sums + C + c) * inv_count)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = b;
+  if ((tid & 31) == 0) red[tid >> 5] = b;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) b = fmaxf(b, red[i]);
+  if (tid == 0) {
+    for (int i = 1; i < (nthr >> 5); ++i) b = fmaxf(b, red[i]);
     int e = 0;
     if (b > 0.f && isfinite(b)) {
       frexpf(b, &e);                 // b = m * 2^e, m in [0.5, 1)
@@ -457,7 +457,47 @@ __global__ void dz_scale_kernel(const unsigned int* __restrict__ gmax_bits, cons
     }
     scale_out[0] = ldexpf(1.f, e);
     scale_out[1] = ldexpf(1.f, -e);
+    *gmax_bits = 0u;
   }
+}
+
+__global__ void dz_scale_kernel(unsigned int* __restrict__ gmax_bits, const float* __restrict__ mean_rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int C,
+                                float* __restrict__ scale_out) {
+  __shared__ float red[32];
+  dz_scale_block(gmax_bits, mean_rstd, gamma, sums, inv_count, C, scale_out, red);
+}
+
+// Column reduction of the backward partial rows (reduce_rows_kernel) whose LAST block (ticket) also derives the dZ scale:
+// one launch instead of two per unit.  block = (32, 8); ticket: zero on entry, left zero.
+__global__ void bn_bwd_sums_scale_kernel(const float* __restrict__ partial, int rows, int C, float* __restrict__ sums,
+                                         unsigned int* __restrict__ gmax_bits, const float* __restrict__ mean_rstd,
+                                         const float* __restrict__ gamma, float inv_count, float* __restrict__ scale_out,
+                                         unsigned int* __restrict__ ticket) {
+  __shared__ double sm[8][33];
+  __shared__ float red[32];
+  __shared__ unsigned int s_last;
+  const int cols = 2 * C;
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (j < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) acc += (double)partial[(size_t)r * cols + j];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    sums[j] = (float)t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  dz_scale_block(gmax_bits, mean_rstd, gamma, sums, inv_count, C, scale_out, red);
+  if (threadIdx.x == 0 && threadIdx.y == 0) *ticket = 0u;
 }
 
 // ------------------------------------------------------------------ backward stage 2
@@ -466,8 +506,10 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ g, const floa
                                          const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                          const float* __restrict__ sums /*[2][C]: sum g, sum g*xhat*/, float inv_count,
                                          size_t npix, int C, void* dz0, void* dz1, float* __restrict__ partial2,
-                                         const float* __restrict__ dz_scale) {
-  extern __shared__ float smem[];  // [ty][cx*4]
+                                         const float* __restrict__ dz_scale, unsigned int* __restrict__ tickets,
+                                         float* __restrict__ dbias) {
+  extern __shared__ __align__(16) float smem[];  // [ty][cx*4]
+  __shared__ unsigned int s_last;
   // F16X2 planes store dz * s / 2^8 through st4 (which multiplies by the activation scale 2^8): pass dz * s * 2^-8
   float fs = 1.f;
   if constexpr (FMT == AIDE_FMT_F16X2) fs = __ldg(dz_scale) * (1.0f / kF16ActScale);
@@ -511,6 +553,38 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ g, const floa
     }
     *reinterpret_cast<float4*>(partial2 + (size_t)blockIdx.x * C + c) = make_float4(a[0], a[1], a[2], a[3]);
   }
+  if (!tickets) return;
+  // dbias_conv = column sums of partial2, folded by the LAST block of this channel group (fixed order, fp64): saves
+  // the separate reduce launch.  tickets[blockIdx.y]: zero on entry, left zero.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicAdd(&tickets[blockIdx.y], 1u) == gridDim.x - 1u ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* dsm = reinterpret_cast<double*>(smem);       // [ty][cx*4] doubles: the launch reserves 8 bytes per slot
+  double t4[4] = {0, 0, 0, 0};
+  if (cvalid) {
+    for (int r = threadIdx.y; r < (int)gridDim.x; r += blockDim.y) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial2 + (size_t)r * C + c));
+      t4[0] += (double)v.x; t4[1] += (double)v.y; t4[2] += (double)v.z; t4[3] += (double)v.w;
+    }
+  }
+  __syncthreads();
+  double* drow = dsm + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) drow[k] = t4[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && cvalid) {
+    double a[4] = {0, 0, 0, 0};
+    for (int t = 0; t < (int)blockDim.y; ++t) {
+      const double* r = dsm + ((size_t)t * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += r[k];
+    }
+    *reinterpret_cast<float4*>(dbias + c) = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.y] = 0u;
 }
 
 // shared geometry for the two backward kernels
@@ -650,8 +724,7 @@ extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift,
   BwdGeom gm = bwd_geom(N, H, W, C);
   dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
   size_t smem = (size_t)gm.cx * gm.ty * 8 * sizeof(float);
-  unsigned int* gbits = reinterpret_cast<unsigned int*>(gmax);
-  if (gbits) AIDE_CUDA(cudaMemsetAsync(gbits, 0, sizeof(unsigned int), as_stream(stream)));
+  unsigned int* gbits = reinterpret_cast<unsigned int*>(gmax);     // zero on entry (aide_bn_relu_bwd_apply re-zeroes it)
   if (n_pool > 0)
     bn_relu_bwd_reduce_kernel<true><<<grid, block, smem, as_stream(stream)>>>(z, scale_shift, mean_rstd, N, H, W, C,
                                                                               s, g, partial, gbits);
@@ -665,30 +738,43 @@ extern "C" int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift,
 extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd,
                                       const float* gamma, const float* partial, int rows, int N, int H, int W, int C,
                                       void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
-                                      float* partial2, const float* gmax, float* dz_scale, void* stream) {
+                                      float* partial2, float* gmax, float* dz_scale, unsigned int* tickets,
+                                      void* stream) {
   AIDE_REQUIRE(g && z && mean_rstd && gamma && partial && dz_p0 && dgamma && dbeta && partial2,
                "bn_relu_bwd_apply: null argument");
   AIDE_REQUIRE(dbeta + C == dgamma, "bn_relu_bwd_apply: dbeta/dgamma must be adjacent ([2][C] buffer: dbeta, dgamma)");
   BwdGeom gm = bwd_geom(N, H, W, C);
   AIDE_REQUIRE(rows == gm.rows, "bn_relu_bwd_apply: rows mismatch (%d vs %d)", rows, gm.rows);
+  AIDE_REQUIRE(!tickets || gm.cgroups < 15, "bn_relu_bwd_apply: too many channel groups for the ticket block");
   cudaStream_t st = as_stream(stream);
-  // sums[0..C) = sum g (= dbeta), sums[C..2C) = sum g*xhat (= dgamma)
-  reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
-  AIDE_CHECK_LAUNCH();
   size_t npix = (size_t)N * H * W;
-  dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
-  size_t smem = (size_t)gm.cx * gm.ty * 4 * sizeof(float);
   float inv = (float)(1.0 / (double)npix);
+  unsigned int* gbits = reinterpret_cast<unsigned int*>(gmax);
+  // sums[0..C) = sum g (= dbeta), sums[C..2C) = sum g*xhat (= dgamma)
   if (fmt == AIDE_FMT_F16X2) {
     AIDE_REQUIRE(gmax && dz_scale, "bn_relu_bwd_apply: F16X2 needs gmax (from bn_relu_bwd_reduce) and dz_scale[2]");
-    dz_scale_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const unsigned int*>(gmax), mean_rstd, gamma, dbeta, inv, C,
-                                       dz_scale);
+    if (tickets) {
+      bn_bwd_sums_scale_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, C, dbeta, gbits, mean_rstd, gamma,
+                                                                            inv, dz_scale, tickets);
+      AIDE_CHECK_LAUNCH();
+    } else {
+      reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
+      AIDE_CHECK_LAUNCH();
+      dz_scale_kernel<<<1, 256, 0, st>>>(gbits, mean_rstd, gamma, dbeta, inv, C, dz_scale);
+      AIDE_CHECK_LAUNCH();
+    }
+  } else {
+    reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
     AIDE_CHECK_LAUNCH();
   }
+  dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
+  const bool fuse_dbias = tickets && dbias_conv;
+  size_t smem = (size_t)gm.cx * gm.ty * 4 * (fuse_dbias ? sizeof(double) : sizeof(float));
   AIDE_DISPATCH_FMT(fmt, (bn_relu_bwd_apply_kernel<FMT><<<grid, block, smem, st>>>(
-                             g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2, dz_scale)));
+                             g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2, dz_scale,
+                             fuse_dbias ? tickets + 1 : nullptr, dbias_conv)));
   AIDE_CHECK_LAUNCH();
-  if (dbias_conv) {
+  if (dbias_conv && !fuse_dbias) {
     reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(partial2, rows, C, C, dbias_conv);
     AIDE_CHECK_LAUNCH();
   }

@@ -57,6 +57,7 @@ struct HaloParams {
   int BN, kc, n_cchunks, row_bytes;
   int MB, nacc, nbuf, tmem_cols;
   int stack, acc_w;                              // hi/lo weight planes stacked along N (see the MMA issuer); columns per accumulator
+  int b_resident;                                // all 9 * n_cchunks weight stages stay in shared memory (loaded once per CTA)
   int lo_col;                                    // stacked mode: column offset of the A_lo x W_hi product (BN = with hi*lo, 0 = with hi*hi)
   int a_slot_bytes, a_stage_bytes, a_stages;
   int b_plane_bytes, b_stage_bytes, b_stages;
@@ -139,6 +140,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
     const uint32_t b_tx = NPL * p.b_plane_bytes;
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
+    if (p.b_resident) {
+      // RESIDENT WEIGHTS (small layers: the whole [cout][9*cin] matrix fits next to the halo ring): every
+      // (channel slice, tap) stage is fetched ONCE per CTA instead of once per item -- the per-item weight re-fetch
+      // was what pinned the Cout <= 64 layers at the L2 throughput cap (profiles/r1f_conv_halo_f16x2_b32_full.csv).
+      if (leader) {
+        mbar_arrive_expect_tx(bfull(0), (uint32_t)(9 * p.n_cchunks) * b_tx);
+        int s = 0;
+        for (int c = 0, c0 = 0; c < p.n_cchunks; ++c, c0 += p.kc) {
+          for (int tap = 0; tap < 9; ++tap, ++s) {
+            const uint32_t b_dst = base + p.b_off + s * p.b_stage_bytes;
+            tma_load_2d(b_dst, &p.tmB0, bfull(0), tap * p.cin + c0, 0);
+            if (NPL == 2) tma_load_2d(b_dst + p.b_plane_bytes, &p.tmB1, bfull(0), tap * p.cin + c0, 0);
+          }
+        }
+      }
+      __syncwarp();
+    }
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int n_tile = item % p.n_tiles, m0 = (item / p.n_tiles) * p.MB;
       const int mbv = min(p.MB, p.m_tiles - m0);
@@ -169,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
         }
         __syncwarp();
         if (++sa == SA) { sa = 0; pha ^= 1; }
+        if (p.b_resident) continue;
         int kcol = c0;                                  // column of (tap, channel slice) in the [cout][9*cin] matrix
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap, kcol += p.cin) {
@@ -211,6 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
     const bool leader = elect_one();
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0, tcount = 0;
+    const bool resident = p.b_resident != 0;
+    if (resident && (int)blockIdx.x < p.total_items) {
+      mbar_wait(bfull(0), 0);
+      tc_fence_after_sync();
+    }
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++tcount) {
       const int m0 = (item / p.n_tiles) * p.MB;
       const int mbv = min(p.MB, p.m_tiles - m0);
@@ -224,13 +248,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
         mbar_wait(afull(sa), pha);
         tc_fence_after_sync();
         uint64_t a_row = a_desc0 + (uint64_t)(sa * a_stage16);
+        if (resident) sb = c * 9;                       // stage index = (channel slice, tap)
 #pragma unroll 1
         for (int dy = 0; dy < 3; ++dy, a_row += (uint64_t)(kHW * row16)) {
           uint64_t a_tap = a_row;
 #pragma unroll 1
           for (int dx = 0; dx < 3; ++dx, a_tap += (uint64_t)row16) {
-            mbar_wait(bfull(sb), phb);
-            tc_fence_after_sync();
+            if (!resident) {
+              mbar_wait(bfull(sb), phb);
+              tc_fence_after_sync();
+            }
             if (leader) {
               const uint64_t b_hi = b_desc0 + (uint64_t)(sb * b_stage16);
               const uint32_t flag0 = (first >> ai) & 1u;
@@ -252,12 +279,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
                   }
                 }
               }
-              umma_commit(bempty(sb));
+              if (!resident) umma_commit(bempty(sb));
             }
             __syncwarp();
             first |= 1u << ai;
             ai = ai + 1 == p.nacc ? 0 : ai + 1;
-            if (++sb == SB) { sb = 0; phb ^= 1; }
+            if (resident) ++sb;
+            else if (++sb == SB) { sb = 0; phb ^= 1; }
           }
         }
         if (leader) umma_commit(aempty(sa));
@@ -349,7 +377,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct HaloPlan {
-  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack;
+  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack, resident;
   int a_slot, a_stage, b_plane, b_stage, smem;
   double cost;
 };
@@ -379,6 +407,25 @@ constexpr CostModel kRow{256.0, 3.0, 20.0, 100.0, 32.0, 0.2, 0.0, 150.0};
 constexpr CostModel kSel{192.0, 6.0, 10.0, 50.0, 64.0, 0.2, 0.0, 150.0};
 
 double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks, int nks, long long m_tiles, int cout) {
+  if (c.resident) {
+    // weights live in shared memory: an item ingests its halos only, against the chip-wide L2 throughput cap
+    // (~36 B/clk/SM measured); the MMA side is as in the streaming plan
+    const long long items = (m_tiles + c.MB - 1) / c.MB;
+    const long long waves = (items + kNumSMs - 1) / kNumSMs;
+    auto mma_clk = [&](double n) {
+      const double fetch = (m.sm_a + n) / m.sm_d;
+      return (n / 2.0 > fetch ? n / 2.0 : fetch) + m.issue;
+    };
+    const double per_step = npl == 1 ? mma_clk(c.BN) : c.stack ? mma_clk(2.0 * c.BN) + mma_clk(c.BN) : 3.0 * mma_clk(c.BN);
+    const double mma = (double)c.MB * 9 * n_cchunks * nks * per_step;
+    const double bytes = (double)n_cchunks * npl * c.row_bytes * (c.MB * kHaloPix);
+    const double epi = (double)c.MB * (c.BN / 32) * m.epi * c.nacc * (c.stack ? 1.5 : 1.0);
+    double t = mma > bytes / 32.0 ? mma : bytes / 32.0;
+    t *= 1.0 + 0.3 / c.a_stages;
+    if (c.nbuf == 1) t += 3.0 * epi;
+    else if (epi > t) t = epi;
+    return (double)waves * t * 0.85;       // streaming plans of these layers measure ~15 % above their model (L2 cap)
+  }
   const long long items = (m_tiles + c.MB - 1) / c.MB * (cout / c.BN);
   const long long waves = (items + kNumSMs - 1) / kNumSMs;
   // an MMA of 128 x BN x 32 B: tensor rate (BN/2 clk) vs operand fetch from shared memory, plus issue overhead
@@ -400,7 +447,8 @@ double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks,
 bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
   const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
   const int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
-  const int force_stack = env_int("AIDE_CONV_STACK", -1);
+  const int force_stack = env_int("AIDE_CONV_STACK", -1), force_rb = env_int("AIDE_CONV_RB", 0);
+  const int force_res = env_int("AIDE_CONV_WRES", -1);       // -1 planner's choice, 0 never, 1 only resident-weight plans
   best->cost = -1;
   for (int bn = 256; bn >= 32; bn >>= 1) {
     if (cout % bn) continue;
@@ -412,13 +460,17 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
       for (int rb = 128; rb >= 64; rb >>= 1) {
         const int kc = rb / es;
         if (cin % kc) continue;
+        if (force_rb && rb != force_rb) continue;
         const int n_cchunks = cin / kc;
         const int nks = rb / 32;
        for (int stack = 0; stack <= 1; ++stack) {
         if (stack && (npl != 2 || 2 * bn > 256)) continue;
         if (force_stack >= 0 && stack != force_stack && !(stack == 0 && (npl != 2 || 2 * bn > 256))) continue;
-        // accumulation chain per TMEM column: 3 MMAs per 32-byte K step, 2 when the weight planes are stacked
-        const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? (stack ? 2 : 3) : 1);
+        // accumulation chain per TMEM column of the LARGE partial sum: 3 MMAs per 32-byte K step, 2 when the weight
+        // planes are stacked, 1 when both cross terms go to the small accumulator (lo_col; measured on the 256x256
+        // known-answer forward: logits vs fp64 4.1e-5 -> 2.3e-5, same value with a cap of 2 accumulators as with 4)
+        const int losep = env_int("AIDE_CONV_LOSEP", 1);
+        const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? (stack ? (losep ? 1 : 2) : 3) : 1);
         const int nacc = wanted_nacc(fmt, chain);
         const int acc_w = bn * (1 + stack);
         if (mb * nacc * acc_w > 512) continue;
@@ -436,7 +488,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
           c.a_stages = 1;
           rest = avail - c.a_stage;
         }
-        if (rest < 2 * c.b_stage) continue;
+        if (rest < 2 * c.b_stage) continue;      // (a resident plan needs even more room)
         c.b_stages = rest / c.b_stage;
         if (c.b_stages > kMaxBStages) c.b_stages = kMaxBStages;
         if (c.a_stages == 2 && n_cchunks > 2 && c.b_stages > 4 && rest - 4 * c.b_stage >= c.a_stage) {
@@ -445,11 +497,29 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
           if (c.b_stages > kMaxBStages) c.b_stages = kMaxBStages;
         }
         c.smem = 1024 + c.a_stages * c.a_stage + c.b_stages * c.b_stage + kBarBytes;
-        const double row_cost = model_cost(kRow, c, npl, n_cchunks, nks, m_tiles, cout);
-        if (pick_row_cost < 0 || row_cost < pick_row_cost * 0.999) {
-          pick_row_cost = row_cost;
-          pick = c;
-          pick.cost = model_cost(kSel, c, npl, n_cchunks, nks, m_tiles, cout);
+        if (force_res != 1) {
+          const double row_cost = model_cost(kRow, c, npl, n_cchunks, nks, m_tiles, cout);
+          if (pick_row_cost < 0 || row_cost < pick_row_cost * 0.999) {
+            pick_row_cost = row_cost;
+            pick = c;
+            pick.cost = model_cost(kSel, c, npl, n_cchunks, nks, m_tiles, cout);
+          }
+        }
+        // resident-weight variant: the whole weight matrix of the layer next to >= 2 halo stages
+        const int wbytes = 9 * n_cchunks * c.b_stage;
+        if (force_res != 0 && bn == cout && wbytes + 2 * c.a_stage <= avail) {
+          HaloPlan r = c;
+          r.resident = 1;
+          r.a_stages = (avail - wbytes) / c.a_stage;
+          if (r.a_stages > kMaxAStages) r.a_stages = kMaxAStages;
+          r.b_stages = 9 * n_cchunks;
+          r.smem = 1024 + r.a_stages * r.a_stage + wbytes + kBarBytes;
+          const double row_cost = model_cost(kRow, r, npl, n_cchunks, nks, m_tiles, cout);
+          if (pick_row_cost < 0 || row_cost < pick_row_cost * 0.999) {
+            pick_row_cost = row_cost;
+            pick = r;
+            pick.cost = model_cost(kSel, r, npl, n_cchunks, nks, m_tiles, cout);
+          }
         }
        }
       }
@@ -516,7 +586,9 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
   p.n_tiles = cout / p.BN;
   p.total_items = ceil_div(p.m_tiles, p.MB) * p.n_tiles;
   p.a_slot_bytes = pl.a_slot; p.a_stage_bytes = pl.a_stage; p.a_stages = pl.a_stages;
-  p.b_plane_bytes = pl.b_plane; p.b_stage_bytes = pl.b_stage; p.b_stages = pl.b_stages;
+  p.b_plane_bytes = pl.b_plane; p.b_stage_bytes = pl.b_stage;
+  p.b_resident = pl.resident;
+  p.b_stages = pl.resident ? 1 : pl.b_stages;          // ring depth (barriers); resident: one "all weights landed" barrier
   p.b_off = pl.a_stages * pl.a_stage;
   p.bar_off = p.b_off + pl.b_stages * pl.b_stage;
   int cols = p.nbuf * p.MB * p.nacc * p.acc_w;
@@ -545,7 +617,7 @@ extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, 
   HaloPlan pl;
   make_plan(fmt, cin, cout, (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH), &pl);
   out[0] = pl.BN; out[1] = pl.MB; out[2] = pl.nacc; out[3] = pl.nbuf; out[4] = pl.row_bytes; out[5] = pl.a_stages;
-  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack;
+  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack + 2 * pl.resident;
   return 0;
 }
 

@@ -110,6 +110,50 @@ __global__ void __launch_bounds__(256) weight_prep_tiled_kernel(const float* __r
   }
 }
 
+// All tensor-core layers of a network in ONE launch (a step used to spend 60 launches here): the per-layer arguments
+// travel as a kernel parameter table, blockIdx.x is mapped to (layer, co tile, ci tile) through the tile prefix sums.
+constexpr int kPrepMaxLayers = 40;
+struct PrepTable {
+  const float* w[kPrepMaxLayers];
+  void* f0[kPrepMaxLayers];
+  void* f1[kPrepMaxLayers];
+  void* d0[kPrepMaxLayers];
+  void* d1[kPrepMaxLayers];
+  int cout[kPrepMaxLayers], cin[kPrepMaxLayers], tile_end[kPrepMaxLayers];
+  int n;
+};
+template <int FMT>
+__global__ void __launch_bounds__(256) weight_prep_batch_kernel(const __grid_constant__ PrepTable t) {
+  constexpr int CO_STRIDE = 32 * 9 + 1;
+  __shared__ float tile[32 * CO_STRIDE];
+  int l = 0;
+  while (l + 1 < t.n && (int)blockIdx.x >= t.tile_end[l]) ++l;
+  const int local = (int)blockIdx.x - (l ? t.tile_end[l - 1] : 0);
+  const int cout = t.cout[l], cin = t.cin[l];
+  const int co0 = (local % (cout / 32)) * 32, ci0 = (local / (cout / 32)) * 32;
+  const float* __restrict__ w = t.w[l];
+  void *f0 = t.f0[l], *f1 = t.f1[l], *d0 = t.d0[l], *d1 = t.d1[l];
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int co = i / 288, r = i - co * 288;
+    tile[co * CO_STRIDE + r] = w[((size_t)(co0 + co) * cin + ci0) * 9 + r];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr float ws = FMT == AIDE_FMT_F16X2 ? kF16WScale / kF16ActScale : 1.0f;
+  if (f0) {
+    for (int row = wid; row < 32 * 9; row += 8) {
+      const int co = row / 9, tap = row - co * 9;
+      st1<FMT>(f0, f1, ((size_t)(co0 + co) * 9 + tap) * cin + ci0 + lane, tile[co * CO_STRIDE + lane * 9 + tap] * ws);
+    }
+  }
+  if (d0) {
+    for (int row = wid; row < 32 * 9; row += 8) {
+      const int ci = row / 9, tap = row - ci * 9;
+      st1<FMT>(d0, d1, ((size_t)(ci0 + ci) * 9 + (8 - tap)) * cout + co0 + lane, tile[lane * CO_STRIDE + ci * 9 + tap] * ws);
+    }
+  }
+}
+
 }  // namespace aide
 
 using namespace aide;
@@ -156,5 +200,33 @@ extern "C" int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
   AIDE_DISPATCH_FMT(fmt, (weight_prep_kernel<FMT><<<blocks, 256, 0, as_stream(stream)>>>(
                              w_oihw, cout, cin, fwd_p0, fwd_p1, dgrad_p0, dgrad_p1)));
   AIDE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int aide_weight_prep_batch(int fmt, int n_layers, const float* const* w_oihw, const int* cout, const int* cin,
+                                      void* const* fwd_p0, void* const* fwd_p1, void* const* dgrad_p0,
+                                      void* const* dgrad_p1, void* stream) {
+  AIDE_REQUIRE(n_layers >= 1 && w_oihw && cout && cin && fwd_p0 && fwd_p1 && dgrad_p0 && dgrad_p1,
+               "weight_prep_batch: bad arguments");
+  AIDE_REQUIRE(fmt == AIDE_FMT_TF32X2 || fmt == AIDE_FMT_BF16 || fmt == AIDE_FMT_F16X2,
+               "weight_prep_batch: tensor-core operand formats only");
+  for (int base = 0; base < n_layers; base += kPrepMaxLayers) {
+    PrepTable t{};
+    t.n = n_layers - base < kPrepMaxLayers ? n_layers - base : kPrepMaxLayers;
+    int tiles = 0;
+    for (int i = 0; i < t.n; ++i) {
+      const int l = base + i;
+      AIDE_REQUIRE(w_oihw[l] && cout[l] > 0 && cin[l] > 0 && cout[l] % 32 == 0 && cin[l] % 32 == 0,
+                   "weight_prep_batch: layer %d needs cout %% 32 == 0 and cin %% 32 == 0", l);
+      AIDE_REQUIRE((fwd_p0[l] || dgrad_p0[l]) && (fmt_planes(fmt) == 1 || ((!fwd_p0[l] || fwd_p1[l]) && (!dgrad_p0[l] || dgrad_p1[l]))),
+                   "weight_prep_batch: layer %d: missing destination plane", l);
+      t.w[i] = w_oihw[l]; t.f0[i] = fwd_p0[l]; t.f1[i] = fwd_p1[l]; t.d0[i] = dgrad_p0[l]; t.d1[i] = dgrad_p1[l];
+      t.cout[i] = cout[l]; t.cin[i] = cin[l];
+      tiles += (cout[l] / 32) * (cin[l] / 32);
+      t.tile_end[i] = tiles;
+    }
+    AIDE_DISPATCH_FMT(fmt, (weight_prep_batch_kernel<FMT><<<tiles, 256, 0, as_stream(stream)>>>(t)));
+    AIDE_CHECK_LAUNCH();
+  }
   return 0;
 }

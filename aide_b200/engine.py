@@ -270,13 +270,23 @@ class PreparedWeights:
         self.arena = torch.empty(total, dtype=torch.uint8, device=dev)
         base = self.arena.data_ptr()
         st = _stream()
+        batch = []                                  # tensor-core layers: ONE launch for the whole network
         for u in plan.units:
             f = FMT_F32 if u.first else fmt
             fwd, dg, pb = self.off[u.name]
             two = _planes(f) == 2
             w = conv_weight_oihw(u, params)
-            call("aide_weight_prep", f, w.data_ptr(), u.cout, u.cin, base + fwd, base + fwd + pb if two else None,
-                 base + dg if dg >= 0 else None, base + dg + pb if (dg >= 0 and two) else None, st)
+            args = (w.data_ptr(), u.cout, u.cin, base + fwd, base + fwd + pb if two else None,
+                    base + dg if dg >= 0 else None, base + dg + pb if (dg >= 0 and two) else None)
+            if f != FMT_F32 and u.cout % 32 == 0 and u.cin % 32 == 0 and not u.transposed:
+                batch.append(args)
+            else:
+                call("aide_weight_prep", f, *args, st)
+        if batch:
+            n = len(batch)
+            col = lambda i, ty: (ty * n)(*[b[i] for b in batch])
+            call("aide_weight_prep_batch", fmt, n, col(0, C.c_void_p), col(1, C.c_int), col(2, C.c_int),
+                 col(3, C.c_void_p), col(4, C.c_void_p), col(5, C.c_void_p), col(6, C.c_void_p), st)
 
     def fwd(self, u: Unit, fmt: int):
         fwd, _, pb = self.off[u.name]
@@ -304,8 +314,19 @@ def _view(layout: Layout, base: int, name: str, coff: int):
     return p0, p1, c, coff
 
 
+def ticket_offsets(plan: Plan) -> Tuple[Dict[str, int], int]:
+    """Word offsets of every unit's statistics tickets inside one per-network int32 buffer (zero-initialised once; the
+    kernels leave the counters at zero), and the buffer's length."""
+    off, cur = {}, 0
+    for u in plan.units:
+        off[u.name] = cur
+        cur += lib.aide_bn_ticket_slots(u.cout)
+    return off, cur
+
+
 def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], weights: PreparedWeights,
-                inputs: Sequence, training: bool, logits: torch.Tensor, arena: torch.Tensor, groups: int = 1) -> None:
+                inputs: Sequence, training: bool, logits: torch.Tensor, arena: torch.Tensor, groups: int = 1,
+                tickets: Optional[Tuple[torch.Tensor, Dict[str, int]]] = None) -> None:
     """One forward pass.  groups > 1: `inputs` is a list of `groups` input tuples (the AIDE step's augmented views,
     trainchaos_proposed_30cases1labeled.py:265-269) stacked along the batch: every convolution / upsample / the head
     run ONCE on the stacked batch, while BatchNorm statistics, the running-statistics updates and the normalisation
@@ -345,7 +366,8 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             call("aide_bn_finalize_grouped", stp, rows_g, G, u.cout, float(Ng * h * w),
                  params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
                  params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
-                 BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * u.cout * 4, st)
+                 BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * u.cout * 4,
+                 tickets[0].data_ptr() + 4 * tickets[1][u.name] if tickets is not None else None, st)
             d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
             pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
             pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
@@ -483,9 +505,11 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
     reserve("part", max_part)
     reserve("part2", max_part)
     reserve("ws", max_ws)
-    reserve("gscale", 16)          # [0] max |g| (bits), [1..2] = {s, 1/s}: dynamic power-of-two scale of an F16X2 dZ
+    reserve("gscale", 128)         # [0] max |g| (bits), [1..2] = {s, 1/s}: dynamic power-of-two scale of an F16X2 dZ;
+                                   # words [16, 32): tickets of the one-launch reductions.  Zero on entry, left zero.
     barena = torch.empty(cur, dtype=torch.uint8, device=arena.device)
     bb = barena.data_ptr()
+    barena[off["gscale"]:off["gscale"] + 128].zero_()
 
     def src_ptr(kind, obj):
         if kind == "unit":
@@ -533,7 +557,7 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             dz1 = dz0 + _align(N * h * w * u.cout * _esize(ufmt)) if _planes(ufmt) == 2 else None
             call("aide_bn_relu_bwd_apply", ufmt, g, z, mr, params[u.bn + ".weight"].data_ptr(), part, rows,
                  N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"), gptr(u.conv + ".bias"),
-                 part2, gmax, dz_scale, st)
+                 part2, gmax, dz_scale, bb + off["gscale"] + 64, st)
             x0, x1, xct, xco = _view(layout, base, u.src[0], u.src[1])
             call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
                  bb + off["ws"], max_ws, gptr(u.conv + ".weight"), st)

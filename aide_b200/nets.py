@@ -93,11 +93,13 @@ class _EngineNet(nn.Module):
         self._tensors: Optional[Dict[str, torch.Tensor]] = None
         self._scratch: Optional[torch.Tensor] = None
         self.last_grad_flat: Optional[torch.Tensor] = None
+        self._ticket_off, self._ticket_total = E.ticket_offsets(plan)
+        self._tickets: Optional[torch.Tensor] = None          # zero-initialised once per device, self-resetting
 
     # ---- bookkeeping ---------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._tensors, self._weights, self._scratch = None, {}, None
+        self._tensors, self._weights, self._scratch, self._tickets = None, {}, None, None
         return out
 
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -183,7 +185,9 @@ class _EngineNet(nn.Module):
             xs = [[x.detach().contiguous() for x in v] for v in inputs]
         else:
             xs = [x.detach().contiguous() for x in inputs]
-        E.run_forward(plan, layout, named, wts, xs, training, logits, arena, groups)
+        if self._tickets is None or self._tickets.device != dev:
+            self._tickets = torch.zeros(max(self._ticket_total, 1), dtype=torch.int32, device=dev)
+        E.run_forward(plan, layout, named, wts, xs, training, logits, arena, groups, (self._tickets, self._ticket_off))
         if training:
             torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], groups)
         tape = None

@@ -138,6 +138,19 @@ def bn_finalize(part, count, gamma, beta, rmean, rvar, training=True, momentum=0
     return ss, mr
 
 
+def bn_finalize_grouped(parts, count, gamma, beta, rmean, rvar, tickets=None, momentum=0.1, eps=1e-5):
+    """parts [G, rows, 2, C] (consumed: folded in place) -> scale_shift [G,2,C], mean_rstd [G,2,C]; the running
+    statistics are updated once per group, in order.  tickets: zero-initialised int32 [aide_bn_ticket_slots(C)] selects
+    the one-launch fold + finalize path."""
+    G, rows, _, C_ = parts.shape
+    ss = torch.empty((G, 2, C_), dtype=torch.float32, device=gamma.device)
+    mr = torch.empty((G, 2, C_), dtype=torch.float32, device=gamma.device)
+    call("aide_bn_finalize_grouped", parts.data_ptr(), rows, G, C_, float(count), gamma.data_ptr(), beta.data_ptr(),
+         rmean.data_ptr() if rmean is not None else None, rvar.data_ptr() if rvar is not None else None, momentum, eps, 1,
+         ss.data_ptr(), mr.data_ptr(), tickets.data_ptr() if tickets is not None else None, _st())
+    return ss, mr
+
+
 def bn_relu_apply(z: torch.Tensor, ss: torch.Tensor, fmt: int, pool: bool = False):
     N, H, W, C_ = z.shape
     y = Act(N, H, W, C_, fmt, z.device)

@@ -58,6 +58,11 @@ int aide_nhwc_to_nchw(int fmt, const void* src_p0, const void* src_p1, int src_c
  * either destination may be NULL. */
 int aide_weight_prep(int fmt, const float* w_oihw, int cout, int cin,
                      void* fwd_p0, void* fwd_p1, void* dgrad_p0, void* dgrad_p1, void* stream);
+/* The same for n_layers tensor-core layers (cout % 32 == 0, cin % 32 == 0) in ONE launch: host arrays of per-layer
+ * pointers / sizes (every conv of fuseunet.py:12-39 after an optimiser step). */
+int aide_weight_prep_batch(int fmt, int n_layers, const float* const* w_oihw, const int* cout, const int* cin,
+                           void* const* fwd_p0, void* const* fwd_p1, void* const* dgrad_p0, void* const* dgrad_p1,
+                           void* stream);
 
 /* ---- conv3x3, stride 1, pad 1 (netblocks.py:24,26,17 -> ATen conv2d / cuDNN) -------------------- */
 /* z[n,h,w,co] = bias[co] + sum_{tap,ci} x[n,h+dy,w+dx,ci] * w[co][tap][ci].
@@ -74,7 +79,7 @@ int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
                      float* stat_partial, void* stream);
 /* Tiling the tcgen05 forward/dgrad kernel picks for a layer (diagnostics for bench.py / tools): out[9] =
  * {cout tile, pixel tiles per CTA iteration, accumulators per tile, TMEM buffers, smem row bytes, halo stages,
- *  weight stages, dynamic smem bytes, hi/lo weight planes stacked along N}.  Returns non-zero when the layer runs on the first-generation kernel. */
+  *  weight stages, dynamic smem bytes, bit 0: hi/lo weight planes stacked along N, bit 1: weights resident in shared memory}.  Returns non-zero when the layer runs on the first-generation kernel. */
 int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, int W, int* out);
 /* dX[n,h,w,ci] = sum_{tap,co} dz[n,h+dy,w+dx,co] * w[co][ci][flipped tap]  (ATen conv backward-data): the forward
  * kernel on dgrad-prepared weights (aide_weight_prep).  dz is a plain [N,H,W,cout] operand-format buffer, dx an fp32
@@ -106,7 +111,11 @@ int aide_bn_finalize(float* stat_partial /* folded in place: consumed */, int ro
  * running statistics are updated once per group, in group order, exactly like sgroups separate forward calls. */
 int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgroups, int C, double count, const float* gamma,
                              const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                             int training, float* scale_shift, float* mean_rstd, void* stream);
+                             int training, float* scale_shift, float* mean_rstd, unsigned int* tickets, void* stream);
+/* tickets (nullable): aide_bn_ticket_slots(C) zero-initialised counters.  When given, the chunk fold and the finalize
+ * run as ONE launch: the last fold block of a channel group to arrive (ticket) finalises it, reading the folded
+ * partials in fixed order -- bit-identical to the two-launch path.  The counters are left at zero. */
+int aide_bn_ticket_slots(int C);
 /* y = relu(scale*z+shift) written to `dst` (full resolution) and, when given, the 2x2 max-pooled y to
  * up to two half-resolution views (the fused-encoder concat and the modal-2 branch, fuseunet.py:51-56). */
 int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, int C, const float* scale_shift,
@@ -122,7 +131,8 @@ int aide_bn_relu_apply_grouped(int fmt, const float* z, int N, int imgs_per_grou
  * up to 3 same-resolution slices and up to 3 half-resolution slices routed through the max-pool
  * arg-max (first maximum in window scan order wins, like ATen max_pool2d_with_indices).  y is
  * recomputed from z.  Writes g [N,H,W,C] and per-block partial sums of (g, g*xhat): [rows][2][C],
- * rows = aide_bn_bwd_rows(N,H,W,C). */
+ * rows = aide_bn_bwd_rows(N,H,W,C).  gmax (nullable): device word that receives max |g| by atomicMax -- it must be
+ * ZERO on entry; aide_bn_relu_bwd_apply consumes it and leaves it zero for the next unit. */
 int aide_bn_bwd_rows(int N, int H, int W, int C);
 int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift, const float* mean_rstd,
                             int N, int H, int W, int C,
@@ -135,11 +145,13 @@ int aide_bn_relu_bwd_reduce(const float* z, const float* scale_shift, const floa
  * partial2: scratch [rows][C] fp32 (rows as above).
  * AIDE_FMT_F16X2: the dz planes hold dz*s, s a power of two derived on the device from `gmax` (the reduce stage's
  * max |g|) and the channel statistics; dz_scale[2] receives {s, 1/s} for aide_conv3x3_dgrad / _wgrad.  Both may be
- * NULL for the other formats. */
+ * NULL for the other formats.  tickets (nullable): 16 zero-initialised words, left zero; when given, the column
+ * reduction + scale derivation run as one launch and dbias_conv is folded by the last block of the apply kernel
+ * (fixed order, same values) instead of two extra launches. */
 int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, const float* mean_rstd, const float* gamma,
                            const float* partial, int rows, int N, int H, int W, int C,
                            void* dz_p0, void* dz_p1, float* dgamma, float* dbeta, float* dbias_conv,
-                           float* partial2, const float* gmax, float* dz_scale, void* stream);
+                           float* partial2, float* gmax, float* dz_scale, unsigned int* tickets, void* stream);
 
 /* ---- nn.Upsample(scale_factor=2, bilinear, align_corners=True) (netblocks.py:16) ---------------- */
 int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_p1, int src_ctot, int src_coff,

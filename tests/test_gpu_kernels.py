@@ -95,6 +95,23 @@ def test_bn_finalize_folds_many_rows(dev):
     ss, mr = ops.bn_finalize(part.to(dev), count, gamma.to(dev), beta.to(dev), None, None, True)
     assert relmax(mr[0], mean) < 1e-6 and relmax(mr[1], 1.0 / torch.sqrt(var + 1e-5)) < 1e-6
     assert relmax(ss[0], gamma.double() / torch.sqrt(var + 1e-5)) < 1e-6
+    # one-launch path (fold + finalize by the last block of each channel group): bit-identical, tickets left at zero;
+    # with running statistics and several statistics groups (the stacked pseudo-label forward)
+    G = 3
+    parts = torch.randn(G, rows, 2, C, generator=torch.Generator().manual_seed(4)).abs() + 0.1
+    parts[:, :, 1] += 50.0
+    outs = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        tk = torch.zeros(ops.lib.aide_bn_ticket_slots(C), dtype=torch.int32, device=dev)
+        ss2, mr2 = ops.bn_finalize_grouped(parts.to(dev), count, gamma.to(dev), beta.to(dev), rm, rv,
+                                           tickets=tk if fused else None)
+        assert int(tk.abs().sum()) == 0
+        outs.append((ss2, mr2, rm, rv))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    m2 = parts[2].double().sum(0)[0] / count
+    assert relmax(outs[1][1][2, 0], m2) < 1e-6
 
 
 @pytest.mark.parametrize("fmt", [0, 1, 2, 3])
@@ -184,9 +201,10 @@ def test_bn_relu_pool_forward(dev, fmt, training):
     assert relmax(rmd, rm_ref) < 1e-5 and relmax(rvd, rv_ref) < 1e-5
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("gscale", [1.0, 3e-7, 2e3])
 @pytest.mark.parametrize("fmt", [0, 1, 3])
-def test_bn_relu_pool_backward(dev, fmt, gscale):
+def test_bn_relu_pool_backward(dev, fmt, gscale, fused):
     """g routing: one same-resolution source + two pooled sources (the modal-2 level-1 pattern).  F16X2 stores dZ
     with a power-of-two scale chosen on the device: exercised with tiny and huge upstream gradients."""
     if fmt != 3 and gscale != 1.0:
@@ -216,7 +234,8 @@ def test_bn_relu_pool_backward(dev, fmt, gscale):
     part2 = torch.empty(rows, Cc, device=dev)
     dptr, dct, dco = (C.c_void_p * 3)(d0.data_ptr()), (C.c_int * 3)(64), (C.c_int * 3)(16)
     pptr, pct, pco = (C.c_void_p * 3)(p0.data_ptr(), p1.data_ptr()), (C.c_int * 3)(64, Cc), (C.c_int * 3)(32, 0)
-    gs = torch.zeros(4, device=dev)             # [0] max|g| bits, [1] s, [2] 1/s
+    gs = torch.zeros(4, device=dev)             # [0] max|g| bits (zero on entry), [1] s, [2] 1/s
+    tk = torch.zeros(16, dtype=torch.int32, device=dev)     # ticket block of the one-launch paths (zero on entry)
     dyn = fmt == 3
     call("aide_bn_relu_bwd_reduce", zd.data_ptr(), ss.data_ptr(), mr.data_ptr(), N, H, W, Cc, dptr, dct, dco, 1,
          pptr, pct, pco, 2, g.data_ptr(), part1.data_ptr(), gs[0:].data_ptr() if dyn else None, st)
@@ -224,12 +243,14 @@ def test_bn_relu_pool_backward(dev, fmt, gscale):
     small = torch.empty(3, Cc, device=dev)
     call("aide_bn_relu_bwd_apply", fmt, g.data_ptr(), zd.data_ptr(), mr.data_ptr(), gamma.detach().to(dev).data_ptr(),
          part1.data_ptr(), rows, N, H, W, Cc, dz.p0, dz.p1, small[1].data_ptr(), small[0].data_ptr(),
-         small[2].data_ptr(), part2.data_ptr(), gs[0:].data_ptr() if dyn else None, gs[1:].data_ptr() if dyn else None, st)
+         small[2].data_ptr(), part2.data_ptr(), gs[0:].data_ptr() if dyn else None, gs[1:].data_ptr() if dyn else None,
+         tk.data_ptr() if fused else None, st)
     got = ops.to_nchw(dz)
+    assert int(tk.abs().sum()) == 0             # tickets are left at zero
     if dyn:
         s_, inv = gs[1].item(), gs[2].item()
         assert s_ > 0 and abs(s_ * inv - 1.0) < 1e-6 and abs(torch.tensor(s_).log2().item() % 1.0) < 1e-6   # power of two
-        assert abs(gs[0:1].view(torch.int32).view(torch.float32).item() - g.abs().max().item()) == 0.0
+        assert gs[0].item() == 0.0                  # max|g| was consumed and reset for the next unit
         got = got * 256.0 * inv                     # Act.to_nchw divides by the static activation scale 2^8
         assert (got.abs().max() * s_).item() < 65504 / 4      # head-room of the bound
     assert relmax(got, dz_ref) < 5e-5

@@ -28,6 +28,8 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--json", default="")
 ap.add_argument("--sweep", action="store_true", help="time every (cout tile, pixel-tile blocking) the planner can build")
 ap.add_argument("--nacc", action="store_true", help="accuracy/time of the accumulator-splitting levels on long chains")
+ap.add_argument("--sweep-full", action="store_true", help="--sweep also over the stacked / plain weight planes and the row width")
+ap.add_argument("--max-cout", type=int, default=0, help="restrict the timing / sweep to layers with cout <= this")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.backends.cudnn.allow_tf32 = False
@@ -44,7 +46,8 @@ def plan(fmt, cin, cout, N, H, W):
     out = (C.c_int * 9)()
     if A.lib.aide_conv3x3_plan_info(fmt, cin, cout, N, H, W, out):
         return None
-    return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6], stack=out[8])
+    return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6], stack=out[8] & 1,
+                res=out[8] >> 1)
 
 
 def check(fmt, N, H, W, cin, cout):
@@ -95,7 +98,7 @@ from aide_b200 import engine as E  # noqa: E402
 plan_net = E.plan_fuseunet(2)
 shapes = {}
 for u in plan_net.units:
-    if not u.first:
+    if not u.first and (not args.max_cout or u.cout <= args.max_cout):
         key = (u.cin, u.cout, 256 >> u.level)
         shapes[key] = shapes.get(key, 0) + 1
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -177,6 +180,43 @@ def time_layer(fmt, cin, cout, hw, reps=3):
         t += e0.elapsed_time(e1)
     return t / reps
 
+
+if args.sweep_full:
+    for fmt in args.fmts:
+        for (cin, cout, hw), count in sorted(shapes.items(), key=lambda kv: -kv[0][2]):
+            flop = 2.0 * B * hw * hw * cout * cin * 9
+            KEYS = ("AIDE_CONV_BN", "AIDE_CONV_MB", "AIDE_CONV_STACK", "AIDE_CONV_RB", "AIDE_CONV_WRES")
+            for k in KEYS:
+                os.environ.pop(k, None)
+            dflt = plan(fmt, cin, cout, B, hw, hw)
+            res = []
+            for bn in (32, 64, 128, 256):
+                if cout % bn:
+                    continue
+                for mb in (1, 2, 4):
+                    for stack in (0, 1):
+                        for rb in (64, 128):
+                            for wres in (0, 1):
+                                os.environ.update(AIDE_CONV_BN=str(bn), AIDE_CONV_MB=str(mb), AIDE_CONV_STACK=str(stack),
+                                                  AIDE_CONV_RB=str(rb), AIDE_CONV_WRES=str(wres))
+                                pl = plan(fmt, cin, cout, B, hw, hw)
+                                if pl is None or pl["BN"] != bn or pl["MB"] != mb or pl["stack"] != stack or pl["rb"] != rb \
+                                        or pl["res"] != wres:
+                                    continue
+                                try:
+                                    ms = time_layer(fmt, cin, cout, hw)
+                                except Exception as ex:  # noqa: BLE001
+                                    print(f"[ERR] sweep {cin}->{cout}@{hw} BN={bn} MB={mb} stack={stack} rb={rb} res={wres}: {ex}",
+                                          flush=True)
+                                    continue
+                                res.append((ms, bn, mb, stack, rb, pl))
+            for k in KEYS:
+                os.environ.pop(k, None)
+            res.sort(key=lambda r: r[0])
+            line = "  ".join(f"BN{bn}/MB{mb}/s{stack}/r{rb}/w{pl['res']}/a{pl['nacc']}b{pl['nbuf']}A{pl['aS']}B{pl['bS']}:{flop / ms / 1e9:.0f}"
+                             for ms, bn, mb, stack, rb, pl in res[:12])
+            print(f"SWEEPF {NAMES[fmt]:7s} {cin:4d}->{cout:3d} @{hw:3d} default {dflt} {flop / time_layer(fmt, cin, cout, hw) / 1e9:.0f} TF | {line}",
+                  flush=True)
 
 if args.sweep:
     sweep = {}
