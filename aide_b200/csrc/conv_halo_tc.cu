@@ -444,11 +444,45 @@ double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks,
   return (double)waves * t;
 }
 
-bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
+// Measured tilings (tools/halo_probe.py --sweep-full on B200 -> tools/make_plan_table.py): the best (cout tile, pixel-tile
+// blocking, stacked planes, row width) for the layer shapes of fuseunet / UNet at the batches the AIDE step launches.
+struct PlanEntry {
+  int fmt, cin, cout, m_tiles, BN, MB, stack, rb;
+};
+constexpr PlanEntry kPlanTable[] = {
+#include "conv_plan_table.inc"
+};
+
+const PlanEntry* lookup_plan(int fmt, int cin, int cout, long long m_tiles) {
+  const PlanEntry* hit = nullptr;
+  double best_ratio = 1.26;                       // same layer, tile count within 25 %: the same tiling regime
+  for (const PlanEntry& e : kPlanTable) {
+    if (e.fmt != fmt || e.cin != cin || e.cout != cout) continue;
+    const double r = (double)m_tiles > e.m_tiles ? (double)m_tiles / e.m_tiles : (double)e.m_tiles / (double)m_tiles;
+    if (r < best_ratio) {
+      best_ratio = r;
+      hit = &e;
+    }
+  }
+  return hit;
+}
+
+bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bool use_table = true) {
   const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
-  const int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
-  const int force_stack = env_int("AIDE_CONV_STACK", -1), force_rb = env_int("AIDE_CONV_RB", 0);
-  const int force_res = env_int("AIDE_CONV_WRES", -1);       // -1 planner's choice, 0 never, 1 only resident-weight plans
+  int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
+  int force_stack = env_int("AIDE_CONV_STACK", -1), force_rb = env_int("AIDE_CONV_RB", 0);
+  // resident-weight plans (-1 planner's choice, 0 never, 1 only those).  Default 0: measured slower than streaming on
+  // every layer they fit (profiles/r2c_*: 64->64 @256 235 vs 311 TFLOP/s) -- the Cout <= 64 layers are bound by
+  // shared-memory operand reads per MMA, not by the weight re-fetch.
+  const int force_res = env_int("AIDE_CONV_WRES", 0);
+  if (use_table && !force_bn && !force_mb && force_stack < 0 && !force_rb && force_res == 0 &&
+      env_int("AIDE_CONV_TABLE", 1)) {
+    if (const PlanEntry* e = lookup_plan(fmt, cin, cout, m_tiles)) {
+      // build exactly the measured tiling through the same enumeration (forced parameters); fall back to the model
+      // if it does not fit (cannot happen for the shapes it was measured on)
+      force_bn = e->BN; force_mb = e->MB; force_stack = e->stack; force_rb = e->rb;
+    }
+  }
   best->cost = -1;
   for (int bn = 256; bn >= 32; bn >>= 1) {
     if (cout % bn) continue;
@@ -527,6 +561,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best) {
       if (best->cost < 0 || pick.cost < best->cost * 0.999) *best = pick;
     }
   }
+  if (best->cost < 0 && use_table) return make_plan(fmt, cin, cout, m_tiles, best, false);
   return best->cost >= 0;
 }
 

@@ -303,7 +303,7 @@ class PreparedWeights:
 # forward
 # ------------------------------------------------------------------------------------------------
 class Tape:
-    __slots__ = ("layout", "arena", "weights", "training", "inputs_shape")
+    __slots__ = ("layout", "arena", "weights", "training", "inputs_shape", "group")
 
 
 def _view(layout: Layout, base: int, name: str, coff: int):
@@ -330,8 +330,8 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
     """One forward pass.  groups > 1: `inputs` is a list of `groups` input tuples (the AIDE step's augmented views,
     trainchaos_proposed_30cases1labeled.py:265-269) stacked along the batch: every convolution / upsample / the head
     run ONCE on the stacked batch, while BatchNorm statistics, the running-statistics updates and the normalisation
-    stay per group, in order -- exactly what `groups` separate forward calls compute (only for forwards that keep no
-    tape: the per-unit scale/shift scratch is reused from group to group)."""
+    stay per group, in order -- exactly what `groups` separate forward calls compute.  Every group keeps its own
+    scale/shift and mean/rstd rows, so a tape of the stacked forward serves a backward through any one group."""
     N, H, W, fmt = layout.N, layout.H, layout.W, layout.fmt
     G = groups
     Ng = N // G
@@ -464,15 +464,26 @@ class GradLayout:
 
 def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: Layout,
                  params: Dict[str, torch.Tensor], weights: PreparedWeights, arena: torch.Tensor,
-                 dlogits: torch.Tensor, grad_flat: torch.Tensor) -> None:
-    """Writes every parameter gradient into `grad_flat` (fp32, laid out by `glayout`)."""
-    N, H, W, fmt = layout.N, layout.H, layout.W, layout.fmt
+                 dlogits: torch.Tensor, grad_flat: torch.Tensor, group: int = 0) -> None:
+    """Writes every parameter gradient into `grad_flat` (fp32, laid out by `glayout`).  `group`: which statistics group
+    of a stacked-batch forward the backward runs through (the train forward rides as the LAST group of the stacked
+    pseudo-label forward, AideTrainer); its images, raw conv outputs and BatchNorm statistics are slices of the tape."""
+    H, W, fmt = layout.H, layout.W, layout.fmt
+    G = layout.groups
+    N = layout.N // G                                  # images of the group
     base = arena.data_ptr()
     st = _stream()
     gbase = grad_flat.data_ptr()
 
     def gptr(name):
         return gbase + glayout.off[name][0] * 4
+
+    def aview(name, coff):
+        """channel view of activation buffer `name`, advanced to the first image of the group"""
+        p0, p1, ctot, co = _view(layout, base, name, coff)
+        lvl = plan.bufs[name][0]
+        skip = group * N * (H >> lvl) * (W >> lvl) * ctot * _esize(layout.buf_fmt(name))
+        return p0 + skip, (p1 + skip if p1 is not None else None), ctot, co
 
     # ---- backward arena: dX per unit / upsample / head, shared scratch for g, dz, partials, wgrad workspace
     off: Dict[str, int] = {}
@@ -521,7 +532,7 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
     for op in reversed(plan.ops):
         if isinstance(op, tuple) and op[0] == "head":
             _, name, cin = op
-            x0, x1, xct, xco = _view(layout, base, name, 0)
+            x0, x1, xct, xco = aview(name, 0)
             call("aide_conv1x1_bwd", fmt, x0, x1, xct, xco, cin, params["last_conv1.weight"].data_ptr(),
                  dlogits.data_ptr(), plan.num_classes, N, H, W, bb + off["dx:head"], gptr("last_conv1.weight"),
                  bb + off["headpart"], st)
@@ -542,9 +553,9 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             pptr = (C.c_void_p * 3)(*[src_ptr(k, o) for k, o, _, _ in pooled])
             pct = (C.c_int * 3)(*[cc for _, _, _, cc in pooled])
             pco = (C.c_int * 3)(*[co for _, _, co, _ in pooled])
-            z = base + layout.off["z:" + u.name]
-            ss = base + layout.off["ss:" + u.name]
-            mr = ss + 2 * u.cout * 4
+            z = base + layout.off["z:" + u.name] + group * N * h * w * u.cout * 4
+            ss = base + layout.off["ss:" + u.name] + group * 2 * u.cout * 4          # scale_shift [G][2][C] ...
+            mr = base + layout.off["ss:" + u.name] + (G + group) * 2 * u.cout * 4    # ... then mean_rstd [G][2][C]
             g, part, part2 = bb + off["g"], bb + off["part"], bb + off["part2"]
             dyn = ufmt == FMT_F16X2
             gmax = bb + off["gscale"] if dyn else None
@@ -558,7 +569,7 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             call("aide_bn_relu_bwd_apply", ufmt, g, z, mr, params[u.bn + ".weight"].data_ptr(), part, rows,
                  N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"), gptr(u.conv + ".bias"),
                  part2, gmax, dz_scale, bb + off["gscale"] + 64, st)
-            x0, x1, xct, xco = _view(layout, base, u.src[0], u.src[1])
+            x0, x1, xct, xco = aview(u.src[0], u.src[1])
             call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
                  bb + off["ws"], max_ws, gptr(u.conv + ".weight"), st)
             if not u.first:

@@ -194,6 +194,7 @@ class _EngineNet(nn.Module):
         if keep_tape:
             tape = E.Tape()
             tape.layout, tape.arena, tape.weights, tape.training = layout, arena, wts, training
+            tape.group = groups - 1          # a stacked forward with a tape: the backward runs through the LAST group
         return logits, tape
 
     def _engine_backward(self, tape, dlogits):
@@ -204,7 +205,7 @@ class _EngineNet(nn.Module):
         # zeros, not empty: the 4-element alignment gaps between tensors are part of the flat Adam / all-reduce buffer
         flat = torch.zeros(self._glayout.total, dtype=torch.float32, device=dlogits.device)
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
-                       dlogits.contiguous(), flat)
+                       dlogits.contiguous(), flat, tape.group)
         self.last_grad_flat = flat
         tw = {u.conv + ".weight" for u in self._plan.units if u.transposed}
         return [E.transposed_weight_grad(self._glayout.view(flat, n)) if n in tw else self._glayout.view(flat, n)

@@ -84,6 +84,8 @@ class AideTrainer:
         self.max_graphs = max_graphs
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
         self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
+        # ... and the train forward as one more group of that stacked forward (train-mode views only, i.e. the chaos flavour)
+        self.stack_train = os.environ.get("AIDE_B200_STACK_TRAIN", "1") != "0"
         self.two_streams = two_streams
         if two_streams:
             self.s1, self.s2 = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
@@ -187,8 +189,19 @@ class AideTrainer:
             was_training = net.training
             if self.flavour != "chaos":
                 net.eval()
+            stacked_train = (self.stack_train and self.group_augs and len(augs) > 1 and net.training)
             with torch.no_grad():
-                if self.group_augs and len(augs) > 1:
+                if stacked_train:
+                    # the train forward rides as the LAST statistics group of the stacked pseudo-label forward (same
+                    # BatchNorm mode, same order of running-statistics updates as :265-269 followed by :301-302): one
+                    # launch per layer for 5 B images; the backward later runs through that group's slice of the tape
+                    views = [self._inputs(v) for v in augs] + [xs]
+                    for v in views:
+                        net._check_inputs(v)
+                    logits_all, me["tape"] = net._engine_forward(views, keep_tape=True, groups=len(views))
+                    chunks = list(logits_all.chunk(len(views), dim=0))
+                    a, me["logits"] = chunks[:-1], chunks[-1]
+                elif self.group_augs and len(augs) > 1:
                     a = net._engine_forward_grouped([self._inputs(v) for v in augs])
                 else:
                     a = [net._engine_forward(self._inputs(v), keep_tape=False)[0] for v in augs]
@@ -199,7 +212,8 @@ class AideTrainer:
                 me["q"], me["w"] = L.pseudo_label(a, self.temperature, self.flavour)
             else:
                 me["q"] = me["w"] = None
-            me["logits"], me["tape"] = net._engine_forward(xs, keep_tape=True)
+            if not stacked_train:
+                me["logits"], me["tape"] = net._engine_forward(xs, keep_tape=True)
         elif stage == 1:
             # own per-image CE+Dice against the OTHER net's targets, consistency against the OTHER net's pseudo label
             lg = me["logits"]

@@ -30,6 +30,12 @@ ap.add_argument("--sweep", action="store_true", help="time every (cout tile, pix
 ap.add_argument("--nacc", action="store_true", help="accuracy/time of the accumulator-splitting levels on long chains")
 ap.add_argument("--sweep-full", action="store_true", help="--sweep also over the stacked / plain weight planes and the row width")
 ap.add_argument("--max-cout", type=int, default=0, help="restrict the timing / sweep to layers with cout <= this")
+ap.add_argument("--model", default="fuseunet", choices=["fuseunet", "unet", "both"])
+ap.add_argument("--size", type=int, default=256)
+ap.add_argument("--skip-check", action="store_true")
+ap.add_argument("--skip-layers", action="store_true", help="skip the old-vs-halo per-layer timing")
+ap.add_argument("--dgrad", action="store_true", help="also sweep the dgrad role of every layer (cin <-> cout)")
+ap.add_argument("--batches", nargs="+", type=int, default=[], help="--sweep-full over several batch sizes (one JSON)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.backends.cudnn.allow_tf32 = False
@@ -69,7 +75,7 @@ SHAPES = [(1, 16, 8, 32, 32), (2, 16, 16, 64, 64), (1, 32, 32, 64, 64), (2, 8, 8
           (3, 24, 40, 96, 96), (1, 16, 128, 32, 64), (2, 32, 32, 256, 512), (4, 64, 64, 64, 256), (1, 16, 16, 1024, 512)]
 
 ok_mode = {}
-for mode in (0,):
+for mode in (() if args.skip_check else (0,)):
     for fmt in args.fmts:
         worst, bad = 0.0, 0
         for shp in SHAPES:
@@ -87,7 +93,7 @@ for mode in (0,):
                   f"plan {plan(fmt, shp[3], shp[4], shp[0], shp[1], shp[2])}", flush=True)
         ok_mode[(mode, fmt)] = bad == 0
         print(f"== desc_mode {mode} {NAMES[fmt]}: {'PASS' if bad == 0 else 'FAIL'} (worst rel {worst:.2e})", flush=True)
-good = [m for m in (0,) if all(ok_mode[(m, f)] for f in args.fmts)]
+good = args.skip_check or [m for m in (0,) if all(ok_mode[(m, f)] for f in args.fmts)]
 print("CHECK", "PASS" if good else "FAIL", flush=True)
 if not good or args.no_timing:
     sys.exit(0 if good else 3)
@@ -95,16 +101,19 @@ if not good or args.no_timing:
 # ---------------------------------------------------------------------------------------------- timing
 from aide_b200 import engine as E  # noqa: E402
 
-plan_net = E.plan_fuseunet(2)
 shapes = {}
-for u in plan_net.units:
-    if not u.first and (not args.max_cout or u.cout <= args.max_cout):
-        key = (u.cin, u.cout, 256 >> u.level)
-        shapes[key] = shapes.get(key, 0) + 1
+for plan_net in ([E.plan_fuseunet(2)] if args.model != "unet" else []) + ([E.plan_unet(2)] if args.model != "fuseunet" else []):
+    for u in plan_net.units:
+        if not u.first and (not args.max_cout or u.cout <= args.max_cout):
+            key = (u.cin, u.cout, args.size >> u.level)
+            shapes[key] = shapes.get(key, 0) + 1
+            if args.dgrad and u.cin % 32 == 0:
+                key = (u.cout, u.cin, args.size >> u.level)
+                shapes[key] = shapes.get(key, 0) + 1
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 B = args.batch
 result = {}
-for fmt in args.fmts:
+for fmt in ([] if args.skip_layers else args.fmts):
     tot = {0: 0.0, 1: 0.0}
     tot_flop = 0.0
     rows = []
@@ -182,7 +191,8 @@ def time_layer(fmt, cin, cout, hw, reps=3):
 
 
 if args.sweep_full:
-    for fmt in args.fmts:
+    full = {}
+    for fmt, B in [(f, b) for f in args.fmts for b in (args.batches or [args.batch])]:
         for (cin, cout, hw), count in sorted(shapes.items(), key=lambda kv: -kv[0][2]):
             flop = 2.0 * B * hw * hw * cout * cin * 9
             KEYS = ("AIDE_CONV_BN", "AIDE_CONV_MB", "AIDE_CONV_STACK", "AIDE_CONV_RB", "AIDE_CONV_WRES")
@@ -215,8 +225,16 @@ if args.sweep_full:
             res.sort(key=lambda r: r[0])
             line = "  ".join(f"BN{bn}/MB{mb}/s{stack}/r{rb}/w{pl['res']}/a{pl['nacc']}b{pl['nbuf']}A{pl['aS']}B{pl['bS']}:{flop / ms / 1e9:.0f}"
                              for ms, bn, mb, stack, rb, pl in res[:12])
-            print(f"SWEEPF {NAMES[fmt]:7s} {cin:4d}->{cout:3d} @{hw:3d} default {dflt} {flop / time_layer(fmt, cin, cout, hw) / 1e9:.0f} TF | {line}",
+            t_def = time_layer(fmt, cin, cout, hw)
+            print(f"SWEEPF {NAMES[fmt]:7s} {cin:4d}->{cout:3d} @{hw:3d} default {dflt} {flop / t_def / 1e9:.0f} TF | {line}",
                   flush=True)
+            full[f"{NAMES[fmt]}:{cin}:{cout}:{hw}:{B}"] = dict(
+                default=dflt, default_ms=round(t_def, 4), gflop=round(flop / 1e9, 2),
+                configs=[dict(ms=round(ms, 4), BN=bn, MB=mb, stack=stack, rb=rb, res=pl["res"], nacc=pl["nacc"], nbuf=pl["nbuf"],
+                              aS=pl["aS"], bS=pl["bS"]) for ms, bn, mb, stack, rb, pl in res])
+    if args.json:
+        with open(args.json.replace(".json", "_full.json"), "w") as f:
+            json.dump(full, f, indent=1)
 
 if args.sweep:
     sweep = {}
