@@ -13,7 +13,8 @@ built: there is no CPU or PyTorch fallback for the compute path.
 """
 from ._lib import AideError, FMT_BF16, FMT_F16X2, FMT_F32, FMT_TF32X2, LIB_PATH, lib  # noqa: F401
 from .engine import MODES, default_mode  # noqa: F401
-from .nets import UNet, fuseunet  # noqa: F401
+from .nets import (UNet, UNet4, UNet8, UNet16, UNet32, UNet128, UNetsa, fuseunet, fuseunetsa,  # noqa: F401
+                   fuseunetsaseparate)
 from .losses import (CEDiceLoss, CEMDiceLoss, CEMDiceLossImage, CrossEntropyLoss2d, Dice_Loss, DiceLoss,  # noqa: F401
                      Dice_fn, MulticlassDiceLoss, MulticlassMSELoss, coteach_step, predict_mask, pseudo_label)
 from .coteach_loss import (Coteachingloss_dropimage, Coteachingloss_dropimagedroppixel,  # noqa: F401

@@ -46,6 +46,16 @@ SIGNATURES = {
                                      C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     "aide_bn_relu_bwd_apply": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "aide_sa_stat_rows": (_i, [_i, _i, _i]),
+    "aide_sa_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i] + [_vp] * 13 + [_i, _i, _i, _vp]),
+    "aide_sa_gate_apply": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp,
+                                _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "aide_sa_bwd_rows": (_i, [_i, _i, _i, _i]),
+    "aide_sa_bwd_gate": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i,
+                              C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i,
+                              C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
+    "aide_sa_bwd_workspace_floats": (_sz, [_i, _i, _i, _i, _i]),
+    "aide_sa_bwd_chain": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i] + [_vp] * 12 + [_i, _i, _i, _i, _vp, _sz] + [_vp] * 10 + [_vp]),
     "aide_upsample2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_upsample2x_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_zero_insert2x_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -83,6 +83,21 @@ class Unit:
 
 
 @dataclass
+class Attention:
+    """Spatial_Attention gate (netblocks.py:68-89 / UNet.py:85-108) applied to a block's output: t = gate(y) * y.
+    `src` is the block's ungated output (its own buffer), `dst` / `pools` are where the gated tensor and its 2x2 max-pool
+    go -- the slots the plain networks let the block's second unit write directly."""
+    name: str            # parameter prefix, e.g. "modal1_sa1" / "sa1"
+    c: int
+    r: int               # c // reduction
+    level: int
+    src: Tuple[str, int]
+    dst: Optional[Tuple[str, int]]
+    pools: List[Tuple[str, int]] = field(default_factory=list)
+    dilation: int = 4
+
+
+@dataclass
 class Upsample:
     src: str
     dst: str
@@ -97,17 +112,30 @@ class Plan:
     n_inputs: int
     num_classes: int
     bufs: Dict[str, Tuple[int, int]]   # activation buffers: name -> (level, channels)
-    ops: list                          # forward order: ("input", i, buf) | Unit | Upsample | ("head", buf, cin)
+    ops: list                          # forward order: ("input", i, buf) | Unit | Attention | Upsample | ("head", buf, cin)
     units: List[Unit]
+    atts: List[Attention] = field(default_factory=list)
 
 
-def _block(ops, units, prefix, cin, cout, level, src, dst, pools, mid_buf, bufs, first=False):
-    """basic_block = two units; the first writes `mid_buf`, the second writes dst/pools."""
+def _block(ops, units, prefix, cin, cout, level, src, dst, pools, mid_buf, bufs, first=False, att=None, atts=None):
+    """basic_block = two units; the first writes `mid_buf`, the second writes dst/pools.  att = (parameter prefix,
+    reduction, dilation): the block is followed by a Spatial_Attention gate -- the second unit then writes its own
+    buffer and the gate op produces dst/pools."""
     bufs[mid_buf] = (level, cout)
     u1 = Unit(prefix + ".1", prefix + ".conv1", prefix + ".bn1", cin, cout, level, src, (mid_buf, 0), [], first)
-    u2 = Unit(prefix + ".2", prefix + ".conv2", prefix + ".bn2", cout, cout, level, (mid_buf, 0), dst, pools)
-    ops += [u1, u2]
+    if att is None:
+        u2 = Unit(prefix + ".2", prefix + ".conv2", prefix + ".bn2", cout, cout, level, (mid_buf, 0), dst, pools)
+        ops += [u1, u2]
+        units += [u1, u2]
+        return
+    name, reduction, dilation = att
+    ybuf = "say:" + name
+    bufs[ybuf] = (level, cout)
+    u2 = Unit(prefix + ".2", prefix + ".conv2", prefix + ".bn2", cout, cout, level, (mid_buf, 0), (ybuf, 0), [])
+    a = Attention(name, cout, cout // reduction, level, (ybuf, 0), dst, pools, dilation)
+    ops += [u1, u2, a]
     units += [u1, u2]
+    atts.append(a)
 
 
 def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes: int, learned_bilinear: bool = False):
@@ -132,11 +160,15 @@ def _decoder(ops, units, bufs, bottom: str, skips_c: Sequence[int], num_classes:
     ops.append(("head", x, cx))
 
 
-def plan_fuseunet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
-    """fuseunet.forward (fuseunet.py:43-91): modal-1 encoder consumes the fused concat, modal-2 is independent."""
+def plan_fuseunet(num_classes: int = 2, learned_bilinear: bool = False, attention: bool = False, separate: bool = False,
+                  reduction: int = 16, dilation: int = 4) -> Plan:
+    """fuseunet.forward (fuseunet.py:43-91): modal-1 encoder consumes the fused concat, modal-2 is independent.
+    attention: fuseunetsa (fuseunet.py:138-208) -- every encoder block is gated by its Spatial_Attention; separate:
+    fuseunetsaseparate (:255-325) -- modal-1 continues from its OWN gated output instead of the fused concat."""
     bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3), "in1": (0, 3)}
     ops: list = [("input", 0, "in0"), ("input", 1, "in1")]
     units: List[Unit] = []
+    atts: List[Attention] = []
     width = [32, 64, 128, 256, 512]
     # fused tensors y1..y4 are the upper halves of cat4..cat1; y5 is its own buffer; p{l} = maxpool(y_l)
     for lvl, c in enumerate(width):
@@ -149,23 +181,29 @@ def plan_fuseunet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
         pool_a = [] if lvl == 4 else [(f"p{lvl + 1}", 0)]
         pool_b = [] if lvl == 4 else [(f"p{lvl + 1}", c)]
         src_a = ("in0", 0) if lvl == 0 else (f"p{lvl}", 0)
-        cin_a = 3 if lvl == 0 else 2 * width[lvl - 1]
+        cin_a = 3 if lvl == 0 else (width[lvl - 1] if separate else 2 * width[lvl - 1])
         src_b = ("in1", 0) if lvl == 0 else (f"p{lvl}", width[lvl - 1])   # modal-2 = second half of the pooled concat
         cin_b = 3 if lvl == 0 else width[lvl - 1]
+        att_a = (f"modal1_sa{lvl + 1}", reduction, dilation) if attention else None
+        att_b = (f"modal2_sa{lvl + 1}", reduction, dilation) if attention else None
         _block(ops, units, f"modal1_downblock{lvl + 1}.block", cin_a, c, lvl, src_a, (fused[0], fused[1]), pool_a,
-               f"a{lvl + 1}m", bufs, first=lvl == 0)
+               f"a{lvl + 1}m", bufs, first=lvl == 0, att=att_a, atts=atts)
         _block(ops, units, f"modal2_downblock{lvl + 1}.block", cin_b, c, lvl, src_b, (fused[0], fused[1] + c), pool_b,
-               f"b{lvl + 1}m", bufs, first=lvl == 0)
+               f"b{lvl + 1}m", bufs, first=lvl == 0, att=att_b, atts=atts)
     _decoder(ops, units, bufs, "y5", [512, 256, 128, 64], num_classes, learned_bilinear)
-    return Plan("fuseunet", 2, num_classes, bufs, ops, units)
+    kind = "fuseunet" if not attention else ("fuseunetsaseparate" if separate else "fuseunetsa")
+    return Plan(kind, 2, num_classes, bufs, ops, units, atts)
 
 
-def plan_unet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
-    """UNet.forward (UNet.py:152-165); max-pool inside down blocks 2..5 (UNet.py:117-121)."""
+def plan_unet(num_classes: int = 2, learned_bilinear: bool = False, attention: bool = False, reduction: int = 16,
+              dilation: int = 4, base: int = 64) -> Plan:
+    """UNet.forward (UNet.py:152-165); max-pool inside down blocks 2..5 (UNet.py:117-121).  attention: UNetsa
+    (UNet.py:190-208), every down block gated by sa{level}."""
     bufs: Dict[str, Tuple[int, int]] = {"in0": (0, 3)}
     ops: list = [("input", 0, "in0")]
     units: List[Unit] = []
-    width = [64, 128, 256, 512, 1024]
+    atts: List[Attention] = []
+    width = [base << i for i in range(5)]          # UNet: 64..1024; UNet128 / UNet32 / ... (UNet.py:210-385): other bases
     for lvl, c in enumerate(width):
         if lvl == 4:
             bufs["x5"] = (4, c)
@@ -178,9 +216,9 @@ def plan_unet(num_classes: int = 2, learned_bilinear: bool = False) -> Plan:
         src = ("in0", 0) if lvl == 0 else (f"p{lvl}", 0)
         cin = 3 if lvl == 0 else width[lvl - 1]
         _block(ops, units, f"down_block{lvl + 1}.block", cin, c, lvl, src, dst, pools, f"d{lvl + 1}m", bufs,
-               first=lvl == 0)
-    _decoder(ops, units, bufs, "x5", [512, 256, 128, 64], num_classes, learned_bilinear)
-    return Plan("unet", 1, num_classes, bufs, ops, units)
+               first=lvl == 0, att=(f"sa{lvl + 1}", reduction, dilation) if attention else None, atts=atts)
+    _decoder(ops, units, bufs, "x5", width[3::-1], num_classes, learned_bilinear)
+    return Plan("unetsa" if attention else "unet", 1, num_classes, bufs, ops, units, atts)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -216,6 +254,13 @@ class Layout:
             cur += _align(rows * 2 * u.cout * 4)
             self.off["ss:" + u.name] = cur            # scale_shift [G][2][C] then mean_rstd [G][2][C]
             cur += _align(groups * 4 * u.cout * 4)
+        for a in plan.atts:                           # Spatial_Attention branch: fp32 intermediates (kept for backward)
+            h, w = H >> a.level, W >> a.level
+            for key, n in (("sa1:", N * h * w * a.r), ("sa2:", N * h * w * a.r), ("sa3:", N * h * w * a.r),
+                           ("saa:", N * h * w), ("sag:", N * h * w), ("sast:", lib.aide_sa_stat_rows(N, h, w) * 2),
+                           ("sass:", groups * 4)):
+                self.off[key + a.name] = cur
+                cur += _align(n * 4)
         self.total = cur
 
     def buf_fmt(self, name: str) -> int:
@@ -372,6 +417,24 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
             pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
             call("aide_bn_relu_apply_grouped", fmt, z, N, Ng, h, w, u.cout, ss, *d, *pa, *pb, st)
+        elif isinstance(op, Attention):
+            a = op
+            h, w = H >> a.level, W >> a.level
+            y = _view(layout, base, a.src[0], a.src[1])
+            P = lambda k: params[f"{a.name}.{k}"].data_ptr()
+            o = lambda k: base + layout.off[k + a.name]
+            call("aide_sa_fwd", fmt, *y, a.c, a.r, a.dilation, P("conv1.weight"), P("conv1.bias"), P("conv2.weight"),
+                 P("conv2.bias"), P("conv3.weight"), P("conv3.bias"), P("conv4.weight"), P("conv4.bias"),
+                 o("sa1:"), o("sa2:"), o("sa3:"), o("saa:"), o("sast:"), N, h, w, st)
+            rows_g = lib.aide_sa_stat_rows(N, h, w) // G
+            ss = o("sass:")
+            call("aide_bn_finalize_grouped", o("sast:"), rows_g, G, 1, float(Ng * h * w), P("bn.weight"), P("bn.bias"),
+                 P("bn.running_mean"), P("bn.running_var"), BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * 4,
+                 None, st)
+            d = _view(layout, base, a.dst[0], a.dst[1]) if a.dst else (None, None, 0, 0)
+            pa = _view(layout, base, a.pools[0][0], a.pools[0][1]) if len(a.pools) > 0 else (None, None, 0, 0)
+            pb = _view(layout, base, a.pools[1][0], a.pools[1][1]) if len(a.pools) > 1 else (None, None, 0, 0)
+            call("aide_sa_gate_apply", fmt, *y, o("saa:"), ss, N, Ng, h, w, a.c, o("sag:"), *d, *pa, *pb, st)
         elif isinstance(op, Upsample):
             h, w = H >> op.level, W >> op.level
             s = _view(layout, base, op.src, 0)
@@ -397,17 +460,20 @@ class BackwardPlan:
         for op in plan.ops:
             if isinstance(op, Unit):
                 cons[op.src[0]].append(("unit", op, op.src[1], op.cin))
+            elif isinstance(op, Attention):
+                cons[op.src[0]].append(("att", op, op.src[1], op.c))
             elif isinstance(op, Upsample):
                 cons[op.src].append(("ups", op, 0, op.c))
             elif op[0] == "head":
                 cons[op[1]].append(("head", op, 0, op[2]))
         self.sources: Dict[str, Tuple[list, list]] = {}
-        for u in plan.units:
+        for u in list(plan.units) + list(plan.atts):      # an attention gate routes gradients like a unit's output does
+            cw = u.cout if isinstance(u, Unit) else u.c
             direct, pooled = [], []
             if u.dst:
-                direct = self._covering(cons[u.dst[0]], u.dst[1], u.cout, u)
+                direct = self._covering(cons[u.dst[0]], u.dst[1], cw, u)
             for (pbuf, pco) in u.pools:
-                pooled += self._covering(cons[pbuf], pco, u.cout, u)
+                pooled += self._covering(cons[pbuf], pco, cw, u)
             if not direct and not pooled:
                 raise RuntimeError(f"unit {u.name} has no consumer")
             if len(direct) > 3 or len(pooled) > 3:
@@ -447,6 +513,16 @@ class GradLayout:
             add(u.conv + ".bias", (u.cout,))
             add(u.bn + ".bias", (u.cout,))       # dbeta  } adjacent: written as one [2][C] vector
             add(u.bn + ".weight", (u.cout,))     # dgamma }
+        for a in plan.atts:       # aide_sa_bwd_chain writes {dW, db} pairs contiguously and {dbeta, dgamma} as one pair
+            for conv, shape in (("conv1", (a.r, a.c, 1, 1)), ("conv2", (a.r, a.r, 3, 3)), ("conv3", (a.r, a.r, 3, 3)),
+                                ("conv4", (1, a.r, 1, 1))):
+                n = shape[0] * shape[1] * shape[2] * shape[3]
+                self.off[f"{a.name}.{conv}.weight"] = (cur, shape)
+                self.off[f"{a.name}.{conv}.bias"] = (cur + n, (shape[0],))
+                cur = (cur + n + shape[0] + 3) // 4 * 4
+            self.off[f"{a.name}.bn.bias"] = (cur, (1,))
+            self.off[f"{a.name}.bn.weight"] = (cur + 1, (1,))
+            cur += 4
         head = next(op for op in plan.ops if isinstance(op, tuple) and op[0] == "head")
         add("last_conv1.weight", (plan.num_classes, head[2], 1, 1))
         self.off["last_conv1.bias"] = (self.off["last_conv1.weight"][0] + plan.num_classes * head[2],
@@ -504,6 +580,17 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
         max_dz = max(max_dz, _align(N * h * w * u.cout * _esize(ufmt)) * _planes(ufmt))
         max_part = max(max_part, lib.aide_bn_bwd_rows(N, h, w, u.cout) * 2 * u.cout * 4)
         max_ws = max(max_ws, lib.aide_conv3x3_wgrad_workspace_bytes(ufmt, u.cin, u.cout, N, h, w))
+    max_sa_pix = max_sa_rows = max_sa_ws = 0
+    for a in plan.atts:
+        h, w = H >> a.level, W >> a.level
+        reserve("dy:" + a.name, N * h * w * a.c * 4)           # gradient w.r.t. the block's ungated output
+        max_sa_pix = max(max_sa_pix, N * h * w)
+        max_sa_rows = max(max_sa_rows, lib.aide_sa_bwd_rows(N, h, w, 1), lib.aide_sa_bwd_rows(N, h, w, 0))
+        max_sa_ws = max(max_sa_ws, lib.aide_sa_bwd_workspace_floats(a.c, a.r, N, h, w))
+    if plan.atts:
+        reserve("sa_dahat", max_sa_pix * 4)
+        reserve("sa_part", max_sa_rows * 2 * 4)
+        reserve("sa_ws", max_sa_ws * 4)
     for op in plan.ops:
         if isinstance(op, Upsample):
             reserve("dlo:" + op.dst, N * (H >> op.level) * (W >> op.level) * op.c * 4)
@@ -525,6 +612,8 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
     def src_ptr(kind, obj):
         if kind == "unit":
             return bb + off["dx:" + obj.name]
+        if kind == "att":
+            return bb + off["dy:" + obj.name]
         if kind == "ups":
             return bb + off["dlo:" + obj.dst]
         return bb + off["dx:head"]
@@ -542,6 +631,31 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             h, w = H >> op.level, W >> op.level
             call("aide_upsample2x_bwd" if op.mode == "bilinear" else "aide_zero_insert2x_bwd",
                  bb + off["dx:" + consumer.name], consumer.cin, 0, bb + off["dlo:" + op.dst], N, h, w, op.c, st)
+        elif isinstance(op, Attention):
+            a = op
+            h, w = H >> a.level, W >> a.level
+            direct, pooled = bplan.sources[a.name]
+            dptr = (C.c_void_p * 3)(*[src_ptr(k, o) for k, o, _, _ in direct])
+            dct = (C.c_int * 3)(*[cc for _, _, _, cc in direct])
+            dco = (C.c_int * 3)(*[co for _, _, co, _ in direct])
+            pptr = (C.c_void_p * 3)(*[src_ptr(k, o) for k, o, _, _ in pooled])
+            pct = (C.c_int * 3)(*[cc for _, _, _, cc in pooled])
+            pco = (C.c_int * 3)(*[co for _, _, co, _ in pooled])
+            y = aview(a.src[0], a.src[1])
+            npix = N * h * w
+            o = lambda k, per: base + layout.off[k + a.name] + group * npix * per * 4     # this group's slice
+            mr = base + layout.off["sass:" + a.name] + (G + group) * 2 * 4                # mean_rstd [G][2] after scale_shift
+            P = lambda k: params[f"{a.name}.{k}"].data_ptr()
+            dy, dahat, part = bb + off["dy:" + a.name], bb + off["sa_dahat"], bb + off["sa_part"]
+            call("aide_sa_bwd_gate", fmt, *y, a.c, o("sag:", 1), o("saa:", 1), mr, N, h, w, dptr, dct, dco, len(direct),
+                 pptr, pct, pco, len(pooled), dy, dahat, part, st)
+            call("aide_sa_bwd_chain", fmt, *y, a.c, a.r, a.dilation, P("conv1.weight"), P("conv2.weight"),
+                 P("conv3.weight"), P("conv4.weight"), P("bn.weight"), o("sa1:", a.r), o("sa2:", a.r), o("sa3:", a.r),
+                 o("saa:", 1), mr, dahat, part, lib.aide_sa_bwd_rows(N, h, w, 1 if pooled else 0), N, h, w,
+                 bb + off["sa_ws"], max_sa_ws, dy, gptr(f"{a.name}.conv1.weight"), gptr(f"{a.name}.conv1.bias"),
+                 gptr(f"{a.name}.conv2.weight"), gptr(f"{a.name}.conv2.bias"), gptr(f"{a.name}.conv3.weight"),
+                 gptr(f"{a.name}.conv3.bias"), gptr(f"{a.name}.conv4.weight"), gptr(f"{a.name}.conv4.bias"),
+                 gptr(f"{a.name}.bn.bias"), st)
         elif isinstance(op, Unit):
             u = op
             h, w = H >> u.level, W >> u.level

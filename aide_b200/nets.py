@@ -41,6 +41,20 @@ def UNet_up_conv_bn_relu(input_channel: int, output_channel: int, learned_biline
                          nn.ReLU())
 
 
+class Spatial_Attention(nn.Module):
+    """Parameter container of netblocks.py:68-80 / UNet.py:85-97 (same tensors, same creation order)."""
+
+    def __init__(self, input_channel: int, reduction: int = 16, dilation: int = 4):
+        super().__init__()
+        r = input_channel // reduction
+        self.conv1 = nn.Conv2d(input_channel, r, kernel_size=1, stride=1, padding=0)
+        self.conv2 = nn.Conv2d(r, r, kernel_size=3, dilation=dilation, stride=1, padding=dilation)
+        self.conv3 = nn.Conv2d(r, r, kernel_size=3, dilation=dilation, stride=1, padding=dilation)
+        self.conv4 = nn.Conv2d(r, 1, kernel_size=1, stride=1, padding=0)
+        self.bn = nn.BatchNorm2d(1)
+        self.sigmoid = nn.Sigmoid()
+
+
 class UNet_basic_down_block(nn.Module):
     def __init__(self, input_channel: int, output_channel: int, down_size: Optional[bool] = None):
         super().__init__()
@@ -189,7 +203,8 @@ class _EngineNet(nn.Module):
             self._tickets = torch.zeros(max(self._ticket_total, 1), dtype=torch.int32, device=dev)
         E.run_forward(plan, layout, named, wts, xs, training, logits, arena, groups, (self._tickets, self._ticket_off))
         if training:
-            torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units], groups)
+            torch._foreach_add_([named[u.bn + ".num_batches_tracked"] for u in plan.units]
+                                + [named[a.name + ".bn.num_batches_tracked"] for a in plan.atts], groups)
         tape = None
         if keep_tape:
             tape = E.Tape()
@@ -294,21 +309,110 @@ class fuseunet(_EngineNet):
 
 
 class UNet(_EngineNet):
-    """Classic 5-level U-Net 3->64->...->1024 (models_singlemodalinput/UNet.py:135-165)."""
+    """Classic 5-level U-Net 3->64->...->1024 (models_singlemodalinput/UNet.py:135-165).  `_base` is the width of the
+    first level: the reference's UNet128 / UNet32 / UNet16 / UNet8 / UNet4 (UNet.py:210-368) are the same network at
+    other widths (subclasses below)."""
+    _base = 64
 
     def __init__(self, num_classes=2, learned_bilinear=False, mode: Optional[str] = None):
         super().__init__()
-        self.down_block1 = UNet_basic_down_block(3, 64, False)
-        self.down_block2 = UNet_basic_down_block(64, 128, True)
-        self.down_block3 = UNet_basic_down_block(128, 256, True)
-        self.down_block4 = UNet_basic_down_block(256, 512, True)
-        self.down_block5 = UNet_basic_down_block(512, 1024, True)
+        b = self._base
+        self.down_block1 = UNet_basic_down_block(3, b, False)
+        self.down_block2 = UNet_basic_down_block(b, 2 * b, True)
+        self.down_block3 = UNet_basic_down_block(2 * b, 4 * b, True)
+        self.down_block4 = UNet_basic_down_block(4 * b, 8 * b, True)
+        self.down_block5 = UNet_basic_down_block(8 * b, 16 * b, True)
+        self.up_block1 = UNet_basic_up_block(16 * b, 8 * b, 8 * b, learned_bilinear)
+        self.up_block2 = UNet_basic_up_block(8 * b, 4 * b, 4 * b, learned_bilinear)
+        self.up_block3 = UNet_basic_up_block(4 * b, 2 * b, 2 * b, learned_bilinear)
+        self.up_block4 = UNet_basic_up_block(2 * b, b, b, learned_bilinear)
+        self.last_conv1 = nn.Conv2d(b, num_classes, 1, padding=0)
+        if b % 32 and b % 4 == 0:
+            # channel counts below the tcgen05 tile granularity (32): every layer runs on the fp32 CUDA-core kernels
+            mode = "exact"
+        elif b % 4:
+            raise NotImplementedError(f"UNet{b}: the NHWC kernels move 4 channels per access; widths below 4 are not built")
+        self._engine_setup(E.plan_unet(num_classes, learned_bilinear, base=b), mode)
+
+    def forward(self, x):
+        return self._run(x)
+
+
+class UNet128(UNet):
+    _base = 128
+
+
+class UNet32(UNet):
+    _base = 32
+
+
+class UNet16(UNet):
+    _base = 16
+
+
+class UNet8(UNet):
+    _base = 8
+
+
+class UNet4(UNet):
+    _base = 4
+
+
+class UNet2(UNet):
+    _base = 2
+
+
+class _fuseunetsa_base(_EngineNet):
+    def __init__(self, num_classes, reduction, dilation, learned_bilinear, mode, separate):
+        super().__init__()
+        enc = [(3, 3, 32), (64, 32, 64), (128, 64, 128), (256, 128, 256), (512, 256, 512)]
+        for m in (1, 2):
+            for i, (c1, c2, co) in enumerate(enc, 1):
+                cin = c2 if (m == 2 or separate) else c1
+                setattr(self, f"modal{m}_downblock{i}", UNet_basic_down_block(cin, co))
+                setattr(self, f"modal{m}_sa{i}", Spatial_Attention(co, reduction=reduction, dilation=dilation))
+                if i < 5:
+                    setattr(self, f"modal{m}_maxpool{i}", nn.MaxPool2d(kernel_size=2, stride=2))
         self.up_block1 = UNet_basic_up_block(1024, 512, 512, learned_bilinear)
         self.up_block2 = UNet_basic_up_block(512, 256, 256, learned_bilinear)
         self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
         self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
         self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
-        self._engine_setup(E.plan_unet(num_classes, learned_bilinear), mode)
+        self._engine_setup(E.plan_fuseunet(num_classes, learned_bilinear, attention=True, separate=separate,
+                                           reduction=reduction, dilation=dilation), mode)
+
+    def forward(self, modal1_inputs, modal2_inputs):
+        return self._run(modal1_inputs, modal2_inputs)
+
+
+class fuseunetsa(_fuseunetsa_base):
+    """fuseunet with a Spatial_Attention gate after every encoder block (models_twomodalinputs/fuseunet.py:93-208)."""
+
+    def __init__(self, num_classes=2, reduction=16, dilation=4, learned_bilinear=False, mode: Optional[str] = None):
+        super().__init__(num_classes, reduction, dilation, learned_bilinear, mode, separate=False)
+
+
+class fuseunetsaseparate(_fuseunetsa_base):
+    """Two fully separate gated encoders, fused only in the decoder's skips (fuseunet.py:210-325)."""
+
+    def __init__(self, num_classes=2, reduction=16, dilation=4, learned_bilinear=False, mode: Optional[str] = None):
+        super().__init__(num_classes, reduction, dilation, learned_bilinear, mode, separate=True)
+
+
+class UNetsa(_EngineNet):
+    """UNet with a Spatial_Attention gate after every down block (models_singlemodalinput/UNet.py:168-208)."""
+
+    def __init__(self, num_classes=2, learned_bilinear=False, mode: Optional[str] = None):
+        super().__init__()
+        for i, (ci, co) in enumerate([(3, 64), (64, 128), (128, 256), (256, 512), (512, 1024)], 1):
+            setattr(self, f"down_block{i}", UNet_basic_down_block(ci, co, i > 1))
+            setattr(self, f"sa{i}", Spatial_Attention(co, reduction=16, dilation=4))
+        self.up_block1 = UNet_basic_up_block(1024, 512, 512, learned_bilinear)
+        self.up_block2 = UNet_basic_up_block(512, 256, 256, learned_bilinear)
+        self.up_block3 = UNet_basic_up_block(256, 128, 128, learned_bilinear)
+        self.up_block4 = UNet_basic_up_block(128, 64, 64, learned_bilinear)
+        self.last_conv1 = nn.Conv2d(64, num_classes, 1, padding=0)
+        self._engine_setup(E.plan_unet(num_classes, learned_bilinear, attention=True), mode)
 
     def forward(self, x):
         return self._run(x)

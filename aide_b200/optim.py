@@ -9,7 +9,7 @@ change therefore also reaches a captured CUDA graph of the training step.
 """
 from __future__ import annotations
 
-from typing import Iterable, List
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 from torch.optim.lr_scheduler import _LRScheduler
@@ -23,7 +23,10 @@ class FlatAdamAMSGrad(torch.optim.Optimizer):
     flat buffers of the same size.  ``step(grad_flat)`` consumes a flat gradient laid out in the same
     parameter order (see flatten_grads) -- or the per-parameter ``.grad`` fields when called without."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 offsets: Optional[Sequence[int]] = None, total: Optional[int] = None):
+        """offsets / total (in floats): an explicit layout of the flat buffer (engine.GradLayout packs some small
+        tensors without padding); default: consecutive tensors, each padded to a multiple of 4 floats."""
         plist: List[torch.nn.Parameter] = [p for p in params]
         super().__init__(plist, dict(lr=lr, betas=betas, eps=eps))
         if len(self.param_groups) != 1:
@@ -34,6 +37,10 @@ class FlatAdamAMSGrad(torch.optim.Optimizer):
         for p in self.params:
             self.offsets.append(cur)
             cur += (p.numel() + 3) // 4 * 4
+        if offsets is not None:
+            self.offsets, cur = [int(o) for o in offsets], int(total)
+            if len(self.offsets) != len(self.params):
+                raise ValueError("one offset per parameter")
         dev = self.params[0].device
         self.flat = torch.zeros(cur, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):

@@ -29,7 +29,7 @@ from . import augment as AUG
 from . import engine as E
 from . import losses as L
 from ._lib import call, lib
-from .nets import UNet, fuseunet
+from .nets import UNet, UNetsa, fuseunet, fuseunetsa, fuseunetsaseparate
 from .optim import FlatAdamAMSGrad
 
 
@@ -38,6 +38,18 @@ def grad_order_params(net) -> List[torch.nn.Parameter]:
     named = dict(net.named_parameters())
     order = sorted(net._glayout.off.items(), key=lambda kv: kv[1][0])
     return [named[name] for name, _ in order]
+
+
+def flat_adam_for(net, lr: float) -> FlatAdamAMSGrad:
+    """Adam-amsgrad whose flat parameter buffer has exactly the layout of the net's flat gradient buffer."""
+    order = sorted(net._glayout.off.items(), key=lambda kv: kv[1][0])
+    named = dict(net.named_parameters())
+    return FlatAdamAMSGrad([named[name] for name, _ in order], lr=lr, offsets=[o for _, (o, _) in order],
+                           total=net._glayout.total)
+
+
+NET_KINDS = {"fuseunet": fuseunet, "unet": UNet, "fuseunetsa": fuseunetsa, "fuseunetsaseparate": fuseunetsaseparate,
+             "unetsa": UNetsa}
 
 
 class AideTrainer:
@@ -55,14 +67,16 @@ class AideTrainer:
         self.kind, self.flavour, self.temperature = kind, flavour, temperature
         self.n_clean, self.segcor_weight = n_clean, segcor_weight
         torch.manual_seed(seed)                      # net1 then net2: independent inits, as in :175-176
-        ctor = fuseunet if kind == "fuseunet" else UNet
+        if kind not in NET_KINDS:
+            raise ValueError(f"kind must be one of {sorted(NET_KINDS)}")          # cf. 'Model not implemented', :78
+        ctor = NET_KINDS[kind]
         self.net1 = ctor(num_classes=2, mode=mode).to(self.device).train()
         self.net2 = ctor(num_classes=2, mode=mode).to(self.device).train()
         if any(u.transposed for u in self.net1._plan.units):
             raise NotImplementedError("AideTrainer keeps parameters in the flat gradient layout; ConvTranspose2d decoders "
                                       "(learned_bilinear=True) run through the nn.Module / torch.optim path")
-        self.opt1 = FlatAdamAMSGrad(grad_order_params(self.net1), lr=lr)
-        self.opt2 = FlatAdamAMSGrad(grad_order_params(self.net2), lr=lr)
+        self.opt1 = flat_adam_for(self.net1, lr)
+        self.opt2 = flat_adam_for(self.net2, lr)
         for net, opt in ((self.net1, self.opt1), (self.net2, self.opt2)):
             if opt.flat.numel() != net._glayout.total:
                 raise RuntimeError("flat parameter buffer and flat gradient layout disagree")

@@ -181,6 +181,45 @@ int aide_conv1x1_bwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
                      float* dx /*[N,H,W,C] fp32*/, float* dw_db /*[K*C] dW then [K] dbias*/,
                      float* partial /*[rows][K*C+K]*/, void* stream);
 
+/* ---- Spatial_Attention gate of the attention variants (netblocks.py:68-89, UNet.py:85-108) ------------------------ */
+/* fuseunetsa / fuseunetsaseparate (fuseunet.py:93-208, :210-325) and UNetsa (UNet.py:168-208) multiply every encoder
+ * block's output y [N,C,H,W] by gate = sigmoid(BatchNorm2d(1)(conv4(conv3(conv2(conv1(y)))))) with conv1 1x1 C -> r = C/16,
+ * conv2 / conv3 3x3 r -> r (dilation d, padding d), conv4 1x1 r -> 1 (weights in nn.Conv2d OIHW layout, fp32).
+ * aide_sa_fwd: a1, a2, a3 [N,H,W,r] and a [N,H,W] (conv4 output, before BatchNorm) in fp32 + per-block partial
+ *   statistics (sum a, sum a^2): stat_partial [aide_sa_stat_rows(N,H,W)][2] (image-major rows).  Finalise them with
+ *   aide_bn_finalize_grouped(C = 1) -> scale_shift [groups][2], mean_rstd [groups][2].
+ * aide_sa_gate_apply: gate [N,H,W] = sigmoid(scale * a + shift); writes gate * y into the consumer's channel slice
+ *   (dst view) and its 2x2 max-pool into up to two half-resolution views (the fused-encoder concat / next level). */
+int aide_sa_stat_rows(int N, int H, int W);
+int aide_sa_fwd(int fmt, const void* y_p0, const void* y_p1, int y_ctot, int y_coff, int C, int r, int dilation,
+                const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                const float* w4, const float* b4, float* a1, float* a2, float* a3, float* a, float* stat_partial,
+                int N, int H, int W, void* stream);
+int aide_sa_gate_apply(int fmt, const void* y_p0, const void* y_p1, int y_ctot, int y_coff, const float* a,
+                       const float* scale_shift, int N, int imgs_per_group, int H, int W, int C, float* gate,
+                       void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                       void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                       void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream);
+/* Backward of t = gate * y.  Stage 1 (aide_sa_bwd_gate): dt = sum of the upstream gradients w.r.t. t (same-resolution
+ * slices and slices routed through the 2x2 max-pool of t, first maximum wins); dy [N,H,W,C] fp32 = dt * gate;
+ * dahat [N,H,W] = (sum_c dt*y) * gate * (1 - gate); partial [aide_sa_bwd_rows()][2] = block sums of (dahat, dahat*ahat).
+ * Stage 2 (aide_sa_bwd_chain): BatchNorm2d(1) backward (train mode), conv4..conv1 backward: adds W1^T da1 into dy and
+ * writes the parameter gradients (each bias gradient directly after its weight gradient; dbn = {dbeta, dgamma}). */
+int aide_sa_bwd_rows(int N, int H, int W, int pooled);
+int aide_sa_bwd_gate(int fmt, const void* y_p0, const void* y_p1, int y_ctot, int y_coff, int C, const float* gate,
+                     const float* a, const float* mean_rstd, int N, int H, int W,
+                     const float* const* direct_ptr, const int* direct_ctot, const int* direct_coff, int n_direct,
+                     const float* const* pool_ptr, const int* pool_ctot, const int* pool_coff, int n_pool,
+                     float* dy, float* dahat, float* partial, void* stream);
+size_t aide_sa_bwd_workspace_floats(int C, int r, int N, int H, int W);
+int aide_sa_bwd_chain(int fmt, const void* y_p0, const void* y_p1, int y_ctot, int y_coff, int C, int r, int dilation,
+                      const float* w1, const float* w2, const float* w3, const float* w4, const float* gamma,
+                      const float* a1, const float* a2, const float* a3, const float* a, const float* mean_rstd,
+                      const float* dahat, const float* partial, int partial_rows, int N, int H, int W,
+                      float* workspace, size_t workspace_floats, float* dy,
+                      float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, float* dw4, float* db4,
+                      float* dbn, void* stream);
+
 /* ---- losses (utils/loss2d.py, utils/metrics2d.py, train_files/trainchaos_proposed_*.py) --------- */
 /* One pass over logits [N,2,H,W] (NCHW fp32) + targets [N,H,W] int64 producing per image, in fp64:
  *   sums[n][0]=sum ce*wc[t]  [1]=sum wc[t] (non-ignored)  [2]=sum s*t  [3]=sum s  [4]=sum t

@@ -11,6 +11,9 @@ dictionaries, no nn.Module graph) of the reference algorithm:
 * ``fuseunet_forward``      <- models_twomodalinputs/fuseunet.py:43-91,
                                models_twomodalinputs/netblocks.py:9-33,128-147
 * ``unet_forward``          <- models_singlemodalinput/UNet.py:4-28,110-165
+* ``fuseunetsa_forward`` / ``fuseunetsaseparate_forward`` / ``unetsa_forward`` (attention variants)
+                            <- models_twomodalinputs/fuseunet.py:93-208,210-325, netblocks.py:68-89,
+                               models_singlemodalinput/UNet.py:85-108,168-208
 * ``ce_dice_per_image`` ... <- utils/loss2d.py:5-13,35-61,87-154
 * ``dice_fn``               <- utils/metrics2d.py:8-29
 * ``pseudo_label``          <- train_files/trainchaos_proposed_30cases1labeled.py:274-292,97-101
@@ -119,6 +122,46 @@ def init_unet(num_classes: int = 2, learned_bilinear: bool = False) -> Params:
     return p
 
 
+def _add_spatial_attention(p: Params, name: str, c: int, reduction: int = 16) -> None:
+    """Spatial_Attention.__init__ (netblocks.py:69-79): conv1 1x1 C->r, conv2 / conv3 3x3 r->r (dilated), conv4 1x1 r->1,
+    BatchNorm2d(1) -- tensors created in this order."""
+    r = c // reduction
+    _add_conv(p, name + ".conv1", c, r, k=1)
+    _add_conv(p, name + ".conv2", r, r, k=3)
+    _add_conv(p, name + ".conv3", r, r, k=3)
+    _add_conv(p, name + ".conv4", r, 1, k=1)
+    _add_bn(p, name + ".bn", 1)
+
+
+def init_fuseunetsa(num_classes: int = 2, separate: bool = False, reduction: int = 16,
+                    learned_bilinear: bool = False) -> Params:
+    """Same state_dict as fuseunetsa() (fuseunet.py:94-136) / fuseunetsaseparate() (:211-253): every encoder block is
+    followed by its Spatial_Attention; the `separate` variant's modal-1 encoder takes its own previous level
+    (32 -> 64 -> ...) instead of the fused concat."""
+    p: Params = {}
+    for m in (1, 2):
+        for lvl, (c1, c2, co) in enumerate(FUSE_ENC, 1):
+            cin = c2 if (m == 2 or separate) else c1
+            _add_basic_block(p, f"modal{m}_downblock{lvl}.block", cin, co)
+            _add_spatial_attention(p, f"modal{m}_sa{lvl}", co, reduction)
+    for i, (ci, cp, co) in enumerate(DECODER, 1):
+        _add_up_block(p, f"up_block{i}", ci, cp, co, learned_bilinear)
+    _add_conv(p, "last_conv1", 64, num_classes, k=1)
+    return p
+
+
+def init_unetsa(num_classes: int = 2, learned_bilinear: bool = False) -> Params:
+    """Same state_dict as UNetsa() (UNet.py:169-188)."""
+    p: Params = {}
+    for lvl, (ci, co) in enumerate(UNET_ENC, 1):
+        _add_basic_block(p, f"down_block{lvl}.block", ci, co)
+        _add_spatial_attention(p, f"sa{lvl}", co)
+    for i, (ci, cp, co) in enumerate(DECODER, 1):
+        _add_up_block(p, f"up_block{i}", ci, cp, co, learned_bilinear)
+    _add_conv(p, "last_conv1", 64, num_classes, k=1)
+    return p
+
+
 def is_buffer(name: str) -> bool:
     return name.endswith(("running_mean", "running_var", "num_batches_tracked"))
 
@@ -185,6 +228,53 @@ def fuseunet_forward(p: Params, modal1: torch.Tensor, modal2: torch.Tensor,
         x = _basic_block(p, f"modal2_downblock{lvl}.block", F.max_pool2d(x, 2, 2), training)
         fused.append(torch.cat((y, x), dim=1))
     return _decoder(p, fused[:4], fused[4], training)
+
+
+def _spatial_attention(p: Params, name: str, x: torch.Tensor, training: bool, dilation: int = 4) -> torch.Tensor:
+    """Spatial_Attention.forward (netblocks.py:82-89) -> gate [N,1,H,W]."""
+    y = F.conv2d(x, p[name + ".conv1.weight"], p[name + ".conv1.bias"])
+    y = F.conv2d(y, p[name + ".conv2.weight"], p[name + ".conv2.bias"], padding=dilation, dilation=dilation)
+    y = F.conv2d(y, p[name + ".conv3.weight"], p[name + ".conv3.bias"], padding=dilation, dilation=dilation)
+    y = F.conv2d(y, p[name + ".conv4.weight"], p[name + ".conv4.bias"])
+    if training:
+        p[name + ".bn.num_batches_tracked"] += 1
+    y = F.batch_norm(y, p[name + ".bn.running_mean"], p[name + ".bn.running_var"], p[name + ".bn.weight"],
+                     p[name + ".bn.bias"], training, BN_MOMENTUM, BN_EPS)
+    return torch.sigmoid(y)
+
+
+def fuseunetsa_forward(p: Params, modal1: torch.Tensor, modal2: torch.Tensor, training: bool = True,
+                       separate: bool = False) -> torch.Tensor:
+    """fuseunetsa.forward (fuseunet.py:138-208); separate=True: fuseunetsaseparate.forward (:255-325), whose modal-1
+    encoder max-pools its OWN gated output instead of the fused concat."""
+    fused = []
+    y, x = modal1, modal2
+    for lvl in range(1, 6):
+        if lvl > 1:
+            y = F.max_pool2d(y if separate else fused[-1], 2, 2)
+            x = F.max_pool2d(x, 2, 2)
+        y = _basic_block(p, f"modal1_downblock{lvl}.block", y, training)
+        y = _spatial_attention(p, f"modal1_sa{lvl}", y, training) * y
+        x = _basic_block(p, f"modal2_downblock{lvl}.block", x, training)
+        x = _spatial_attention(p, f"modal2_sa{lvl}", x, training) * x
+        fused.append(torch.cat((y, x), dim=1))
+    return _decoder(p, fused[:4], fused[4], training)
+
+
+def fuseunetsaseparate_forward(p: Params, modal1: torch.Tensor, modal2: torch.Tensor, training: bool = True) -> torch.Tensor:
+    return fuseunetsa_forward(p, modal1, modal2, training, separate=True)
+
+
+def unetsa_forward(p: Params, x: torch.Tensor, training: bool = True) -> torch.Tensor:
+    """UNetsa.forward (UNet.py:190-208)."""
+    feats: List[torch.Tensor] = []
+    for lvl in range(1, 6):
+        if lvl > 1:
+            x = F.max_pool2d(x, 2, 2)
+        x = _basic_block(p, f"down_block{lvl}.block", x, training)
+        x = _spatial_attention(p, f"sa{lvl}", x, training) * x
+        feats.append(x)
+    return _decoder(p, feats[:4], feats[4], training)
 
 
 def unet_forward(p: Params, x: torch.Tensor, training: bool = True) -> torch.Tensor:

@@ -338,8 +338,64 @@ def main_learned_bilinear():
           % (os.path.getsize(os.path.join(HERE, "golden_lb.pt")) / 1024))
 
 
+def main_attention():
+    """Attention variants (fuseunetsa, fuseunetsaseparate, UNetsa: fuseunet.py:93-325, UNet.py:168-208, Spatial_Attention
+    netblocks.py:68-89): the oracle against the unmodified reference, frozen into golden_sa.pt.
+    python tests/golden/make_golden.py sa"""
+    from models_twomodalinputs import fuseunetsa as RefSA, fuseunetsaseparate as RefSAS
+    from models_singlemodalinput import UNetsa as RefUSA
+    out = {}
+    torch.set_num_threads(8)
+    crit_mean = refutils.CEMDiceLoss(cediceweight=[1.0, 1.0], ceclassweight=torch.tensor([1.0, 1.0]),
+                                     diceclassweight=[1.0, 1.0])
+    cases = (("fuseunetsa", RefSA, lambda: O.init_fuseunetsa(2), O.fuseunetsa_forward, 2),
+             ("fuseunetsaseparate", RefSAS, lambda: O.init_fuseunetsa(2, True), O.fuseunetsaseparate_forward, 2),
+             ("unetsa", RefUSA, lambda: O.init_unetsa(2), O.unetsa_forward, 1))
+    for kind, Ref, init, fwd, n_in in cases:
+        torch.manual_seed(2)
+        ref = Ref(num_classes=2)
+        torch.manual_seed(2)
+        check_state(ref, init(), kind)
+        out[kind + "_keys"] = list(ref.state_dict().keys())
+        for tag, (b, h, w) in {"s32": (2, 32, 32), "s48x64": (3, 48, 64)}.items():
+            (x1, x2), t1, t2, _ = O.synthetic_batch(b, h, w, seed=1234)
+            xs = (x1, x2)[:n_in]
+            torch.manual_seed(2)
+            net = Ref(num_classes=2)
+            p = O.clone_params(dict(net.state_dict()), requires_grad=True)
+            net.train()
+            y_ref = net(*xs)
+            y_or = fwd(p, *xs, training=True)
+            same(y_ref, y_or, f"{tag} {kind} logits")
+            check_state(net, {k: v.detach() for k, v in p.items()}, f"{tag} {kind} post-fwd buffers")
+            l_ref = crit_mean(y_ref, t2)
+            same(l_ref, O.ce_dice_mean(y_or, t2), f"{tag} {kind} CEMDiceLoss")
+            names = [k for k, _ in net.named_parameters()]
+            g_ref = grads_of(l_ref, [q for _, q in net.named_parameters()])
+            g_or = grads_of(O.ce_dice_mean(y_or, t2), [p[k] for k in names])
+            for k, a, c in zip(names, g_ref, g_or):
+                same(a, c, f"{tag} {kind} grad {k}")
+            net.eval()
+            with torch.no_grad():
+                ye = net(*xs)
+                same(ye, fwd({k: v.detach() for k, v in p.items()}, *xs, training=False), f"{tag} {kind} eval logits")
+            sa = [k for k in names if "sa" in k.split(".")[0]]
+            out.setdefault(tag, {})[kind] = dict(
+                logits=y_ref.detach().clone(), loss_mean=l_ref.item(), logits_eval=ye.clone(),
+                grad_last_w=g_ref[names.index("last_conv1.weight")].clone(),
+                grad_sa={k: g_ref[names.index(k)].clone() for k in sa if g_ref[names.index(k)].numel() <= 4096},
+                grad_absmax={k: g.abs().max().item() for k, g in zip(names, g_ref)},
+                sa_bn_rm={k: v.clone() for k, v in net.state_dict().items() if k.endswith("bn.running_mean")},
+                sa_bn_rv={k: v.clone() for k, v in net.state_dict().items() if k.endswith("bn.running_var")})
+    torch.save(out, os.path.join(HERE, "golden_sa.pt"))
+    print("oracle == reference (attention variants) on every check; wrote golden_sa.pt (%.1f KB)"
+          % (os.path.getsize(os.path.join(HERE, "golden_sa.pt")) / 1024))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "lb":
+    if len(sys.argv) > 1 and sys.argv[1] == "sa":
+        main_attention()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lb":
         main_learned_bilinear()
     else:
         main()

@@ -427,3 +427,85 @@ def test_predict_mask_equals_reference_argmax(dev, golden):
         ref = torch.argmax(F.softmax(t, dim=1), dim=1).to(torch.uint8)
         got = A.predict_mask(t.to(dev))
         assert got.dtype == torch.uint8 and torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("fmt", [0, 3])
+@pytest.mark.parametrize("C,pooled", [(32, True), (64, False), (256, True)])
+def test_spatial_attention_gate_forward_backward(dev, fmt, C, pooled):
+    """Spatial_Attention (netblocks.py:68-89) + the gating product t = gate * y as the engine runs it: forward
+    (aide_sa_fwd, aide_bn_finalize, aide_sa_gate_apply incl. the 2x2 max-pool of t) and backward (aide_sa_bwd_gate,
+    aide_sa_bwd_chain) against torch autograd on the CPU, one same-resolution and one max-pool routed upstream gradient."""
+    import ctypes as Ct
+    from aide_b200 import ops
+    from aide_b200._lib import call, lib
+    N, H, W, r, dil = 2, 16, 24, C // 16, 4
+    g = torch.Generator().manual_seed(C)
+    y = torch.randn(N, C, H, W, generator=g).relu()
+    if fmt == 3:
+        y = ops.to_nchw(ops.from_nchw(y.to(dev), 3)).cpu()          # the value the operand planes actually hold
+    y.requires_grad_()
+    mk = lambda *s_, sc=0.3: (torch.randn(*s_, generator=g) * sc).requires_grad_()
+    w1, b1, w2, b2 = mk(r, C, 1, 1), mk(r), mk(r, r, 3, 3), mk(r)
+    w3, b3, w4, b4 = mk(r, r, 3, 3), mk(r), mk(1, r, 1, 1), mk(1)
+    gamma, beta = (torch.rand(1, generator=g) + 0.5).requires_grad_(), mk(1)
+    rm, rv = torch.zeros(1), torch.ones(1)
+    a = F.conv2d(y, w1, b1)
+    a = F.conv2d(a, w2, b2, padding=dil, dilation=dil)
+    a = F.conv2d(a, w3, b3, padding=dil, dilation=dil)
+    a = F.conv2d(a, w4, b4)
+    gate = torch.sigmoid(F.batch_norm(a, rm, rv, gamma, beta, True, 0.1, 1e-5))
+    t = gate * y
+    gd = torch.randn(N, C, H, W, generator=g)
+    gp = torch.randn(N, C, H // 2, W // 2, generator=g)
+    loss = (t * gd).sum() + ((F.max_pool2d(t, 2, 2) * gp).sum() if pooled else 0.0)
+    leaves = [y, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta]
+    ref = torch.autograd.grad(loss, leaves)
+    # ---- engine
+    st = torch.cuda.current_stream().cuda_stream
+    D = lambda x: x.detach().to(dev).contiguous()
+    ya = ops.from_nchw(D(y), fmt)
+    dW = [D(x) for x in (w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta)]
+    f32 = lambda *s_: torch.empty(*s_, dtype=torch.float32, device=dev)
+    a1, a2, a3, aa, gt = f32(N, H, W, r), f32(N, H, W, r), f32(N, H, W, r), f32(N, H, W), f32(N, H, W)
+    rows = lib.aide_sa_stat_rows(N, H, W)
+    stat = f32(rows, 2)
+    call("aide_sa_fwd", fmt, *ya.view(), C, r, dil, *[x.data_ptr() for x in dW[:8]], a1.data_ptr(), a2.data_ptr(),
+         a3.data_ptr(), aa.data_ptr(), stat.data_ptr(), N, H, W, st)
+    drm, drv = torch.zeros(1, device=dev), torch.ones(1, device=dev)
+    ss, mr = ops.bn_finalize(stat.view(rows, 2, 1), N * H * W, dW[8], dW[9], drm, drv, True)
+    out = ops.Act(N, H, W, C, fmt, dev)
+    pl = ops.Act(N, H // 2, W // 2, C, fmt, dev)
+    none = (None, None, 0, 0)
+    call("aide_sa_gate_apply", fmt, *ya.view(), aa.data_ptr(), ss.data_ptr(), N, N, H, W, C, gt.data_ptr(), *out.view(),
+         *(pl.view() if pooled else none), *none, st)
+    tol = 2e-5 if fmt == 0 else 3e-5
+    assert relmax(ops.to_nchw(out), t.detach()) < tol
+    assert relmax(gt, gate.detach()[:, 0]) < 1e-5
+    assert relmax(drm, rm) < 1e-5 and relmax(drv, rv) < 1e-5            # F.batch_norm updated rm / rv in place
+    if pooled:
+        assert relmax(ops.to_nchw(pl), F.max_pool2d(t.detach(), 2, 2)) < tol
+    nhwc = lambda x: x.permute(0, 2, 3, 1).contiguous().to(dev)
+    d0, p0 = nhwc(gd), nhwc(gp)
+    dptr, dct, dco = (Ct.c_void_p * 3)(d0.data_ptr()), (Ct.c_int * 3)(C), (Ct.c_int * 3)(0)
+    pptr, pct, pco = (Ct.c_void_p * 3)(p0.data_ptr()), (Ct.c_int * 3)(C), (Ct.c_int * 3)(0)
+    dy, dah = f32(N, H, W, C), f32(N, H, W)
+    prow = lib.aide_sa_bwd_rows(N, H, W, 1 if pooled else 0)
+    part = f32(prow, 2)
+    call("aide_sa_bwd_gate", fmt, *ya.view(), C, gt.data_ptr(), aa.data_ptr(), mr.data_ptr(), N, H, W, dptr, dct, dco, 1,
+         pptr, pct, pco, 1 if pooled else 0, dy.data_ptr(), dah.data_ptr(), part.data_ptr(), st)
+    nws = lib.aide_sa_bwd_workspace_floats(C, r, N, H, W)
+    ws = f32(nws)
+    gsz = [r * C, r, r * r * 9, r, r * r * 9, r, r, 1, 2]
+    gbuf = f32(sum(gsz))
+    offs = [sum(gsz[:i]) for i in range(len(gsz))]
+    gp_ = [gbuf.data_ptr() + 4 * o for o in offs]
+    call("aide_sa_bwd_chain", fmt, *ya.view(), C, r, dil, dW[0].data_ptr(), dW[2].data_ptr(), dW[4].data_ptr(),
+         dW[6].data_ptr(), dW[8].data_ptr(), a1.data_ptr(), a2.data_ptr(), a3.data_ptr(), aa.data_ptr(), mr.data_ptr(),
+         dah.data_ptr(), part.data_ptr(), prow, N, H, W, ws.data_ptr(), nws, dy.data_ptr(), *gp_, st)
+    torch.cuda.synchronize()
+    got = [gbuf[o:o + n] for o, n in zip(offs, gsz)]
+    gtol = 2e-4
+    assert relmax(ops.nhwc_to_nchw(dy), ref[0]) < gtol, "dy"
+    for name, gg, rr in zip(("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4"), got[:8], ref[1:9]):
+        assert relmax(gg, rr.flatten()) < gtol, name
+    assert relmax(got[8][1:2], ref[9]) < gtol and relmax(got[8][0:1], ref[10]) < gtol      # {dbeta, dgamma}

@@ -436,3 +436,81 @@ def test_graphed_eval_forward_equals_eager_and_is_faster(oracle):
     print(f"single-slice eval forward 256x256: graph {t_graph * 1e3:.2f} ms ({1 / t_graph:.0f} slices/s), "
           f"eager {t_eager * 1e3:.2f} ms")
     assert t_graph < t_eager
+
+
+@pytest.mark.parametrize("mode", ["exact", "parity"])
+@pytest.mark.parametrize("kind", ["fuseunetsa", "fuseunetsaseparate", "unetsa"])
+def test_attention_variants_vs_reference_vectors(oracle, kind, mode):
+    """fuseunetsa / fuseunetsaseparate / UNetsa (fuseunet.py:93-325, UNet.py:168-208): every encoder block gated by its
+    Spatial_Attention (netblocks.py:68-89).  Forward vs vectors frozen from the unmodified reference (golden_sa.pt),
+    gradients vs the reference values (attention parameters, shortest path) and the live oracle (direction of the whole
+    gradient), reference state_dict layout, eval mode on the running statistics."""
+    import aide_b200
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_sa.pt"), weights_only=False)
+    b, h, w = 3, 48, 64
+    (x1, x2), t1, t2, _ = oracle.synthetic_batch(b, h, w, seed=1234)
+    ctor, init, fwd, xs = {
+        "fuseunetsa": (aide_b200.fuseunetsa, lambda: oracle.init_fuseunetsa(2), oracle.fuseunetsa_forward, (x1, x2)),
+        "fuseunetsaseparate": (aide_b200.fuseunetsaseparate, lambda: oracle.init_fuseunetsa(2, True),
+                               oracle.fuseunetsaseparate_forward, (x1, x2)),
+        "unetsa": (aide_b200.UNetsa, lambda: oracle.init_unetsa(2), oracle.unetsa_forward, (x1,))}[kind]
+    torch.manual_seed(2)
+    net = ctor(num_classes=2, mode=mode).to(dev)
+    assert list(net.state_dict().keys()) == g[kind + "_keys"]
+    net.train()
+    y = net(*[x.to(dev) for x in xs])
+    c = g["s48x64"][kind]
+    e_logit = relmax(y, c["logits"])
+    assert e_logit < LOGIT_TOL[mode], e_logit
+    loss = aide_b200.CEMDiceLoss([1., 1.], [1., 1.], [1., 1.])(y, t2.to(dev))
+    assert abs(loss.item() - c["loss_mean"]) < 2e-5
+    loss.backward()
+    eng = {k: v.grad for k, v in net.named_parameters()}
+    assert relmax(eng["last_conv1.weight"], c["grad_last_w"]) < 2e-3
+    # live oracle: whole-gradient direction, and the attention branch's own parameters
+    torch.manual_seed(2)
+    p = oracle.clone_params(init(), requires_grad=True)
+    yo = fwd(p, *xs, training=True)
+    names = [k for k in p if not oracle.is_buffer(k) and not is_prebn_bias(k)]
+    go = dict(zip(names, torch.autograd.grad(oracle.ce_dice_mean(yo, t2), [p[k] for k in names])))
+    for k in names:
+        assert eng[k] is not None and eng[k].shape == go[k].shape, k
+    fa = torch.cat([eng[k].detach().cpu().double().flatten() for k in names])
+    fb = torch.cat([go[k].detach().double().flatten() for k in names])
+    gap = 1.0 - torch.nn.functional.cosine_similarity(fa, fb, dim=0).item()
+    sa = [k for k in names if "sa" in k.split(".")[0]]
+    fa = torch.cat([eng[k].detach().cpu().double().flatten() for k in sa])
+    fb = torch.cat([go[k].detach().double().flatten() for k in sa])
+    gap_sa = 1.0 - torch.nn.functional.cosine_similarity(fa, fb, dim=0).item()
+    print(f"{kind}/{mode}: logits {e_logit:.2e}, 1-cos(all grads) {gap:.2e}, 1-cos(attention grads) {gap_sa:.2e}")
+    assert gap < 1e-3 and gap_sa < 1e-3
+    sd = net.state_dict()
+    for k, v in c["sa_bn_rm"].items():
+        assert relmax(sd[k], v) < 1e-4, k
+    for k, v in c["sa_bn_rv"].items():
+        assert relmax(sd[k], v) < 1e-4, k
+    assert int(sd[[k for k in sd if k.endswith("bn.num_batches_tracked") and "sa" in k][0]]) == 1
+    net.eval()
+    with torch.no_grad():
+        ye = net(*[x.to(dev) for x in xs])
+    assert relmax(ye, c["logits_eval"]) < 1e-3
+
+
+def test_unet_width_variants_run(oracle):
+    """UNet128 / UNet32 / UNet16 / UNet8 / UNet4 (UNet.py:210-368): the same network at other widths; widths below the
+    tcgen05 tile granularity run on the fp32 CUDA-core kernels.  Forward + backward against the oracle's UNet forward
+    evaluated on the module's own parameters."""
+    import aide_b200
+    dev = torch.device("cuda:0")
+    (x1, _), t1, _, _ = oracle.synthetic_batch(2, 32, 32, seed=5)
+    for cls in (aide_b200.UNet32, aide_b200.UNet16, aide_b200.UNet4):
+        torch.manual_seed(3)
+        net = cls(num_classes=2).to(dev).train()
+        p = oracle.clone_params({k: v.detach().cpu() for k, v in net.state_dict().items()}, requires_grad=True)
+        y = net(x1.to(dev))
+        yo = oracle.unet_forward(p, x1, training=True)
+        assert relmax(y, yo) < 2e-4, cls.__name__
+        aide_b200.DiceLoss()(y, t1.to(dev)).backward()
+        gw = torch.autograd.grad(oracle.dice_loss_mean(yo, t1), p["last_conv1.weight"])[0]
+        assert relmax(net.last_conv1.weight.grad, gw) < 2e-3, cls.__name__

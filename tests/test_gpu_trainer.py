@@ -136,3 +136,32 @@ def test_trainer_step_with_reverse_augmentation(oracle, graph):
         assert abs(m["loss1"].item() - r["loss1"].item()) < 2e-5 * max(1, abs(r["loss1"].item())), rep
         assert abs(m["loss2"].item() - r["loss2"].item()) < 2e-5 * max(1, abs(r["loss2"].item())), rep
         assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"]), rep
+
+
+@pytest.mark.parametrize("kind,flavour", [("unetsa", "kidney"), ("fuseunetsa", "chaos")])
+def test_trainer_step_attention_variants(oracle, kind, flavour):
+    """The AIDE step with the attention networks a script can select (trainkidney_proposed_mask1.py:73-80: UNetsa)."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    tr = AideTrainer(kind, mode="parity", device=dev, seed=2, flavour=flavour, cuda_graph=True)
+    torch.manual_seed(2)
+    unet = kind == "unetsa"
+    init = (lambda: oracle.init_unetsa(2)) if unet else (lambda: oracle.init_fuseunetsa(2))
+    fwd = oracle.unetsa_forward if unet else oracle.fuseunetsa_forward
+    p1 = oracle.clone_params(init(), requires_grad=True)
+    p2 = oracle.clone_params(init(), requires_grad=True)
+    (x1, x2), t1, t2, augs = oracle.synthetic_batch(B, S, S, seed=321, n_aug=4)
+    ins = (lambda a: (a[0],)) if unet else (lambda a: a)
+    r = oracle.aide_step(fwd, p1, p2, ins((x1, x2)), [ins(a) for a in augs], t1, t2, 0.25, flavour=flavour)
+    d = lambda t: t.to(dev)
+    xin = d(x1) if unet else (d(x1), d(x2))
+    ain = [d(a[0]) for a in augs] if unet else [tuple(d(t) for t in a) for a in augs]
+    m = tr.step(xin, d(t1), d(t2), ain, 0.25)
+    assert abs(m["loss1"].item() - r["loss1"].item()) < 5e-5 and abs(m["loss2"].item() - r["loss2"].item()) < 5e-5
+    assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"])
+    oracle.adam_amsgrad_step(p1, r["grads1"], {}, 1)
+    sd = tr.net1.state_dict()
+    key = "sa3.conv2.weight" if unet else "modal2_sa3.conv2.weight"
+    diff = (sd[key].cpu() - p1[key].detach()).abs()
+    assert diff.max().item() <= 2.1e-4 and diff.median().item() < 2e-5, (diff.max().item(), diff.median().item())

@@ -84,14 +84,15 @@ def test_dropin_packages_import():
     try:
         for m in ("models_twomodalinputs", "models_singlemodalinput", "utils"):
             sys.modules.pop(m, None)
-        from models_twomodalinputs import fuseunet
-        from models_singlemodalinput import UNet, UNetsa
+        from models_twomodalinputs import fuseunet, fuseunetsa, fuseunetsaseparate
+        from models_singlemodalinput import UNet, UNetsa, UNet2, UNet4, UNet8, UNet16, UNet32, UNet128
         from utils import (CrossEntropyLoss2d, DiceLoss, MulticlassDiceLoss, CEMDiceLoss, CEMDiceLossImage, PolyLR,
                            MulticlassDice_fn, MulticlassAccuracy_fn, Dice_fn, MulticlassMSELoss)
         import aide_b200
-        assert fuseunet is aide_b200.fuseunet and UNet is aide_b200.UNet
+        assert fuseunet is aide_b200.fuseunet and UNet is aide_b200.UNet and UNetsa is aide_b200.UNetsa
+        assert fuseunetsa is aide_b200.fuseunetsa and fuseunetsaseparate is aide_b200.fuseunetsaseparate
         with pytest.raises(NotImplementedError):
-            UNetsa()
+            UNet2()                       # 2-channel level: below the 4-channel access granularity of the NHWC kernels
     finally:
         sys.path.pop(0)
         for m in ("models_twomodalinputs", "models_singlemodalinput", "utils"):
