@@ -20,6 +20,6 @@ from .losses import (CEDiceLoss, CEMDiceLoss, CEMDiceLossImage, CrossEntropyLoss
 from .coteach_loss import (Coteachingloss_dropimage, Coteachingloss_dropimagedroppixel,  # noqa: F401
                            Coteachingloss_dropregionce, Coteachingloss_weightimage)
 from .optim import FlatAdamAMSGrad, PolyLR  # noqa: F401
-from .augment import reverse_aug_tensor, reverseaug  # noqa: F401
+from .augment import augmented_views, forward_aug, reverse_aug_tensor, reverseaug  # noqa: F401
 
 __version__ = "0.1.0"

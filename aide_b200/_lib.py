@@ -70,6 +70,7 @@ SIGNATURES = {
     "aide_pseudo_label": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aide_argmax_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "aide_reverse_aug": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "aide_forward_aug": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "aide_coteach_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aide_adam_amsgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i, _f, _vp]),
     "aide_coteach_select_ex": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp,

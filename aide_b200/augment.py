@@ -1,4 +1,11 @@
-"""Reverse augmentation of the augmented forwards' outputs on the GPU.
+"""Augmentation on the GPU: the forward augmentation of the input images and the reverse augmentation of the
+augmented forwards' outputs.
+
+Forward (``forward_aug`` / ``augmented_views``): what the reference's data loader does per view on the CPU through
+PIL -- datasetchaos_proposed/transform.py:81-106 (rotate +-degree, BILINEAR, uint8), :16-34 (horizontal flip),
+:108-131 (ToTensor), :134-170 (Normalize) -- as one kernel per view, bit-exact.
+
+Reverse (``reverseaug`` / ``reverse_aug_tensor``):
 
 Drop-in for the reference's ``reverseaug(augset, augoutput, classno)``
 (train_files/trainchaos_proposed_30cases1labeled.py:81-95), which copies every (sample, view, class) plane to the CPU,
@@ -76,3 +83,55 @@ def reverseaug(augset: Dict, augoutput: List[torch.Tensor], classno: int) -> Lis
         keep = torch.tensor([int(augset["augno"][b]) > aug_idx for b in range(n_b)], device=t.device)
         t[:n_b] = torch.where(keep.view(-1, 1, 1, 1), done, t[:n_b])
     return augoutput
+
+
+def forward_aug(images_u8: torch.Tensor, degrees: Sequence[float], hflips: Sequence[int], mean: torch.Tensor,
+                std: torch.Tensor) -> torch.Tensor:
+    """images_u8: [B,H,W,3] uint8 CUDA (the resized, un-augmented RGB images in PIL memory order).  Returns the view
+    ``Normalize(ToTensor(flip(rotate(img, degree))))`` as fp32 [B,3,H,W]: rotation by ``degrees[b]`` (PIL semantics:
+    counter-clockwise, BILINEAR, fill 0), then FLIP_LEFT_RIGHT where ``hflips[b]``, then /255 and (x - mean) / std with
+    per-sample per-channel ``mean`` / ``std`` [B,3] (the statistics of the un-augmented image, transform.py:140-147)."""
+    if not images_u8.is_cuda:
+        raise RuntimeError("aide_b200 runs on CUDA only (there is no CPU fallback)")
+    if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[3] != 3:
+        raise ValueError(f"expected uint8 [B,H,W,3] images, got {tuple(images_u8.shape)} {images_u8.dtype}")
+    B, H, W, _ = images_u8.shape
+    if len(degrees) != B or len(hflips) != B:
+        raise ValueError("one (degree, hflip) pair per sample expected")
+    mats, modes = [], []
+    for d in degrees:
+        mode, m = rotate_matrix(float(d), W, H)
+        modes.append(mode)
+        mats.append(m)
+    dev = images_u8.device
+    mt = torch.tensor(mats, dtype=torch.float64).to(dev)
+    md = torch.tensor(modes, dtype=torch.int32).to(dev)
+    fl = torch.tensor([1 if f else 0 for f in hflips], dtype=torch.int32).to(dev)
+    mean = mean.to(device=dev, dtype=torch.float32).reshape(B, 3).contiguous()
+    std = std.to(device=dev, dtype=torch.float32).reshape(B, 3).contiguous()
+    src = images_u8.contiguous()
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    call("aide_forward_aug", src.data_ptr(), out.data_ptr(), mt.data_ptr(), md.data_ptr(), fl.data_ptr(), mean.data_ptr(),
+         std.data_ptr(), B, H, W, torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def augmented_views(img1_u8: torch.Tensor, img2_u8: torch.Tensor, mean1, std1, mean2, std2, n_views: int = 4,
+                    rotation: float = 60.0, rng=None):
+    """The ``augset`` of the reference's data loader for a whole batch, built on the GPU: for every view k one random
+    rotation in [-rotation, rotation) (transform.py:86-104) and one coin flip (:18-33) PER SAMPLE, applied to both
+    modalities.  Returns (augset dict with ``augno``, ``degree{k}``, ``hflip{k}`` lists -- what ``reverseaug`` and
+    ``AideTrainer.step(augset=...)`` take -- and a list of n_views (modal1, modal2) fp32 [B,3,H,W] pairs)."""
+    import random as _random
+    rng = rng or _random
+    B = img1_u8.shape[0]
+    augset: Dict = {"augno": [n_views] * B}
+    for k in range(1, n_views + 1):           # RandomRotate runs before RandomHorizontallyFlip (train script :191-197)
+        augset[f"degree{k}"] = [rng.random() * 2 * rotation - rotation for _ in range(B)]
+    for k in range(1, n_views + 1):
+        augset[f"hflip{k}"] = [1 if rng.random() < 0.5 else 0 for _ in range(B)]
+    views = []
+    for k in range(1, n_views + 1):
+        views.append((forward_aug(img1_u8, augset[f"degree{k}"], augset[f"hflip{k}"], mean1, std1),
+                      forward_aug(img2_u8, augset[f"degree{k}"], augset[f"hflip{k}"], mean2, std2)))
+    return augset, views

@@ -257,6 +257,13 @@ int aide_argmax_mask(const float* logits, uint8_t* mask, int N, int K, int H, in
  * ROTATE_270 fast paths on square images) and a flip flag -- all device arrays. */
 int aide_reverse_aug(const float* src, float* dst, const double* matrices, const int* modes, const int* hflips,
                      int n_img, int K, int H, int W, void* stream);
+/* Forward augmentation of the INPUT images (the 4 views per sample of the proposed loop): what the data loader does on
+ * the CPU through PIL for every view -- datasetchaos_proposed/transform.py:81-106 Image.rotate(degree, BILINEAR) on the
+ * uint8 RGB image, :16-34 FLIP_LEFT_RIGHT (after the rotation), :108-131 ToTensor (/255), :134-170 Normalize with the
+ * un-augmented image's per-channel mean / std -- reproduced bit for bit.  src: [n_img,H,W,3] uint8 (PIL "RGB" memory
+ * order), dst: [n_img,3,H,W] fp32; matrices / modes as for aide_reverse_aug (built for +degree); mean, std: [n_img][3]. */
+int aide_forward_aug(const uint8_t* src_hwc, float* dst_chw, const double* matrices, const int* modes, const int* hflips,
+                     const float* mean, const float* stdv, int n_img, int H, int W, void* stream);
 /* Small-loss selection (trainchaos_proposed_30cases1labeled.py:305-321): ascending argsort of
  * `pre_other` (the OTHER net's per-image loss) -> idx[N]; the first n_clean images are "clean".
  * Emits this net's per-image coefficients and its scalar loss

@@ -543,3 +543,54 @@ def reverseaug_plane(src, hflip: bool, angle_deg: float):
     v2 = np.where(has2, s[y2, x0].astype(f64) + (s[y2, x1] - s[y2, x0]).astype(f64) * dx, v1)
     out = (v1 + (v2 - v1) * dy).astype(np.float32)
     return np.where(inside, out, np.float32(0.0))
+
+
+# --------------------------------------------------------------------------------------
+# forward augmentation of the input images ("next" row f2 of SURVEY.md section 8, second half)
+# --------------------------------------------------------------------------------------
+def forward_aug_pil(img_u8, degree: float, hflip: bool, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    """One view exactly as the reference's loader makes it (datasetchaos_proposed/transform.py; Compose order of
+    train_files/trainchaos_proposed_30cases1labeled.py:191-197): PIL rotate(degree, BILINEAR) on the uint8 RGB image
+    (:81-106), FLIP_LEFT_RIGHT (:16-34), ToTensor (:108-131), Normalize with the given per-channel mean / std
+    (:134-170).  img_u8: numpy [H,W,3] uint8.  Returns fp32 [3,H,W]."""
+    import numpy as np
+    from PIL import Image
+    im = Image.fromarray(img_u8).rotate(degree, Image.BILINEAR)
+    if hflip:
+        im = im.transpose(Image.FLIP_LEFT_RIGHT)
+    t = torch.from_numpy(np.array(im).transpose(2, 0, 1)).float() / 255.0
+    return t.sub(mean.reshape(3, 1, 1)).div(std.reshape(3, 1, 1))
+
+
+def rotate_u8(src, angle_deg: float):
+    """numpy restatement of PIL's Image.rotate(angle, BILINEAR) on an RGB uint8 image [H,W,3] (Pillow
+    src/libImaging/Geometry.c: affine_transform + bilinear_filter32RGB -- neighbours clamped, interpolation in double,
+    result truncated to uint8, outside -> 0).  Checked bit for bit against PIL in tests/test_oracle_golden.py."""
+    import numpy as np
+    h, w, _ = src.shape
+    mode, m = rotate_matrix(angle_deg, w, h)
+    if mode == 1:
+        return src.copy()
+    if mode == 2:
+        return src[::-1, ::-1].copy()
+    if mode == 3:
+        return np.ascontiguousarray(np.rot90(src, 1))
+    if mode == 4:
+        return np.ascontiguousarray(np.rot90(src, 3))
+    ys, xs = np.mgrid[0:h, 0:w]
+    xin = m[0] * (xs + 0.5) + m[1] * (ys + 0.5) + m[2]
+    yin = m[3] * (xs + 0.5) + m[4] * (ys + 0.5) + m[5]
+    inside = (xin >= 0.0) & (xin < w) & (yin >= 0.0) & (yin < h)
+    xin, yin = xin - 0.5, yin - 0.5
+    x, y = np.floor(xin).astype(np.int64), np.floor(yin).astype(np.int64)
+    dx, dy = xin - x, yin - y
+    x0, x1 = np.clip(x, 0, w - 1), np.clip(x + 1, 0, w - 1)
+    yc, y2 = np.clip(y, 0, h - 1), np.clip(y + 1, 0, h - 1)
+    has2 = (y + 1 >= 0) & (y + 1 < h)
+    s = src.astype(np.float64)
+    out = np.zeros_like(src)
+    for b in range(3):
+        v1 = s[yc, x0, b] + (s[yc, x1, b] - s[yc, x0, b]) * dx
+        v2 = np.where(has2, s[y2, x0, b] + (s[y2, x1, b] - s[y2, x0, b]) * dx, v1)
+        out[..., b] = np.where(inside, (v1 + (v2 - v1) * dy).astype(np.uint8), 0)
+    return out

@@ -507,5 +507,34 @@ def test_spatial_attention_gate_forward_backward(dev, fmt, C, pooled):
     gtol = 2e-4
     assert relmax(ops.nhwc_to_nchw(dy), ref[0]) < gtol, "dy"
     for name, gg, rr in zip(("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4"), got[:8], ref[1:9]):
-        assert relmax(gg, rr.flatten()) < gtol, name
+        if name in ("b3", "b4"):
+            # a constant added before BatchNorm2d(1) cancels: the true gradient is zero (rounding noise on both sides)
+            assert (gg.cpu() - rr.flatten()).abs().max().item() < gtol * ref[5].abs().max().item(), name
+        else:
+            assert relmax(gg, rr.flatten()) < gtol, name
     assert relmax(got[8][1:2], ref[9]) < gtol and relmax(got[8][0:1], ref[10]) < gtol      # {dbeta, dgamma}
+
+
+def test_forward_augmentation_matches_pil_bit_for_bit(dev, oracle):
+    """GPU forward augmentation of the input images (aide_forward_aug) against the reference loader's chain through PIL
+    and torch (datasetchaos_proposed/transform.py: rotate BILINEAR on uint8 RGB, FLIP_LEFT_RIGHT, ToTensor, Normalize)."""
+    import random
+    import numpy as np
+    import aide_b200 as A
+    rng = np.random.default_rng(3)
+    for (H, W) in ((64, 64), (48, 80)):
+        B = 6
+        imgs = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+        degs = [random.Random(i).random() * 120 - 60 for i in range(B - 2)] + [0.0, 180.0]
+        flips = [i % 2 for i in range(B)]
+        base = torch.from_numpy(imgs.transpose(0, 3, 1, 2)).float() / 255.0
+        mean, std = base.mean(dim=(2, 3)), base.std(dim=(2, 3))                 # transform.py:140-147, per image
+        ref = torch.stack([oracle.forward_aug_pil(imgs[b], degs[b], bool(flips[b]), mean[b], std[b]) for b in range(B)])
+        got = A.forward_aug(torch.from_numpy(imgs).to(dev), degs, flips, mean, std)
+        assert torch.equal(got.cpu(), ref), (H, W, (got.cpu() - ref).abs().max().item())
+    # the batch helper draws like the loader: 4 rotations, then 4 flips, per sample
+    u1 = torch.from_numpy(rng.integers(0, 256, size=(2, 32, 32, 3), dtype=np.uint8)).to(dev)
+    m, s_ = torch.full((2, 3), 0.4), torch.full((2, 3), 0.2)
+    augset, views = A.augmented_views(u1, u1, m, s_, m, s_, rng=random.Random(7))
+    assert len(views) == 4 and views[0][0].shape == (2, 3, 32, 32) and augset["augno"] == [4, 4]
+    assert all(-60.0 <= d < 60.0 for k in range(1, 5) for d in augset[f"degree{k}"])

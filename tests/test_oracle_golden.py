@@ -160,3 +160,19 @@ def test_learned_bilinear_networks(oracle, tag, shape):
         with torch.no_grad():
             ye = fwd({k: v.detach() for k, v in p.items()}, *xs, training=False)
         assert torch.allclose(ye, c["logits_eval"], rtol=0, atol=1e-4 * c["logits_eval"].abs().max().item())
+
+
+def test_forward_augmentation_restatement_matches_pil():
+    """oracle.rotate_u8 (numpy restatement of Pillow's 8-bit bilinear rotate) against PIL itself, bit for bit -- the pin
+    of the GPU forward-augmentation kernel (datasetchaos_proposed/transform.py:81-106)."""
+    import random
+    import numpy as np
+    from PIL import Image
+    from oracle import aide_oracle as O
+    rng = np.random.default_rng(0)
+    for trial in range(24):
+        h, w = (64, 64) if trial % 2 else (48, 80)
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        angle = random.Random(trial).random() * 120 - 60 if trial < 20 else [0.0, 180.0, 90.0, 270.0][trial - 20]
+        ref = np.array(Image.fromarray(img).rotate(angle, Image.BILINEAR))
+        assert np.array_equal(O.rotate_u8(img, angle), ref), (trial, angle)
