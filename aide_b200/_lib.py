@@ -29,6 +29,11 @@ SIGNATURES = {
                                     C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "aide_conv3x3_stat_rows": (_i, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "aide_conv3x3_bn_relu_ok": (_i, [_i, _i, _i, _i, _i, _i]),
+    "aide_conv3x3_bn_relu_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                      _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "aide_bn_eval_scale_shift_batch": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                            C.POINTER(_i), C.POINTER(_vp), _f, _vp]),
     "aide_conv3x3_plan_info": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_i)]),
     "aide_conv3x3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_dgrad": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

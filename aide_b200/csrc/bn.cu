@@ -241,6 +241,32 @@ __global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int ro
   if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0u;     // ready for the next launch
 }
 
+// ------------------------------------------------------------------ eval mode: scale / shift of MANY BatchNorm layers at once
+// y = scale * z + shift with scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (the same fp32
+// operations as bn_finalize_kernel's eval branch).  One launch for every unit of a network (an eval forward used to spend
+// one finalize launch per unit); blockIdx.x -> (layer, 256-channel chunk) through the prefix sums.
+constexpr int kEvalMaxLayers = 48;
+struct EvalSsTable {
+  const float* gamma[kEvalMaxLayers];
+  const float* beta[kEvalMaxLayers];
+  const float* rmean[kEvalMaxLayers];
+  const float* rvar[kEvalMaxLayers];
+  float* ss[kEvalMaxLayers];
+  int C[kEvalMaxLayers], block_end[kEvalMaxLayers];
+  int n;
+};
+__global__ void bn_eval_scale_shift_batch_kernel(const __grid_constant__ EvalSsTable t, float eps) {
+  int l = 0;
+  while (l + 1 < t.n && (int)blockIdx.x >= t.block_end[l]) ++l;
+  const int c = ((int)blockIdx.x - (l ? t.block_end[l - 1] : 0)) * 256 + threadIdx.x;
+  const int C = t.C[l];
+  if (c >= C) return;
+  const float rstd = 1.0f / sqrtf(t.rvar[l][c] + eps);
+  const float sc = t.gamma[l][c] * rstd;
+  t.ss[l][c] = sc;
+  t.ss[l][C + c] = t.beta[l][c] - t.rmean[l][c] * sc;
+}
+
 // ------------------------------------------------------------------ forward apply
 __device__ __forceinline__ float4 bn_relu4(float4 z, float4 sc, float4 sh) {
   return make_float4(fmaxf(fmaf(z.x, sc.x, sh.x), 0.f), fmaxf(fmaf(z.y, sc.y, sh.y), 0.f),
@@ -776,6 +802,30 @@ extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, c
   AIDE_CHECK_LAUNCH();
   if (dbias_conv && !fuse_dbias) {
     reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(partial2, rows, C, C, dbias_conv);
+    AIDE_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int aide_bn_eval_scale_shift_batch(int n_layers, const float* const* gamma, const float* const* beta,
+                                              const float* const* running_mean, const float* const* running_var,
+                                              const int* C, float* const* scale_shift, float eps, void* stream) {
+  AIDE_REQUIRE(n_layers >= 1 && gamma && beta && running_mean && running_var && C && scale_shift,
+               "bn_eval_scale_shift_batch: bad arguments");
+  for (int base = 0; base < n_layers; base += kEvalMaxLayers) {
+    EvalSsTable t{};
+    t.n = n_layers - base < kEvalMaxLayers ? n_layers - base : kEvalMaxLayers;
+    int blocks = 0;
+    for (int i = 0; i < t.n; ++i) {
+      const int l = base + i;
+      AIDE_REQUIRE(gamma[l] && beta[l] && running_mean[l] && running_var[l] && scale_shift[l] && C[l] > 0,
+                   "bn_eval_scale_shift_batch: layer %d: null argument", l);
+      t.gamma[i] = gamma[l]; t.beta[i] = beta[l]; t.rmean[i] = running_mean[l]; t.rvar[i] = running_var[l];
+      t.ss[i] = scale_shift[l]; t.C[i] = C[l];
+      blocks += ceil_div(C[l], 256);
+      t.block_end[i] = blocks;
+    }
+    bn_eval_scale_shift_batch_kernel<<<blocks, 256, 0, as_stream(stream)>>>(t, eps);
     AIDE_CHECK_LAUNCH();
   }
   return 0;

@@ -20,9 +20,13 @@ int tc_wgrad(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, in
              const float* out_scale_ptr, cudaStream_t st);
 bool halo_shape_ok(int fmt, int cin, int cout, int N, int H, int W);
 int halo_stat_rows(int N, int H, int W);
+struct HaloFused {
+  const float* ss;
+  View dst, pa, pb;
+};
 int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
                  const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
-                 float out_scale, const float* out_scale_ptr, cudaStream_t st);
+                 float out_scale, const float* out_scale_ptr, cudaStream_t st, const HaloFused* fused = nullptr);
 bool wgrad_halo_ok(int fmt, int cin, int cout, int N, int H, int W);
 size_t wgrad_halo_workspace_bytes(int fmt, int cin, int cout, int N, int H, int W);
 int wgrad_halo(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* dz0, const void* dz1,
@@ -127,4 +131,31 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
   return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes, dw_oihw,
                   fmt == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr,
                   as_stream(stream));
+}
+
+// ---- inference: conv3x3 + eval-mode BatchNorm + ReLU (+ MaxPool2d) in ONE launch ---------------------------------------
+extern "C" int aide_conv3x3_bn_relu_ok(int fmt, int cin, int cout, int N, int H, int W) {
+  return (fmt == AIDE_FMT_F16X2 || fmt == AIDE_FMT_BF16 || fmt == AIDE_FMT_TF32X2) && tc_shape_ok(fmt, cin, cout) &&
+                 halo_shape_ok(fmt, cin, cout, N, H, W)
+             ? 1
+             : 0;
+}
+
+extern "C" int aide_conv3x3_bn_relu_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                                        const void* w_p0, const void* w_p1, const float* bias, const float* scale_shift,
+                                        int cout, int N, int H, int W, void* dst_p0, void* dst_p1, int dst_ctot,
+                                        int dst_coff, void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                                        void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream) {
+  AIDE_REQUIRE(x_p0 && w_p0 && scale_shift && cin > 0 && cout > 0 && N > 0 && H > 0 && W > 0, "conv3x3_bn_relu_fwd: bad arguments");
+  AIDE_REQUIRE(aide_conv3x3_bn_relu_ok(fmt, cin, cout, N, H, W),
+               "conv3x3_bn_relu_fwd: shape / format not covered by the fused kernel (use aide_conv3x3_fwd + aide_bn_relu_apply)");
+  AIDE_REQUIRE(x_coff >= 0 && x_coff + cin <= x_ctot, "conv3x3_bn_relu_fwd: channel view out of range");
+  AIDE_REQUIRE(dst_coff % 8 == 0 && dst_ctot % 8 == 0 && poolA_coff % 8 == 0 && poolA_ctot % 8 == 0 && poolB_coff % 8 == 0 &&
+                   poolB_ctot % 8 == 0,
+               "conv3x3_bn_relu_fwd: destination channel offsets must be multiples of 8 (128-bit plane stores)");
+  HaloFused f{scale_shift, View{dst_p0, dst_p1, dst_ctot, dst_coff}, View{poolA_p0, poolA_p1, poolA_ctot, poolA_coff},
+              View{poolB_p0, poolB_p1, poolB_ctot, poolB_coff}};
+  const float op_scale = fmt == AIDE_FMT_F16X2 ? 1.0f / (kF16ActScale * kF16WScale) : 1.0f;
+  return halo_conv3x3(fmt, x_p0, x_p1, x_ctot, x_coff, cin, w_p0, w_p1, bias, nullptr, cout, 0, cout, N, H, W, nullptr,
+                      op_scale, nullptr, as_stream(stream), &f);
 }

@@ -31,6 +31,11 @@ namespace aide {
 
 using namespace ptx;
 
+struct HaloFused {                // fused inference epilogue: eval-mode BN scale/shift + ReLU (+ 2x2 max-pool) destinations
+  const float* ss;                // [2][cout]
+  View dst, pa, pb;
+};
+
 int act_tmap(CUtensorMap* m, int dtype, const void* plane, int ctot, int coff, int C, int N, int H, int W, int box_c,
              int box_w, int box_h, int swizzle_bytes);
 int mat_tmap(CUtensorMap* m, int dtype, const void* plane, int rows, int kdim, int box_k, int box_rows,
@@ -50,6 +55,11 @@ struct HaloParams {
   float* z;
   const float* bias;
   float* stat_partial;
+  // fused inference epilogue (eval-mode BatchNorm folded in): y = relu(scale[c] * (acc + bias) + shift[c]) written as
+  // operand planes into the consumer's channel slice (+ its 2x2 max-pool into up to two half-resolution slices)
+  const float* ep_ss;                            // [2][cout] scale, shift (nullptr: plain fp32 z output)
+  void *y0, *y1, *pa0, *pa1, *pb0, *pb1;
+  int y_ctot, y_coff, pa_ctot, pa_coff, pb_ctot, pb_coff;
   const float* out_scale_ptr;
   float out_scale;
   int z_ctot, z_coff, cout, cin, H, W;
@@ -76,6 +86,38 @@ __device__ __forceinline__ float column_sums_32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// 32 consecutive channels of one pixel -> operand planes (the conversions of common.cuh::st4, 128-bit stores)
+template <int KIND>
+__device__ __forceinline__ void store_planes_32(void* p0, void* p1, size_t e, const float (&v)[32]) {
+  if constexpr (KIND == K_F16X2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __align__(16) __half h[8];
+      __align__(16) __half l[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f16_split(v[j + k] * kF16ActScale, h[k], l[k]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p0) + e + j) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p1) + e + j) = *reinterpret_cast<const uint4*>(l);
+    }
+  } else if constexpr (KIND == K_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h[k] = __float2bfloat16_rn(v[j + k]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p0) + e + j) = *reinterpret_cast<const uint4*>(h);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 hi = make_float4(tf32_rn(v[j]), tf32_rn(v[j + 1]), tf32_rn(v[j + 2]), tf32_rn(v[j + 3]));
+      float4 lo = make_float4(v[j] - hi.x, v[j + 1] - hi.y, v[j + 2] - hi.z, v[j + 3] - hi.w);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p0) + e + j) = hi;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p1) + e + j) = lo;
+    }
+  }
 }
 
 template <int KIND, int NKS>
@@ -337,6 +379,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
             float t = v[j] * scale;
             if (bp) t += __ldg(bp + j);
             v[j] = valid ? t : 0.f;
+          }
+          if (p.ep_ss) {
+            // ---- inference: BatchNorm (running statistics) + ReLU (+ max-pool) here, same operations in the same
+            // order as bn_relu_apply_kernel applies to the fp32 z of the unfused path -> bit-identical planes
+            const float* sc = p.ep_ss + n0 + ch * 32;
+            const float* sh = sc + p.cout;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
+            const size_t pix = ((size_t)n_img * p.H + hh) * p.W + ww;
+            if (valid && p.y0) store_planes_32<KIND>(p.y0, p.y1, pix * p.y_ctot + p.y_coff + n0 + ch * 32, v);
+            if (p.pa0 || p.pb0) {
+              // 2x2 max-pool: the window partners of pixel (ty, tx) are lanes ^1 (tx) and ^8 (ty) of this warp
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+              }
+              if (valid && !(tx & 1) && !(ty & 1)) {
+                const size_t win = ((size_t)n_img * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1);
+                if (p.pa0) store_planes_32<KIND>(p.pa0, p.pa1, win * p.pa_ctot + p.pa_coff + n0 + ch * 32, v);
+                if (p.pb0) store_planes_32<KIND>(p.pb0, p.pb1, win * p.pb_ctot + p.pb_coff + n0 + ch * 32, v);
+              }
+            }
+            continue;
           }
           if (valid) {
 #pragma unroll
@@ -601,7 +667,7 @@ int halo_stat_rows(int N, int H, int W) { return 4 * N * ceil_div(W, kTW) * ceil
 
 int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, int cin, const void* w0, const void* w1,
                  const float* bias, float* z, int z_ctot, int z_coff, int cout, int N, int H, int W, float* stat_partial,
-                 float out_scale, const float* out_scale_ptr, cudaStream_t st) {
+                 float out_scale, const float* out_scale_ptr, cudaStream_t st, const HaloFused* fused) {
   const int kind = kind_of(fmt);
   const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
   const int dtype = fmt == AIDE_FMT_BF16 ? 1 : fmt == AIDE_FMT_F16X2 ? 2 : 0;
@@ -630,6 +696,14 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   p.z = z; p.bias = bias; p.stat_partial = stat_partial;
+  if (fused) {
+    AIDE_REQUIRE(fused->ss && (fused->dst.p0 || fused->pa.p0 || fused->pb.p0), "conv3x3(fused): no destination");
+    AIDE_REQUIRE(!(fused->pa.p0 || fused->pb.p0) || (H % 2 == 0 && W % 2 == 0), "conv3x3(fused): pooling needs even H, W");
+    p.ep_ss = fused->ss;
+    p.y0 = fused->dst.p0; p.y1 = fused->dst.p1; p.y_ctot = fused->dst.ctot; p.y_coff = fused->dst.coff;
+    p.pa0 = fused->pa.p0; p.pa1 = fused->pa.p1; p.pa_ctot = fused->pa.ctot; p.pa_coff = fused->pa.coff;
+    p.pb0 = fused->pb.p0; p.pb1 = fused->pb.p1; p.pb_ctot = fused->pb.ctot; p.pb_coff = fused->pb.coff;
+  }
   p.out_scale = out_scale; p.out_scale_ptr = out_scale_ptr;
   p.z_ctot = z_ctot; p.z_coff = z_coff; p.cout = cout; p.cin = cin; p.H = H; p.W = W;
   AIDE_REQUIRE(pl.smem <= kSmemMax, "conv3x3(halo): shared memory %d too large", pl.smem);

@@ -389,6 +389,20 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
         skip = g * Ng * (H >> lvl) * (W >> lvl) * ctot * _esize(layout.buf_fmt(name))
         return p0 + skip, (p1 + skip if p1 is not None else None), ctot, co
 
+    fuse_eval = (not training) and os.environ.get("AIDE_B200_EVAL_FUSE", "1") != "0"
+    if fuse_eval:
+        # eval mode: scale / shift of EVERY BatchNorm (units and attention gates) in one launch; the units' BN + ReLU
+        # (+ max-pool) then run inside the conv epilogue (aide_conv3x3_bn_relu_fwd)
+        rows = [(u.bn, u.cout, base + layout.off["ss:" + u.name]) for u in plan.units]
+        rows += [(a.name + ".bn", 1, base + layout.off["sass:" + a.name]) for a in plan.atts]
+        n = len(rows)
+        arr = lambda vals, ty: (ty * n)(*vals)
+        call("aide_bn_eval_scale_shift_batch", n,
+             arr([params[b + ".weight"].data_ptr() for b, _, _ in rows], C.c_void_p),
+             arr([params[b + ".bias"].data_ptr() for b, _, _ in rows], C.c_void_p),
+             arr([params[b + ".running_mean"].data_ptr() for b, _, _ in rows], C.c_void_p),
+             arr([params[b + ".running_var"].data_ptr() for b, _, _ in rows], C.c_void_p),
+             arr([c for _, c, _ in rows], C.c_int), arr([o for _, _, o in rows], C.c_void_p), BN_EPS, st)
     for op in plan.ops:
         if isinstance(op, tuple) and op[0] == "input":
             _, i, name = op
@@ -405,17 +419,24 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
             z = base + layout.off["z:" + u.name]
             stp = base + layout.off["st:" + u.name]
             ss = base + layout.off["ss:" + u.name]
+            d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
+            pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
+            pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
+            if fuse_eval and not u.first and lib.aide_conv3x3_bn_relu_ok(ufmt, u.cin, u.cout, N, h, w):
+                call("aide_conv3x3_bn_relu_fwd", ufmt, x0, x1, xct, xco, u.cin, w0, w1, params[u.conv + ".bias"].data_ptr(),
+                     ss, u.cout, N, h, w, *d, *pa, *pb, st)
+                continue
             call("aide_conv3x3_fwd", ufmt, x0, x1, xct, xco, u.cin, w0, w1, params[u.conv + ".bias"].data_ptr(),
                  z, u.cout, 0, u.cout, N, h, w, stp if training else None, st)
+            if fuse_eval:                       # scale / shift already there (one group: every image shares them)
+                call("aide_bn_relu_apply_grouped", fmt, z, N, N, h, w, u.cout, ss, *d, *pa, *pb, st)
+                continue
             rows_g = layout.stat_rows[u.name] // G
             call("aide_bn_finalize_grouped", stp, rows_g, G, u.cout, float(Ng * h * w),
                  params[u.bn + ".weight"].data_ptr(), params[u.bn + ".bias"].data_ptr(),
                  params[u.bn + ".running_mean"].data_ptr(), params[u.bn + ".running_var"].data_ptr(),
                  BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * u.cout * 4,
                  tickets[0].data_ptr() + 4 * tickets[1][u.name] if tickets is not None else None, st)
-            d = _view(layout, base, u.dst[0], u.dst[1]) if u.dst else (None, None, 0, 0)
-            pa = _view(layout, base, u.pools[0][0], u.pools[0][1]) if len(u.pools) > 0 else (None, None, 0, 0)
-            pb = _view(layout, base, u.pools[1][0], u.pools[1][1]) if len(u.pools) > 1 else (None, None, 0, 0)
             call("aide_bn_relu_apply_grouped", fmt, z, N, Ng, h, w, u.cout, ss, *d, *pa, *pb, st)
         elif isinstance(op, Attention):
             a = op
@@ -428,13 +449,15 @@ def run_forward(plan: Plan, layout: Layout, params: Dict[str, torch.Tensor], wei
                  o("sa1:"), o("sa2:"), o("sa3:"), o("saa:"), o("sast:"), N, h, w, st)
             rows_g = lib.aide_sa_stat_rows(N, h, w) // G
             ss = o("sass:")
-            call("aide_bn_finalize_grouped", o("sast:"), rows_g, G, 1, float(Ng * h * w), P("bn.weight"), P("bn.bias"),
-                 P("bn.running_mean"), P("bn.running_var"), BN_MOMENTUM, BN_EPS, 1 if training else 0, ss, ss + G * 2 * 4,
-                 None, st)
+            if not fuse_eval:
+                call("aide_bn_finalize_grouped", o("sast:"), rows_g, G, 1, float(Ng * h * w), P("bn.weight"), P("bn.bias"),
+                     P("bn.running_mean"), P("bn.running_var"), BN_MOMENTUM, BN_EPS, 1 if training else 0, ss,
+                     ss + G * 2 * 4, None, st)
             d = _view(layout, base, a.dst[0], a.dst[1]) if a.dst else (None, None, 0, 0)
             pa = _view(layout, base, a.pools[0][0], a.pools[0][1]) if len(a.pools) > 0 else (None, None, 0, 0)
             pb = _view(layout, base, a.pools[1][0], a.pools[1][1]) if len(a.pools) > 1 else (None, None, 0, 0)
-            call("aide_sa_gate_apply", fmt, *y, o("saa:"), ss, N, Ng, h, w, a.c, o("sag:"), *d, *pa, *pb, st)
+            call("aide_sa_gate_apply", fmt, *y, o("saa:"), ss, N, N if fuse_eval else Ng, h, w, a.c, o("sag:"), *d, *pa,
+                 *pb, st)
         elif isinstance(op, Upsample):
             h, w = H >> op.level, W >> op.level
             s = _view(layout, base, op.src, 0)

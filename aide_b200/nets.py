@@ -264,8 +264,10 @@ class _GraphedEval:
             total = net._layouts[(N, H, W, fmt, 1)].total
             self._arena = torch.empty(total, dtype=torch.uint8, device=self.static_in[0].device)   # owned by the graph
             self.graph = torch.cuda.CUDAGraph()
+            n0 = E.lib.aide_launch_count()
             with torch.cuda.graph(self.graph):
                 self.out, _ = net._engine_forward(self.static_in, keep_tape=False, arena=self._arena)
+            self.n_kernels = E.lib.aide_launch_count() - n0          # kernels of this library per replay
         self._wkey = self._weights_key()
         self._weights = net._weights.get(fmt)          # keep the operand planes the captured kernels read alive
 

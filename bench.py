@@ -350,6 +350,43 @@ def hbm_roofline(fmt, B, S, device, peaks):
                 ms=round(ms, 4))
 
 
+def eval_single_slice(args, S, device, n_slices=200):
+    """The per-epoch evaluation / pseudo-label rewrite loops (trainchaos_proposed_30cases1labeled.py:373-496,
+    evalchaos_comparison_1cases.py:203-214): one slice at a time -- H2D of the two modalities, eval-mode forward
+    (net.graphed_eval: BatchNorm folded into the conv epilogues, one CUDA graph), softmax -> argmax mask
+    (aide_argmax_mask), D2H of the uint8 mask."""
+    import aide_b200 as A
+    torch.manual_seed(2)
+    net = A.fuseunet(num_classes=2, mode=args.mode).to(device).eval()
+    g = torch.Generator().manual_seed(99)
+    host = [tuple(torch.randn(1, 3, S, S, generator=g).pin_memory() for _ in range(2)) for _ in range(4)]
+    masks = [torch.empty((1, S, S), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    dev_in = tuple(torch.empty(1, 3, S, S, device=device) for _ in range(2))
+    f = net.graphed_eval(*dev_in)
+    l0 = A.lib.aide_launch_count()
+
+    def one(i):
+        for d, h in zip(dev_in, host[i % 4]):
+            d.copy_(h, non_blocking=True)
+        with torch.no_grad():
+            masks[i % 4].copy_(A.predict_mask(f(*dev_in)), non_blocking=True)
+
+    for i in range(5):
+        one(i)
+    per_fwd = f.n_kernels
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_slices):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / n_slices
+    return dict(value=round(1e3 / ms, 1), unit="slices/s", ms_per_slice=round(ms, 4), slices=n_slices,
+                launches_per_slice=per_fwd + 1, h2d_bytes_per_slice=2 * 3 * S * S * 4, d2h_bytes_per_slice=S * S,
+                api="net.graphed_eval(modal1, modal2) + predict_mask, one 256x256 slice per call (pinned host in / out)")
+
+
 def module_e2e(args, B, S, device, K):
     """The call pattern of an UNMODIFIED training script (train_files/trainchaos_proposed_30cases1labeled.py:263-325)
     on the drop-in modules: 8 detached augmented forwards, F.softmax / sharpen in torch, 2 train forwards through
@@ -703,6 +740,10 @@ def main():
                                      algorithmic_tflops=round(B * K / (ms_t / 1e3) * 6 * FUSEUNET_FWD_GFLOP_256 * (S / 256.0) ** 2 / 1e3, 1),
                                      note="train forward + backward + Adam of both nets, no augmented forwards (R_train)")
         if world == 1 and not args.no_extras:
+            try:
+                out["eval_single_slice"] = eval_single_slice(args, S, device)
+            except Exception as e:  # noqa: BLE001
+                out["eval_single_slice"] = dict(value=None, error=f"{type(e).__name__}: {e}")
             try:
                 out["e2e_module"] = module_e2e(args, B, S, device, max(2, min(K, 5)))
             except Exception as e:  # noqa: BLE001

@@ -77,6 +77,18 @@ int aide_conv3x3_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, in
                      const void* w_p0, const void* w_p1, const float* bias,
                      float* z, int z_ctot, int z_coff, int cout, int N, int H, int W,
                      float* stat_partial, void* stream);
+/* Inference form of a whole conv3x3 -> BatchNorm2d(eval) -> ReLU (-> MaxPool2d(2,2)) unit (netblocks.py:30-33 under
+ * module.eval(); evalchaos_comparison_1cases.py:203-214) as ONE tcgen05 launch: the epilogue applies
+ * y = relu(scale*(acc+bias)+shift) with scale_shift [2][cout] from aide_bn_eval_scale_shift_batch and writes the operand
+ * planes straight into the consumer's channel slice (dst) and the 2x2 max-pool into up to two half-resolution slices --
+ * no fp32 z round trip, no finalize / apply launches; bit-identical to aide_conv3x3_fwd + aide_bn_relu_apply.
+ * aide_conv3x3_bn_relu_ok: 1 when the (format, shape) is covered (tensor-core formats, maps of at least 8x8). */
+int aide_conv3x3_bn_relu_ok(int fmt, int cin, int cout, int N, int H, int W);
+int aide_conv3x3_bn_relu_fwd(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                             const void* w_p0, const void* w_p1, const float* bias, const float* scale_shift, int cout,
+                             int N, int H, int W, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,
+                             void* poolA_p0, void* poolA_p1, int poolA_ctot, int poolA_coff,
+                             void* poolB_p0, void* poolB_p1, int poolB_ctot, int poolB_coff, void* stream);
 /* Tiling the tcgen05 forward/dgrad kernel picks for a layer (diagnostics for bench.py / tools): out[9] =
  * {cout tile, pixel tiles per CTA iteration, accumulators per tile, TMEM buffers, smem row bytes, halo stages,
   *  weight stages, dynamic smem bytes, bit 0: hi/lo weight planes stacked along N, bit 1: weights resident in shared memory}.  Returns non-zero when the layer runs on the first-generation kernel. */
@@ -116,6 +128,12 @@ int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgroups, int C, 
  * run as ONE launch: the last fold block of a channel group to arrive (ticket) finalises it, reading the folded
  * partials in fixed order -- bit-identical to the two-launch path.  The counters are left at zero. */
 int aide_bn_ticket_slots(int C);
+/* Eval mode (module.eval(): running statistics): scale / shift [2][C] of n_layers BatchNorm layers in ONE launch (host
+ * arrays of per-layer device pointers) -- the per-epoch evaluation / pseudo-label rewrite loops
+ * (trainchaos_proposed_30cases1labeled.py:373-496) run thousands of single-slice eval forwards. */
+int aide_bn_eval_scale_shift_batch(int n_layers, const float* const* gamma, const float* const* beta,
+                                   const float* const* running_mean, const float* const* running_var, const int* C,
+                                   float* const* scale_shift, float eps, void* stream);
 /* y = relu(scale*z+shift) written to `dst` (full resolution) and, when given, the 2x2 max-pooled y to
  * up to two half-resolution views (the fused-encoder concat and the modal-2 branch, fuseunet.py:51-56). */
 int aide_bn_relu_apply(int fmt, const float* z, int N, int H, int W, int C, const float* scale_shift,

@@ -514,3 +514,37 @@ def test_unet_width_variants_run(oracle):
         aide_b200.DiceLoss()(y, t1.to(dev)).backward()
         gw = torch.autograd.grad(oracle.dice_loss_mean(yo, t1), p["last_conv1.weight"])[0]
         assert relmax(net.last_conv1.weight.grad, gw) < 2e-3, cls.__name__
+
+
+@pytest.mark.parametrize("kind", ["fuse", "unet", "unetsa"])
+def test_fused_eval_forward_is_bit_identical_to_unfused(oracle, kind, monkeypatch):
+    """Eval mode folds BatchNorm(running statistics) + ReLU (+ max-pool) into the conv epilogue
+    (aide_conv3x3_bn_relu_fwd) and derives every layer's scale / shift in one launch; the planes it writes must equal
+    the conv -> finalize -> apply sequence bit for bit, and the launch count must drop."""
+    import aide_b200
+    from aide_b200 import lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    net = (aide_b200.UNetsa(num_classes=2, mode="parity") if kind == "unetsa" else build(kind, "parity", dev)).to(dev)
+    sd = net.state_dict()
+    for k in sd:                                      # non-trivial running statistics / affine parameters
+        if k.endswith("running_mean") or (k.endswith(".bias") and "bn" in k):
+            sd[k] = torch.randn_like(sd[k]) * 0.1
+        if k.endswith("running_var"):
+            sd[k] = torch.rand_like(sd[k]) + 0.5
+    net.load_state_dict(sd)
+    net.eval()
+    g = torch.Generator().manual_seed(8)
+    xs = tuple(torch.randn(2, 3, 64, 96, generator=g).to(dev) for _ in range(2 if kind == "fuse" else 1))
+    with torch.no_grad():
+        monkeypatch.setenv("AIDE_B200_EVAL_FUSE", "0")
+        n0 = lib.aide_launch_count()
+        y_ref = net(*xs).clone()
+        n_unfused = lib.aide_launch_count() - n0
+        monkeypatch.setenv("AIDE_B200_EVAL_FUSE", "1")
+        n0 = lib.aide_launch_count()
+        y = net(*xs)
+        n_fused = lib.aide_launch_count() - n0
+    assert torch.equal(y, y_ref)
+    print(f"{kind}: eval forward launches {n_unfused} -> {n_fused}")
+    assert n_fused < 0.7 * n_unfused
