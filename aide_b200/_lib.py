@@ -72,6 +72,12 @@ SIGNATURES = {
     "aide_loss_blocks": (_i, [_i, _i]),
     "aide_loss_image_finalize": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "aide_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f, _vp, _vp]),
+    "aide_pixel_loss_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
+    "aide_pixel_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp]),
+    "aide_softmax_mse_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "aide_softmax_mse_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "aide_maxpool_nchw_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "aide_maxpool_nchw_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "aide_pseudo_label": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "aide_argmax_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "aide_reverse_aug": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -2,27 +2,22 @@
 
 No reference script calls these classes; the co-teaching that actually runs is the
 inline step fused in aide_b200.losses.coteach_step.  They are provided for import compatibility:
-the image-level selection reuses the fused per-image CE+Dice kernel, the tiny index bookkeeping is
-tensor plumbing.  As in the reference only ``reduction='none'`` is meaningful (the default 'mean'
+the image-level selection reuses the fused per-image CE+Dice kernel, the per-pixel / per-region maps
+(cross-entropy, bidirectional KL, max-pool of logits and targets) run on aide_pixel_loss_* / aide_maxpool_nchw_*; only the
+index bookkeeping on the small per-image / per-region vectors (argsort, gather, mean) is tensor plumbing.  As in the reference only ``reduction='none'`` is meaningful (the default 'mean'
 raises there: torch.mean(scalar, dim=[1,2]), coteach_loss.py:102).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-from .losses import _PerImageLoss, _check
+from .losses import _PerImageLoss, _check, maxpool_nchw, pixel_loss_map
 
 
 def _per_image(logits, targets, weight):
     lg, tg = _check(logits, targets)
     return _PerImageLoss.apply(lg, tg, float(weight), 1.0, (1.0, 1.0), 1.0, 255)
-
-
-def _kl_bidirection(a, b):                      # coteach_loss.py:85-92
-    pa, pb = F.softmax(a, dim=1), F.softmax(b, dim=1)
-    return (pa * torch.log(pa / pb)).sum(1) + (pb * torch.log(pb / pa)).sum(1)
 
 
 class _Base(nn.Module):
@@ -66,9 +61,10 @@ class Coteachingloss_dropregionce(nn.Module):   # coteach_loss.py:163-196
         tw, th = inputs1.shape[2], inputs1.shape[3]
         pw, ph = int(tw * self.scale), int(th * self.scale)
         k = (int(tw / pw), int(th / ph))
-        pool = lambda x: F.max_pool2d(x, kernel_size=k, stride=k, padding=0, ceil_mode=True)
-        p1, p2, tp = pool(inputs1), pool(inputs2), pool(targets.float()).long()
-        ce = lambda x: F.nll_loss(F.log_softmax(x, dim=1), tp, reduction="none").view(x.shape[0], -1)
+        pool = lambda x: maxpool_nchw(x, k[0], k[1])           # aide_maxpool_nchw (ceil_mode, stride = kernel)
+        p1, p2 = pool(inputs1), pool(inputs2)
+        tp = pool(targets.float().unsqueeze(1)).squeeze(1).long()
+        ce = lambda x: pixel_loss_map(x, tp).view(x.shape[0], -1)      # per-region cross-entropy map, one kernel
         l1, l2 = ce(p1), ce(p2)
         n = int((1 - forget_rate) * l1.shape[1])
         i1, i2 = torch.argsort(l1.detach(), dim=1)[:, :n], torch.argsort(l2.detach(), dim=1)[:, :n]
@@ -84,16 +80,14 @@ class Coteachingloss_dropimagedroppixel(_Base):  # coteach_loss.py:198-254
         n_rem2 = None
         if len(d1) > 0:
             a, b, t = inputs1[d2], inputs2[d2], targets[d2]
-            ce = F.nll_loss(F.log_softmax(a, dim=1), t, reduction="none")
-            drop = ((_kl_bidirection(a, b) + ce).view(-1) * t.view(-1).float())
+            drop = (pixel_loss_map(a, t, logits2=b, kl=True).view(-1) * t.view(-1).float())     # KL(a,b)+KL(b,a)+CE(a)
             fore = drop[drop > 0]
             order = torch.argsort(fore.detach())
             n_rem2 = int(rem * len(order))
             out1 = out1 + 0.25 * fore[order[:n_rem2]].mean()
         if len(d2) > 0:
             a, b, t = inputs1[d1], inputs2[d1], targets[d1]
-            ce = F.nll_loss(F.log_softmax(b, dim=1), t, reduction="none")
-            drop = ((_kl_bidirection(a, b) + ce).view(-1) * t.view(-1).float())
+            drop = (pixel_loss_map(b, t, logits2=a, kl=True).view(-1) * t.view(-1).float())     # symmetric KL + CE(b)
             fore = drop[drop > 0]
             order = torch.argsort(fore.detach())
             out2 = out2 + 0.25 * fore[order[:n_rem2]].mean()     # the reference reuses num_remember2 (:249)

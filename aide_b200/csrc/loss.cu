@@ -360,3 +360,178 @@ extern "C" int aide_coteach_select(const float* pre_other, const float* loss_img
   return aide_coteach_select_ex(pre_other, N, 0, loss_img, sums, N, H, W, n_clean, rate, nullptr, seg_w, cor_w, w_ce,
                                 w_dice, idx, a_ce, a_dice, a_mse, loss_out, stream);
 }
+
+// ---------------------------------------------------------------- per-pixel maps of the drop-in loss classes
+// CrossEntropyLoss2d(reduction='none') (utils/loss2d.py:5-13), the pixel branch of Coteachingloss_dropimagedroppixel
+// (utils/coteach_loss.py:223-254: KLbidirection :85-92 + CE), Coteachingloss_dropregionce (:163-196) and
+// MulticlassMSELoss(reduction='none') (loss2d.py:109-117) return MAPS the calling script reduces itself; these kernels
+// produce the maps and their gradients in one pass each (two classes, as everywhere in the reference).
+namespace aide {
+
+// out[p] = [mode & 1] wc[t] * CE(z, t) (0 where t == ignore_index) + [mode & 2] KL(p1||p2) + KL(p2||p1)
+// two classes: KL(p||q) + KL(q||p) = (s1 - s2) * (d1 - d2) with d = z1 - z0, s = sigmoid(d)
+__global__ void pixel_loss_fwd_kernel(const float* __restrict__ l1, const float* __restrict__ l2,
+                                      const int64_t* __restrict__ tg, int HW, size_t total, float wc0, float wc1,
+                                      int ignore_index, int mode, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, p = i - n * HW, b = n * 2 * HW + p;
+    const float z0 = l1[b], z1 = l1[b + HW];
+    const long long t = tg[i];
+    float v = 0.f;
+    if ((mode & 1) && t != ignore_index) v += (t == 1 ? wc1 : wc0) * softplusf(t == 1 ? z0 - z1 : z1 - z0);
+    if (mode & 2) {
+      const float y0 = l2[b], y1 = l2[b + HW];
+      float a0, a1, b0, b1;
+      softmax2(z0, z1, a0, a1);
+      softmax2(y0, y1, b0, b1);
+      v += (a1 - b1) * ((z1 - z0) - (y1 - y0));
+    }
+    out[i] = v;
+  }
+}
+__global__ void pixel_loss_bwd_kernel(const float* __restrict__ l1, const float* __restrict__ l2,
+                                      const int64_t* __restrict__ tg, const float* __restrict__ gout, int HW, size_t total,
+                                      float wc0, float wc1, int ignore_index, int mode, float* __restrict__ d1,
+                                      float* __restrict__ d2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, p = i - n * HW, b = n * 2 * HW + p;
+    const float z0 = l1[b], z1 = l1[b + HW], g = gout[i];
+    const long long t = tg[i];
+    float a0, a1;
+    softmax2(z0, z1, a0, a1);
+    float gd1 = 0.f, gd2 = 0.f;                 // d/d(d1), d/d(d2)
+    if ((mode & 1) && t != ignore_index) gd1 += (t == 1 ? wc1 : wc0) * (a1 - (float)t);
+    if (mode & 2) {
+      const float y0 = l2[b], y1 = l2[b + HW];
+      float b0, b1;
+      softmax2(y0, y1, b0, b1);
+      const float dd = (z1 - z0) - (y1 - y0), ds = a1 - b1;
+      gd1 += a1 * a0 * dd + ds;
+      gd2 -= b1 * b0 * dd + ds;
+    }
+    d1[b] = -gd1 * g;
+    d1[b + HW] = gd1 * g;
+    if (d2) {
+      d2[b] = -gd2 * g;
+      d2[b + HW] = gd2 * g;
+    }
+  }
+}
+
+// out[n][k][p] = (softmax(z)[k] - target[n][k][p])^2   (two classes)
+__global__ void softmax_mse_fwd_kernel(const float* __restrict__ z, const float* __restrict__ tg, int HW, size_t npix,
+                                       float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, p = i - n * HW, b = n * 2 * HW + p;
+    float s0, s1;
+    softmax2(z[b], z[b + HW], s0, s1);
+    const float e0 = s0 - tg[b], e1 = s1 - tg[b + HW];
+    out[b] = e0 * e0;
+    out[b + HW] = e1 * e1;
+  }
+}
+__global__ void softmax_mse_bwd_kernel(const float* __restrict__ z, const float* __restrict__ tg,
+                                       const float* __restrict__ gout, int HW, size_t npix, float* __restrict__ dz) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, p = i - n * HW, b = n * 2 * HW + p;
+    float s0, s1;
+    softmax2(z[b], z[b + HW], s0, s1);
+    const float g0 = 2.f * (s0 - tg[b]) * gout[b], g1 = 2.f * (s1 - tg[b + HW]) * gout[b + HW];
+    const float gd = s1 * s0 * (g1 - g0);       // through softmax: d s1/dd = s1 s0, d s0/dd = -s1 s0
+    dz[b] = -gd;
+    dz[b + HW] = gd;
+  }
+}
+
+// max_pool2d(kernel = stride = (kh, kw), padding 0, ceil_mode) on NCHW planes, forward (+ argmax) and backward
+__global__ void maxpool_nchw_fwd_kernel(const float* __restrict__ x, int H, int W, int kh, int kw, int OH, int OW,
+                                        size_t total, float* __restrict__ y, int* __restrict__ arg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % OW), oh = (int)((i / OW) % OH);
+    const size_t plane = i / ((size_t)OW * OH);
+    const float* xp = x + plane * (size_t)H * W;
+    float m = -INFINITY;
+    int best = -1;
+    for (int yy = oh * kh; yy < min(H, oh * kh + kh); ++yy)
+      for (int xx = ow * kw; xx < min(W, ow * kw + kw); ++xx) {
+        const float v = xp[(size_t)yy * W + xx];
+        if (best < 0 || v > m || v != v) {            // first maximum wins, NaN propagates (ATen max_pool2d)
+          m = v;
+          best = yy * W + xx;
+        }
+      }
+    y[i] = m;
+    if (arg) arg[i] = best;
+  }
+}
+__global__ void maxpool_nchw_bwd_kernel(const float* __restrict__ gy, const int* __restrict__ arg, int HWin, int OHW,
+                                        size_t total, float* __restrict__ gx /* zero-initialised */) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t plane = i / OHW;
+    gx[plane * (size_t)HWin + arg[i]] = gy[i];        // windows do not overlap (stride = kernel): no atomics needed
+  }
+}
+
+static int grid1d(size_t total) {
+  long long b = (long long)((total + 255) / 256);
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace aide
+
+extern "C" int aide_pixel_loss_fwd(const float* logits1, const float* logits2, const int64_t* targets, int N, int H, int W,
+                                   float wc0, float wc1, int ignore_index, int mode, float* out, void* stream) {
+  AIDE_REQUIRE(logits1 && targets && out && N > 0 && H > 0 && W > 0 && (mode & 3) && (!(mode & 2) || logits2),
+               "pixel_loss_fwd: bad arguments (mode bit 0 = CE, bit 1 = bidirectional KL, which needs logits2)");
+  const size_t total = (size_t)N * H * W;
+  aide::pixel_loss_fwd_kernel<<<aide::grid1d(total), 256, 0, as_stream(stream)>>>(logits1, logits2, targets, H * W, total, wc0,
+                                                                                  wc1, ignore_index, mode, out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int aide_pixel_loss_bwd(const float* logits1, const float* logits2, const int64_t* targets, const float* gout,
+                                   int N, int H, int W, float wc0, float wc1, int ignore_index, int mode, float* dlogits1,
+                                   float* dlogits2, void* stream) {
+  AIDE_REQUIRE(logits1 && targets && gout && dlogits1 && (mode & 3) && (!(mode & 2) || logits2), "pixel_loss_bwd: bad arguments");
+  const size_t total = (size_t)N * H * W;
+  aide::pixel_loss_bwd_kernel<<<aide::grid1d(total), 256, 0, as_stream(stream)>>>(logits1, logits2, targets, gout, H * W, total,
+                                                                                  wc0, wc1, ignore_index, mode, dlogits1,
+                                                                                  dlogits2);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int aide_softmax_mse_fwd(const float* logits, const float* target, int N, int H, int W, float* out, void* stream) {
+  AIDE_REQUIRE(logits && target && out && N > 0, "softmax_mse_fwd: bad arguments");
+  const size_t npix = (size_t)N * H * W;
+  aide::softmax_mse_fwd_kernel<<<aide::grid1d(npix), 256, 0, as_stream(stream)>>>(logits, target, H * W, npix, out);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int aide_softmax_mse_bwd(const float* logits, const float* target, const float* gout, int N, int H, int W,
+                                    float* dlogits, void* stream) {
+  AIDE_REQUIRE(logits && target && gout && dlogits && N > 0, "softmax_mse_bwd: bad arguments");
+  const size_t npix = (size_t)N * H * W;
+  aide::softmax_mse_bwd_kernel<<<aide::grid1d(npix), 256, 0, as_stream(stream)>>>(logits, target, gout, H * W, npix, dlogits);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int aide_maxpool_nchw_fwd(const float* x, int planes, int H, int W, int kh, int kw, float* y, int* argmax,
+                                     void* stream) {
+  AIDE_REQUIRE(x && y && planes > 0 && H > 0 && W > 0 && kh > 0 && kw > 0, "maxpool_nchw_fwd: bad arguments");
+  const int OH = (H + kh - 1) / kh, OW = (W + kw - 1) / kw;
+  const size_t total = (size_t)planes * OH * OW;
+  aide::maxpool_nchw_fwd_kernel<<<aide::grid1d(total), 256, 0, as_stream(stream)>>>(x, H, W, kh, kw, OH, OW, total, y, argmax);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int aide_maxpool_nchw_bwd(const float* gy, const int* argmax, int planes, int H, int W, int kh, int kw, float* gx,
+                                     void* stream) {
+  AIDE_REQUIRE(gy && argmax && gx && planes > 0, "maxpool_nchw_bwd: bad arguments");
+  const int OH = (H + kh - 1) / kh, OW = (W + kw - 1) / kw;
+  const size_t total = (size_t)planes * OH * OW;
+  AIDE_CUDA(cudaMemsetAsync(gx, 0, (size_t)planes * H * W * sizeof(float), as_stream(stream)));
+  aide::maxpool_nchw_bwd_kernel<<<aide::grid1d(total), 256, 0, as_stream(stream)>>>(gy, argmax, H * W, OH * OW, total, gx);
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}

@@ -149,6 +149,93 @@ class _BatchLoss(torch.autograd.Function):
         return d, None, None, None, None, None, None, None
 
 
+class _PixelLossMap(torch.autograd.Function):
+    """[N,H,W] map: (mode & 1) class-weighted cross-entropy + (mode & 2) bidirectional KL between two logit tensors."""
+
+    @staticmethod
+    def forward(ctx, logits1, logits2, targets, class_w, ignore_index, mode):
+        N, _, H, W = logits1.shape
+        out = torch.empty((N, H, W), dtype=torch.float32, device=logits1.device)
+        call("aide_pixel_loss_fwd", logits1.data_ptr(), logits2.data_ptr() if logits2 is not None else None,
+             targets.data_ptr(), N, H, W, class_w[0], class_w[1], ignore_index, mode, out.data_ptr(), _stream())
+        ctx.save_for_backward(logits1, logits2 if logits2 is not None else logits1, targets)
+        ctx.cfg = (class_w, ignore_index, mode, logits2 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        l1, l2, targets = ctx.saved_tensors
+        class_w, ignore_index, mode, has2 = ctx.cfg
+        N, _, H, W = l1.shape
+        go = go.contiguous().float()
+        d1 = torch.empty_like(l1)
+        d2 = torch.empty_like(l2) if (has2 and ctx.needs_input_grad[1]) else None
+        call("aide_pixel_loss_bwd", l1.data_ptr(), l2.data_ptr() if has2 else None, targets.data_ptr(), go.data_ptr(), N, H,
+             W, class_w[0], class_w[1], ignore_index, mode, d1.data_ptr(), d2.data_ptr() if d2 is not None else None,
+             _stream())
+        return d1, d2, None, None, None, None
+
+
+def pixel_loss_map(logits1, targets, logits2=None, class_w=(1.0, 1.0), ignore_index=255, ce=True, kl=False):
+    """Per-pixel loss map [N,H,W] on the fused kernels (CrossEntropyLoss2d('none'), coteach_loss.py's drop map)."""
+    l1, t = _check(logits1, targets)
+    l2 = None
+    if kl:
+        l2, _ = _check(logits2, targets)
+    return _PixelLossMap.apply(l1, l2, t, class_w, ignore_index, (1 if ce else 0) | (2 if kl else 0))
+
+
+class _SoftmaxMSE(torch.autograd.Function):
+    """(softmax(z, 1) - target)^2 elementwise, [N,2,H,W] (MulticlassMSELoss, loss2d.py:109-117)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        N, _, H, W = logits.shape
+        out = torch.empty_like(logits)
+        call("aide_softmax_mse_fwd", logits.data_ptr(), target.data_ptr(), N, H, W, out.data_ptr(), _stream())
+        ctx.save_for_backward(logits, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        logits, target = ctx.saved_tensors
+        N, _, H, W = logits.shape
+        go = go.contiguous().float()
+        d = torch.empty_like(logits)
+        call("aide_softmax_mse_bwd", logits.data_ptr(), target.data_ptr(), go.data_ptr(), N, H, W, d.data_ptr(), _stream())
+        return d, None
+
+
+class _MaxPoolNCHW(torch.autograd.Function):
+    """max_pool2d(kernel = stride = k, ceil_mode=True) on NCHW fp32 (coteach_loss.py:170-178)."""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw):
+        N, Cc, H, W = x.shape
+        OH, OW = -(-H // kh), -(-W // kw)
+        y = torch.empty((N, Cc, OH, OW), dtype=torch.float32, device=x.device)
+        arg = torch.empty((N, Cc, OH, OW), dtype=torch.int32, device=x.device)
+        call("aide_maxpool_nchw_fwd", x.data_ptr(), N * Cc, H, W, kh, kw, y.data_ptr(), arg.data_ptr(), _stream())
+        ctx.save_for_backward(arg)
+        ctx.cfg = (N * Cc, H, W, kh, kw, x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (arg,) = ctx.saved_tensors
+        planes, H, W, kh, kw, shape = ctx.cfg
+        gx = torch.empty(shape, dtype=torch.float32, device=gy.device)
+        call("aide_maxpool_nchw_bwd", gy.contiguous().float().data_ptr(), arg.data_ptr(), planes, H, W, kh, kw, gx.data_ptr(),
+             _stream())
+        return gx, None, None
+
+
+def maxpool_nchw(x: torch.Tensor, kh: int, kw: int) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("aide_b200 runs on CUDA only (there is no CPU fallback)")
+    return _MaxPoolNCHW.apply(x.contiguous().float(), int(kh), int(kw))
+
+
 # -------------------------------------------------------------------------------------------------
 # drop-in classes (constructor signatures as in utils/loss2d.py)
 # -------------------------------------------------------------------------------------------------
@@ -161,9 +248,7 @@ class CrossEntropyLoss2d(nn.Module):
     def forward(self, inputs, targets):
         logits, targets = _check(inputs, targets)
         if self.reduction == "none":
-            # per-pixel map: not on the hot path (CEMDiceLossImage fuses it); plain tensor plumbing
-            w = torch.tensor(self.class_w, dtype=logits.dtype, device=logits.device)
-            return F.cross_entropy(logits, targets, weight=w, reduction="none", ignore_index=self.ignore_index)
+            return _PixelLossMap.apply(logits, None, targets, self.class_w, self.ignore_index, 1)     # [N,H,W] map
         return _BatchLoss.apply(logits, targets, 1.0, 0.0, self.class_w, 1.0, self.ignore_index, self.reduction)
 
 
@@ -215,8 +300,14 @@ class MulticlassMSELoss(nn.Module):
         self.reduction = reduction
 
     def forward(self, input, target):
-        # elementwise map; the fused weighted form used by the AIDE step is coteach_step() below
-        return F.mse_loss(F.softmax(input, dim=1), target, reduction=self.reduction)
+        # one kernel for softmax -> difference -> square (and one for its gradient); the AIDE step's weighted form is
+        # fused further in coteach_step() below
+        if not input.is_cuda:
+            raise RuntimeError("aide_b200 losses run on CUDA only (there is no CPU fallback)")
+        if input.dim() != 4 or input.shape[1] != 2 or target.shape != input.shape:
+            raise NotImplementedError("MulticlassMSELoss needs logits and targets [N,2,H,W] (two classes)")
+        m = _SoftmaxMSE.apply(input.contiguous().float(), target.detach().contiguous().float())
+        return {"none": m, "mean": m.mean(), "sum": m.sum()}[self.reduction]
 
 
 class CEMDiceLoss(nn.Module):

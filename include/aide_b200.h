@@ -261,6 +261,24 @@ int aide_loss_bwd(const float* logits, const int64_t* targets, const float* q, c
                   const double* sums, const float* a_ce, const float* a_dice, const float* a_mse,
                   int N, int H, int W, float wc0, float wc1, int ignore_index, float smooth,
                   float* dlogits, void* stream);
+/* Per-pixel MAPS of the drop-in loss classes (two classes; NCHW fp32 logits, int64 targets) and their gradients:
+ *   aide_pixel_loss_*: mode bit 0 -> wc[t] * cross-entropy (CrossEntropyLoss2d(reduction='none'), loss2d.py:5-13; 0 at
+ *     ignore_index); bit 1 -> + KL(p1||p2) + KL(p2||p1) of the two softmaxes (KLbidirection, coteach_loss.py:85-92) --
+ *     together the "drop" map of Coteachingloss_dropimagedroppixel (coteach_loss.py:231-233).  out / gout: [N,H,W].
+ *   aide_softmax_mse_*: (softmax(z) - target)^2, MulticlassMSELoss(reduction='none') (loss2d.py:109-117); [N,2,H,W].
+ *   aide_maxpool_nchw_*: max_pool2d(kernel = stride = (kh, kw), ceil_mode=True) on NCHW planes with arg-max for the
+ *     backward routing (Coteachingloss_dropregionce pools logits and targets, coteach_loss.py:170-178). */
+int aide_pixel_loss_fwd(const float* logits1, const float* logits2, const int64_t* targets, int N, int H, int W,
+                        float wc0, float wc1, int ignore_index, int mode, float* out, void* stream);
+int aide_pixel_loss_bwd(const float* logits1, const float* logits2, const int64_t* targets, const float* gout,
+                        int N, int H, int W, float wc0, float wc1, int ignore_index, int mode,
+                        float* dlogits1, float* dlogits2, void* stream);
+int aide_softmax_mse_fwd(const float* logits, const float* target, int N, int H, int W, float* out, void* stream);
+int aide_softmax_mse_bwd(const float* logits, const float* target, const float* gout, int N, int H, int W,
+                         float* dlogits, void* stream);
+int aide_maxpool_nchw_fwd(const float* x, int planes, int H, int W, int kh, int kw, float* y, int* argmax, void* stream);
+int aide_maxpool_nchw_bwd(const float* gy, const int* argmax, int planes, int H, int W, int kh, int kw, float* gx,
+                          void* stream);
 /* softmax of n_aug logit tensors, mean, sharpen p^expo / sum, weight map 1-4*q0*q1
  * (trainchaos_proposed_30cases1labeled.py:274-292,97-101). */
 int aide_pseudo_label(const float* const* aug_logits, int n_aug, int N, int H, int W, float expo,

@@ -538,3 +538,55 @@ def test_forward_augmentation_matches_pil_bit_for_bit(dev, oracle):
     augset, views = A.augmented_views(u1, u1, m, s_, m, s_, rng=random.Random(7))
     assert len(views) == 4 and views[0][0].shape == (2, 3, 32, 32) and augset["augno"] == [4, 4]
     assert all(-60.0 <= d < 60.0 for k in range(1, 5) for d in augset[f"degree{k}"])
+
+
+def test_pixel_loss_maps_against_autograd(dev):
+    """The per-pixel maps behind CrossEntropyLoss2d('none'), MulticlassMSELoss('none'), the KL + CE drop map of
+    Coteachingloss_dropimagedroppixel and the ceil-mode max-pool of Coteachingloss_dropregionce: values and gradients
+    against the reference formulas evaluated by torch on the CPU (utils/loss2d.py:5-13,109-117, coteach_loss.py:85-92)."""
+    import aide_b200 as A
+    from aide_b200.losses import maxpool_nchw, pixel_loss_map
+    g = torch.Generator().manual_seed(9)
+    N, H, W = 3, 20, 28
+    a = (torch.randn(N, 2, H, W, generator=g) * 2).requires_grad_()
+    b = (torch.randn(N, 2, H, W, generator=g) * 2).requires_grad_()
+    t = (torch.rand(N, H, W, generator=g) < 0.3).long()
+    t[0, :3] = 255                                                    # ignored pixels
+    up = torch.randn(N, H, W, generator=g)
+    # cross-entropy map with class weights and ignore_index
+    wcl = torch.tensor([0.3, 1.7])
+    ref = F.nll_loss(F.log_softmax(a, dim=1), t, weight=wcl, reduction="none", ignore_index=255)
+    ga_ref, = torch.autograd.grad((ref * up).sum(), a)
+    ad = a.detach().to(dev).requires_grad_()
+    got = A.CrossEntropyLoss2d(weight=wcl, reduction="none")(ad, t.to(dev))
+    (got * up.to(dev)).sum().backward()
+    assert relmax(got, ref.detach()) < 1e-5 and relmax(ad.grad, ga_ref) < 1e-5
+    # bidirectional KL + CE (no ignore: coteach_loss.py uses plain nll_loss)
+    t2 = (torch.rand(N, H, W, generator=g) < 0.3).long()
+    pa, pb = F.softmax(a, dim=1), F.softmax(b, dim=1)
+    kl = (pa * torch.log(pa / pb)).sum(1) + (pb * torch.log(pb / pa)).sum(1)
+    ref = kl + F.nll_loss(F.log_softmax(a, dim=1), t2, reduction="none")
+    ga_ref, gb_ref = torch.autograd.grad((ref * up).sum(), [a, b])
+    ad, bd = a.detach().to(dev).requires_grad_(), b.detach().to(dev).requires_grad_()
+    got = pixel_loss_map(ad, t2.to(dev), logits2=bd, kl=True)
+    (got * up.to(dev)).sum().backward()
+    assert relmax(got, ref.detach()) < 2e-5 and relmax(ad.grad, ga_ref) < 2e-5 and relmax(bd.grad, gb_ref) < 2e-5
+    # MulticlassMSELoss
+    q = F.softmax(torch.randn(N, 2, H, W, generator=g), dim=1)
+    up4 = torch.randn(N, 2, H, W, generator=g)
+    ref = F.mse_loss(F.softmax(a, dim=1), q, reduction="none")
+    ga_ref, = torch.autograd.grad((ref * up4).sum(), a)
+    ad = a.detach().to(dev).requires_grad_()
+    got = A.MulticlassMSELoss(reduction="none")(ad, q.to(dev))
+    (got * up4.to(dev)).sum().backward()
+    assert relmax(got, ref.detach()) < 1e-5 and relmax(ad.grad, ga_ref) < 1e-5
+    assert abs(A.MulticlassMSELoss()(a.detach().to(dev), q.to(dev)).item() - ref.mean().item()) < 1e-6
+    # ceil-mode max-pool with stride = kernel (odd sizes: partial windows at the border)
+    x = torch.randn(2, 2, 21, 30, generator=g).requires_grad_()
+    ref = F.max_pool2d(x, kernel_size=(2, 4), stride=(2, 4), padding=0, ceil_mode=True)
+    upp = torch.randn(ref.shape, generator=g)
+    gx_ref, = torch.autograd.grad((ref * upp).sum(), x)
+    xd = x.detach().to(dev).requires_grad_()
+    got = maxpool_nchw(xd, 2, 4)
+    (got * upp.to(dev)).sum().backward()
+    assert torch.equal(got.detach().cpu(), ref.detach()) and torch.equal(xd.grad.cpu(), gx_ref)
