@@ -563,7 +563,7 @@ class GradLayout:
 
 def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: Layout,
                  params: Dict[str, torch.Tensor], weights: PreparedWeights, arena: torch.Tensor,
-                 dlogits: torch.Tensor, grad_flat: torch.Tensor, group: int = 0) -> None:
+                 dlogits: torch.Tensor, grad_flat: torch.Tensor, group: int = 0, on_done=None) -> None:
     """Writes every parameter gradient into `grad_flat` (fp32, laid out by `glayout`).  `group`: which statistics group
     of a stacked-batch forward the backward runs through (the train forward rides as the LAST group of the stacked
     pseudo-label forward, AideTrainer); its images, raw conv outputs and BatchNorm statistics are slices of the tape."""
@@ -648,6 +648,8 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             call("aide_conv1x1_bwd", fmt, x0, x1, xct, xco, cin, params["last_conv1.weight"].data_ptr(),
                  dlogits.data_ptr(), plan.num_classes, N, H, W, bb + off["dx:head"], gptr("last_conv1.weight"),
                  bb + off["headpart"], st)
+            if on_done is not None:
+                on_done("head")
         elif isinstance(op, Upsample):
             # the (single) consumer of op.dst is the up-conv unit; its dX is the high-resolution gradient
             consumer = next(u for u in plan.units if u.src[0] == op.dst)
@@ -679,6 +681,8 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
                  gptr(f"{a.name}.conv2.weight"), gptr(f"{a.name}.conv2.bias"), gptr(f"{a.name}.conv3.weight"),
                  gptr(f"{a.name}.conv3.bias"), gptr(f"{a.name}.conv4.weight"), gptr(f"{a.name}.conv4.bias"),
                  gptr(f"{a.name}.bn.bias"), st)
+            if on_done is not None:
+                on_done(a.name)
         elif isinstance(op, Unit):
             u = op
             h, w = H >> u.level, W >> u.level
@@ -713,3 +717,35 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
                 w0, w1 = weights.dgrad(u, fmt)
                 call("aide_conv3x3_dgrad", fmt, dz0, dz1, u.cout, w0, w1, dz_inv,
                      bb + off["dx:" + u.name], u.cin, 0, u.cin, N, h, w, st)
+            if on_done is not None:
+                on_done(u.name)
+
+
+def gradient_buckets(plan: Plan, glayout: GradLayout, n_buckets: int = 4):
+    """Split the flat gradient buffer into ranges that become final one after the other while the backward pass walks
+    the network from the head to the first encoder level: [(trigger, [(lo, hi), ...]), ...] in completion order --
+    after the unit / gate `trigger` is done, every listed float range holds final gradients.  The flat layout follows
+    the forward order of the units, so the ranges of the units are suffixes cut at level boundaries (the decoder's
+    ~16 M and the deepest encoder level's ~8 M parameters are ready before the expensive high-resolution encoder
+    levels run their backward); attention-gate and head parameters live behind the units and travel with the LAST bucket
+    (the first level's gate finishes just before the end)."""
+    units = plan.units
+    first_off = {u.name: glayout.off[u.conv + ".weight"][0] for u in units}
+    tail_start = min([glayout.off[f"{a.name}.conv1.weight"][0] for a in plan.atts] + [glayout.off["last_conv1.weight"][0]])
+    # cut points: the first unit (in forward order) of the decoder and of the deepest encoder levels
+    dec0 = next(u for u in units if u.name.startswith("up_block1"))
+    cuts = [dec0]
+    level_first = {}
+    for u in units:
+        if not u.name.startswith("up_block"):
+            level_first.setdefault(u.level, u)
+    for lvl in sorted(level_first, reverse=True)[:max(n_buckets - 2, 0)]:
+        cuts.append(level_first[lvl])
+    out, hi = [], tail_start
+    for u in cuts:
+        lo = first_off[u.name]
+        if lo < hi:
+            out.append((u.name, [(lo, hi)]))
+            hi = lo
+    out.append((units[0].name, [(0, hi), (tail_start, glayout.total)]))
+    return out

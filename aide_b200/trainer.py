@@ -96,6 +96,11 @@ class AideTrainer:
         self.rate_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._rate_uploaded = None
         self.max_graphs = max_graphs
+        # gradient all-reduce in buckets launched while the backward pass is still running (decoder first); 0 / 1 = one
+        # all-reduce per net after its backward
+        self.n_buckets = int(os.environ.get("AIDE_B200_BUCKETS", "4"))
+        self._buckets = {id(n): {t: r for t, r in E.gradient_buckets(n._plan, n._glayout, self.n_buckets)}
+                         for n in (self.net1, self.net2)}
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
         self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
         # ... and the train forward as one more group of that stacked forward (train-mode views only, i.e. the chaos flavour)
@@ -255,10 +260,22 @@ class AideTrainer:
             has_q = other["q"] is not None
             d = L.loss_backward(lg, t_other, me["sums"], coef[0], coef[1], coef[2] if has_q else None,
                                 other["q"], other["w"])
-            net._engine_backward(me["tape"], d)
+            works = []
+            bucketed = self.world > 1 and self.n_buckets > 1
+            if bucketed:
+                ranges = self._buckets[id(net)]
+
+                def on_done(name):                 # these float ranges of the flat gradient are final: reduce them now
+                    for lo, hi in ranges.get(name, ()):
+                        works.append(torch.distributed.all_reduce(net.last_grad_flat[lo:hi], group=self.group,
+                                                                  async_op=True))
+            net._engine_backward(me["tape"], d, on_done if bucketed else None)
             flat = net.last_grad_flat
             if self.world > 1:
-                torch.distributed.all_reduce(flat, group=self.group)
+                if not bucketed:
+                    torch.distributed.all_reduce(flat, group=self.group)
+                for w_ in works:
+                    w_.wait()
                 if self.global_select:             # the scalar was this rank's share of the global loss
                     torch.distributed.all_reduce(loss, group=self.group)
             # local selection: mean of the per-rank gradients; global selection: the coefficients already carry the

@@ -207,3 +207,31 @@ def test_trainer_reverse_aug_parameters_follow_pil(oracle):
             mode, m = oracle.rotate_matrix(0 - augset[f"degree{v + 1}"][b], 64, 64)
             assert int(modes[v, b]) == mode and mats[v, b].tolist() == m
             assert int(flips[v, b]) == augset[f"hflip{v + 1}"][b]
+
+
+def test_gradient_buckets_cover_the_flat_buffer_in_completion_order():
+    """Bucketed all-reduce: the float ranges handed to NCCL while the backward is still running must
+    tile the flat gradient buffer exactly once, and every range must be final when its trigger unit is done -- i.e. all
+    parameters inside it belong to units the backward pass (reverse forward order) has already visited."""
+    from aide_b200 import engine as E
+    for plan in (E.plan_fuseunet(2), E.plan_unet(2), E.plan_fuseunet(2, attention=True), E.plan_unet(2, attention=True)):
+        gl = E.GradLayout(plan)
+        buckets = E.gradient_buckets(plan, gl, 4)
+        cov = sorted(r for _, rs in buckets for r in rs)
+        assert cov[0][0] == 0 and cov[-1][1] == gl.total
+        assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
+        order = [u.name for u in reversed(plan.units)]                     # backward visiting order of the units
+        done_at = {name: i for i, name in enumerate(order)}
+        owner = {}                                                          # parameter -> unit / gate that finishes it
+        for u in plan.units:
+            for k in (u.conv + ".weight", u.conv + ".bias", u.bn + ".weight", u.bn + ".bias"):
+                owner[k] = u.name
+        last_trigger = buckets[-1][0]
+        for trig, ranges in buckets:
+            for lo, hi in ranges:
+                for name, (off, shape) in gl.off.items():
+                    if lo <= off < hi and name in owner:
+                        assert done_at[owner[name]] <= done_at[trig], (plan.kind, trig, name)
+                    if lo <= off < hi and name not in owner:               # gates / head: only in the last bucket
+                        assert trig == last_trigger, (plan.kind, trig, name)
+        assert [t for t, _ in buckets] == sorted([t for t, _ in buckets], key=lambda t: done_at[t])

@@ -59,6 +59,54 @@ for graph in (False, True):
         assert not torch.equal(mine, p0)
     dist.barrier()
     print(f"[rank {rank}] graph={graph} ok", flush=True)
+# (3) nn.DataParallel semantics (global_select=True): the per-image losses of all ranks are gathered, the small-loss
+# sort and the clean / rest split are global, gradients add up.  Reference emulation with the oracle: every shard runs
+# its own forward (replica-local BatchNorm statistics, as DataParallel does), outputs are concatenated and the loss of
+# trainchaos_proposed_30cases1labeled.py:303-321 is evaluated on the global batch.
+tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=False, global_select=True)
+tr.broadcast_parameters(0)
+x, t1, t2, augs = shard(rank)
+m = tr.step(x, t1, t2, augs, 0.25)
+torch.cuda.synchronize()
+flat = tr.net1.last_grad_flat.clone()
+other = flat.clone()
+dist.broadcast(other, 0)
+assert torch.equal(flat, other), "all-reduced gradients differ between ranks"
+if rank == 0:
+    torch.manual_seed(2)
+    p1 = O.clone_params(O.init_fuseunet(2), requires_grad=True)
+    p2 = O.clone_params(O.init_fuseunet(2), requires_grad=True)
+    outs1, outs2, q1s, w1s, q2s, w2s, t1s, t2s = [], [], [], [], [], [], [], []
+    for r in range(world):
+        (x1, x2), a, b, au = O.synthetic_batch(B, S, S, seed=300 + r, n_aug=2)
+        with torch.no_grad():
+            a1 = [O.fuseunet_forward(p1, *v, training=True) for v in au]
+            a2 = [O.fuseunet_forward(p2, *v, training=True) for v in au]
+        q1, w1 = O.pseudo_label(a1)
+        q2, w2 = O.pseudo_label(a2)
+        outs1.append(O.fuseunet_forward(p1, x1, x2, training=True))
+        outs2.append(O.fuseunet_forward(p2, x1, x2, training=True))
+        for lst, v in ((q1s, q1), (w1s, w1), (q2s, q2), (w2s, w2), (t1s, a), (t2s, b)):
+            lst.append(v)
+    cat = lambda l: torch.cat(l, 0)
+    res = O.coteach_losses(cat(outs1), cat(outs2), cat(t1s), cat(t2s), cat(q1s), cat(w1s), cat(q2s), cat(w2s), 0.25,
+                           n_clean=2)
+    names = [k for k in p1 if not O.is_buffer(k)]
+    g1 = dict(zip(names, torch.autograd.grad(res["loss1"], [p1[k] for k in names])))
+    assert torch.equal(m["indx1"].cpu(), res["indx1"]) and torch.equal(m["indx2"].cpu(), res["indx2"]), "global argsort"
+    assert abs(m["loss1"].item() - res["loss1"].item()) < 2e-5 * max(1.0, abs(res["loss1"].item())), (m["loss1"].item(), res["loss1"].item())
+    gl = tr.net1._glayout
+    e = gl.view(flat, "last_conv1.weight").cpu()
+    rel = ((e - g1["last_conv1.weight"]).abs().max() / g1["last_conv1.weight"].abs().max()).item()
+    assert rel < 1e-3, rel
+    live = [k for k in names if not k.endswith(("block.conv1.bias", "block.conv2.bias", "bilinear_up.1.bias"))]
+    fa = torch.cat([gl.view(flat, k).cpu().double().flatten() for k in live])
+    fb = torch.cat([g1[k].double().flatten() for k in live])
+    gap = 1.0 - torch.nn.functional.cosine_similarity(fa, fb, dim=0).item()
+    assert gap < 1e-3, gap
+    print(f"[rank 0] global_select ok: loss1 {m['loss1'].item():.6f} vs {res['loss1'].item():.6f}, last_conv1 grad rel {rel:.1e}, "
+          f"1-cos {gap:.1e}", flush=True)
+dist.barrier()
 torch.cuda.synchronize()
 if rank == 0:
     print("DDP_CHECK_OK", flush=True)
