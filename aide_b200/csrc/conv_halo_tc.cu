@@ -443,7 +443,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct HaloPlan {
-  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack, resident;
+  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack, resident, occ;   // occ: CTAs per SM (1 or 2)
   int a_slot, a_stage, b_plane, b_stage, smem;
   double cost;
 };
@@ -513,7 +513,7 @@ double model_cost(const CostModel& m, const HaloPlan& c, int npl, int n_cchunks,
 // Measured tilings (tools/halo_probe.py --sweep-full on B200 -> tools/make_plan_table.py): the best (cout tile, pixel-tile
 // blocking, stacked planes, row width) for the layer shapes of fuseunet / UNet at the batches the AIDE step launches.
 struct PlanEntry {
-  int fmt, cin, cout, m_tiles, BN, MB, stack, rb;
+  int fmt, cin, cout, m_tiles, BN, MB, stack, rb, occ;
 };
 constexpr PlanEntry kPlanTable[] = {
 #include "conv_plan_table.inc"
@@ -541,12 +541,15 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
   // every layer they fit (profiles/r2c_*: 64->64 @256 235 vs 311 TFLOP/s) -- the Cout <= 64 layers are bound by
   // shared-memory operand reads per MMA, not by the weight re-fetch.
   const int force_res = env_int("AIDE_CONV_WRES", 0);
-  if (use_table && !force_bn && !force_mb && force_stack < 0 && !force_rb && force_res == 0 &&
+  // Two CTAs per SM (half the shared memory, <= 256 TMEM columns each): a second resident CTA issues MMAs while the
+  // first waits on its barriers -- pays on the narrow layers whose tensor pipe idles between short MMAs.  1 / 2 force it.
+  int force_occ = env_int("AIDE_CONV_OCC", 0);
+  if (use_table && !force_bn && !force_mb && force_stack < 0 && !force_rb && force_res == 0 && !force_occ &&
       env_int("AIDE_CONV_TABLE", 1)) {
     if (const PlanEntry* e = lookup_plan(fmt, cin, cout, m_tiles)) {
       // build exactly the measured tiling through the same enumeration (forced parameters); fall back to the model
       // if it does not fit (cannot happen for the shapes it was measured on)
-      force_bn = e->BN; force_mb = e->MB; force_stack = e->stack; force_rb = e->rb;
+      force_bn = e->BN; force_mb = e->MB; force_stack = e->stack; force_rb = e->rb; force_occ = e->occ;
     }
   }
   best->cost = -1;
@@ -563,6 +566,8 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
         if (force_rb && rb != force_rb) continue;
         const int n_cchunks = cin / kc;
         const int nks = rb / 32;
+       for (int occ = 1; occ <= 2; ++occ) {
+       if ((force_occ ? force_occ : 1) != occ) continue;          // the cost model never picks 2 by itself: table / env only
        for (int stack = 0; stack <= 1; ++stack) {
         if (stack && (npl != 2 || 2 * bn > 256)) continue;
         if (force_stack >= 0 && stack != force_stack && !(stack == 0 && (npl != 2 || 2 * bn > 256))) continue;
@@ -573,15 +578,16 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
         const long long chain = (long long)9 * n_cchunks * nks * (npl == 2 ? (stack ? (losep ? 1 : 2) : 3) : 1);
         const int nacc = wanted_nacc(fmt, chain);
         const int acc_w = bn * (1 + stack);
-        if (mb * nacc * acc_w > 512) continue;
+        const int tmem_max = occ == 2 ? 256 : 512;
+        if (mb * nacc * acc_w > tmem_max) continue;
         HaloPlan c{};
-        c.BN = bn; c.MB = mb; c.nacc = nacc; c.row_bytes = rb; c.stack = stack;
-        c.nbuf = (2 * mb * nacc * acc_w <= 512) ? 2 : 1;
+        c.BN = bn; c.MB = mb; c.nacc = nacc; c.row_bytes = rb; c.stack = stack; c.occ = occ;
+        c.nbuf = (2 * mb * nacc * acc_w <= tmem_max) ? 2 : 1;
         c.a_slot = (kHaloPix * rb + 1023) / 1024 * 1024;
         c.a_stage = npl * mb * c.a_slot;
         c.b_plane = bn * rb;
         c.b_stage = npl * c.b_plane;
-        const int avail = kSmemMax - 1024 - kBarBytes;
+        const int avail = (occ == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 1024 - kBarBytes;   // 1 KB per CTA is reserved by the system
         c.a_stages = 2;
         int rest = avail - c.a_stages * c.a_stage;
         if (rest < 2 * c.b_stage) {                                // try a single halo stage before giving up
@@ -621,6 +627,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
             pick.cost = model_cost(kSel, r, npl, n_cchunks, nks, m_tiles, cout);
           }
         }
+       }
        }
       }
       if (pick_row_cost < 0) continue;
@@ -714,7 +721,8 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
     if (act_tmap(&p.tmA1, dtype, x1, x_ctot, x_coff, cin, N, H, W, p.kc, kHW, kHH, p.row_bytes)) return 1;
     if (mat_tmap(&p.tmB1, dtype, w1, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
   }
-  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
+  const int max_ctas = kNumSMs * (pl.occ == 2 ? 2 : 1);
+  const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;
   if (kind == K_BF16) return launch<K_BF16>(p, grid, pl.smem, st);
   if (kind == K_F16X2) return launch<K_F16X2>(p, grid, pl.smem, st);
   return launch<K_TF32X2>(p, grid, pl.smem, st);
@@ -726,7 +734,7 @@ extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, 
   HaloPlan pl;
   make_plan(fmt, cin, cout, (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH), &pl);
   out[0] = pl.BN; out[1] = pl.MB; out[2] = pl.nacc; out[3] = pl.nbuf; out[4] = pl.row_bytes; out[5] = pl.a_stages;
-  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack + 2 * pl.resident;
+  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack + 2 * pl.resident + 4 * (pl.occ == 2);
   return 0;
 }
 

@@ -42,6 +42,21 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* p0, voi
   }
 }
 
+// Network inputs: [N,3,H,W] fp32 -> [N,H,W,3] fp32 (the only layout change on the step's input side).  The generic tile
+// transpose above runs at 3/32 channel occupancy (155 GB/s measured); here a thread owns 4 consecutive pixels: three
+// 128-bit plane reads, three 128-bit interleaved writes, both fully coalesced.
+__global__ void nchw3_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t HW4, size_t total4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW4, q = i - n * HW4;                 // 4-pixel group q of image n
+    const float4* s = reinterpret_cast<const float4*>(src) + n * 3 * HW4 + q;
+    const float4 r = s[0], g = s[HW4], b = s[2 * HW4];
+    float4* d = reinterpret_cast<float4*>(dst) + (n * HW4 + q) * 3;
+    d[0] = make_float4(r.x, g.x, b.x, r.y);
+    d[1] = make_float4(g.y, b.y, r.z, g.z);
+    d[2] = make_float4(b.z, r.w, g.w, b.w);
+  }
+}
+
 template <int FMT>
 __global__ void nhwc_to_nchw_kernel(const void* p0, const void* p1, int ctot, int coff, float* __restrict__ dst,
                                     int C, int HW) {
@@ -166,6 +181,15 @@ extern "C" int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* 
                                  int N, int C, int H, int W, void* stream) {
   AIDE_REQUIRE(src && dst_p0 && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
   AIDE_REQUIRE(fmt_planes(fmt) == 1 || dst_p1, "nchw_to_nhwc: TF32X2 / F16X2 need two planes");
+  if (fmt == AIDE_FMT_F32 && C == 3 && dst_ctot == 3 && dst_coff == 0 && ((size_t)H * W) % 4 == 0 &&
+      ((uintptr_t)src | (uintptr_t)dst_p0) % 16 == 0) {
+    const size_t HW4 = (size_t)H * W / 4, total4 = HW4 * N;
+    long long blocks = (long long)((total4 + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    nchw3_to_nhwc_f32_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, reinterpret_cast<float*>(dst_p0), HW4, total4);
+    AIDE_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid(ceil_div((long long)H * W, 32), ceil_div(C, 32), N), block(32, 8);
   AIDE_DISPATCH_FMT(fmt, (nchw_to_nhwc_kernel<FMT><<<grid, block, 0, as_stream(stream)>>>(
                              src, dst_p0, dst_p1, dst_ctot, dst_coff, C, H * W)));

@@ -53,7 +53,7 @@ def plan(fmt, cin, cout, N, H, W):
     if A.lib.aide_conv3x3_plan_info(fmt, cin, cout, N, H, W, out):
         return None
     return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6], stack=out[8] & 1,
-                res=out[8] >> 1)
+                res=(out[8] >> 1) & 1, occ=2 if out[8] & 4 else 1)
 
 
 def check(fmt, N, H, W, cin, cout):
@@ -195,7 +195,7 @@ if args.sweep_full:
     for fmt, B in [(f, b) for f in args.fmts for b in (args.batches or [args.batch])]:
         for (cin, cout, hw), count in sorted(shapes.items(), key=lambda kv: -kv[0][2]):
             flop = 2.0 * B * hw * hw * cout * cin * 9
-            KEYS = ("AIDE_CONV_BN", "AIDE_CONV_MB", "AIDE_CONV_STACK", "AIDE_CONV_RB", "AIDE_CONV_WRES")
+            KEYS = ("AIDE_CONV_BN", "AIDE_CONV_MB", "AIDE_CONV_STACK", "AIDE_CONV_RB", "AIDE_CONV_WRES", "AIDE_CONV_OCC")
             for k in KEYS:
                 os.environ.pop(k, None)
             dflt = plan(fmt, cin, cout, B, hw, hw)
@@ -206,12 +206,13 @@ if args.sweep_full:
                 for mb in (1, 2, 4):
                     for stack in (0, 1):
                         for rb in (64, 128):
-                            for wres in (0, 1):
+                            for occ in (1, 2):
+                                wres = 0
                                 os.environ.update(AIDE_CONV_BN=str(bn), AIDE_CONV_MB=str(mb), AIDE_CONV_STACK=str(stack),
-                                                  AIDE_CONV_RB=str(rb), AIDE_CONV_WRES=str(wres))
+                                                  AIDE_CONV_RB=str(rb), AIDE_CONV_WRES="0", AIDE_CONV_OCC=str(occ))
                                 pl = plan(fmt, cin, cout, B, hw, hw)
                                 if pl is None or pl["BN"] != bn or pl["MB"] != mb or pl["stack"] != stack or pl["rb"] != rb \
-                                        or pl["res"] != wres:
+                                        or pl["occ"] != occ:
                                     continue
                                 try:
                                     ms = time_layer(fmt, cin, cout, hw)
@@ -223,14 +224,14 @@ if args.sweep_full:
             for k in KEYS:
                 os.environ.pop(k, None)
             res.sort(key=lambda r: r[0])
-            line = "  ".join(f"BN{bn}/MB{mb}/s{stack}/r{rb}/w{pl['res']}/a{pl['nacc']}b{pl['nbuf']}A{pl['aS']}B{pl['bS']}:{flop / ms / 1e9:.0f}"
+            line = "  ".join(f"BN{bn}/MB{mb}/s{stack}/r{rb}/o{pl['occ']}/a{pl['nacc']}b{pl['nbuf']}A{pl['aS']}B{pl['bS']}:{flop / ms / 1e9:.0f}"
                              for ms, bn, mb, stack, rb, pl in res[:12])
             t_def = time_layer(fmt, cin, cout, hw)
             print(f"SWEEPF {NAMES[fmt]:7s} {cin:4d}->{cout:3d} @{hw:3d} default {dflt} {flop / t_def / 1e9:.0f} TF | {line}",
                   flush=True)
             full[f"{NAMES[fmt]}:{cin}:{cout}:{hw}:{B}"] = dict(
                 default=dflt, default_ms=round(t_def, 4), gflop=round(flop / 1e9, 2),
-                configs=[dict(ms=round(ms, 4), BN=bn, MB=mb, stack=stack, rb=rb, res=pl["res"], nacc=pl["nacc"], nbuf=pl["nbuf"],
+                configs=[dict(ms=round(ms, 4), BN=bn, MB=mb, stack=stack, rb=rb, res=pl["res"], occ=pl["occ"], nacc=pl["nacc"], nbuf=pl["nbuf"],
                               aS=pl["aS"], bS=pl["bS"]) for ms, bn, mb, stack, rb, pl in res])
     if args.json:
         with open(args.json.replace(".json", "_full.json"), "w") as f:
