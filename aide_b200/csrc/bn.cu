@@ -6,6 +6,8 @@
 // results are bit-reproducible run to run (no float atomics).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace aide {
 
 // ------------------------------------------------------------------ column reduction of partial rows
@@ -794,7 +796,11 @@ extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, c
     AIDE_CHECK_LAUNCH();
   }
   dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
-  const bool fuse_dbias = tickets && dbias_conv;
+  // Folding dbias_conv in the apply kernel's last block is OFF by default: one block walking ~1 200 partial rows at the
+  // end of the launch cost more (0.46 of the copy peak for the whole kernel, tools/hbm_probe.py) than the separate
+  // column-reduce launch it saved (0.56).  AIDE_BN_FUSE_DBIAS=1 turns it back on.
+  static const bool fuse_dbias_env = []() { const char* e = std::getenv("AIDE_BN_FUSE_DBIAS"); return e && *e == '1'; }();
+  const bool fuse_dbias = tickets && dbias_conv && fuse_dbias_env;
   size_t smem = (size_t)gm.cx * gm.ty * 4 * (fuse_dbias ? sizeof(double) : sizeof(float));
   AIDE_DISPATCH_FMT(fmt, (bn_relu_bwd_apply_kernel<FMT><<<grid, block, smem, st>>>(
                              g, z, mean_rstd, gamma, dbeta, inv, npix, C, dz_p0, dz_p1, partial2, dz_scale,

@@ -13,6 +13,12 @@
 // Bytes per MMA fall ~3x (277 FLOP per TMA byte at BN = 128).  Split-K over pixel tiles into a workspace, fixed-order
 // reduction by wgrad_reduce_kernel (deterministic).
 //
+// STACKM (F16X2, cin % 128 == 64 -- the 64-channel layers, which used to fall back to the first kernel at 9 % tensor
+// pipe): the 128 MMA rows are [hi plane, 64 channels | lo plane, 64 channels] -- the two 64-channel blocks of the
+// MN-major operand are simply the two planes (LBO = plane distance) -- so x_hi*dz and x_lo*dz come out of ONE MMA in
+// TMEM lanes [0,64) and [64,128); two MMAs per tap (against dz_hi and dz_lo) give the full 4-term product and the
+// epilogue adds the two lane halves through shared memory.
+//
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (warp-uniform loop, one elected lane), warps 2..5
 // epilogue (TMEM lane = input channel).
 #include "common.cuh"
@@ -46,10 +52,14 @@ struct WParams {
   int tiles_w, tiles_h, tiles_total, tiles_per_split;
   int BN, nb_b;                                  // cout tile, number of 64-channel dZ blocks in it
   int a_plane, b_plane, stage_bytes, stages, bar_off, tmem_cols;
+  int scratch_off;                               // STACKM: 8 KB exchange buffer of the epilogue
 };
 
-template <int NPL, bool F16>
+template <int NPL, bool F16, bool STACKM>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_constant__ WParams p) {
+  static_assert(!STACKM || NPL == 2, "stacking the planes along M needs a two-plane format");
+  constexpr int CB = STACKM ? 64 : 128;          // input channels per CTA
+  constexpr int NA = STACKM ? 1 : 2;             // 64-channel activation blocks per plane
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
-    const uint32_t tx = NPL * (2 * kABlk + p.nb_b * kBBlk);
+    const uint32_t tx = NPL * (NA * kABlk + p.nb_b * kBBlk);
     int s = 0;
     uint32_t ph = 0;
     int n_img = t_begin / tiles_per_img;
@@ -109,10 +119,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
         const uint32_t a_dst = base + s * p.stage_bytes;
         const uint32_t b_dst = a_dst + NPL * p.a_plane;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          tma_load_4d(a_dst + j * kABlk, &p.tmX0, full_bar(s), ci_blk * 128 + j * 64, w0 - 1, h0 + dy - 1, n_img);
+        for (int j = 0; j < NA; ++j) {
+          tma_load_4d(a_dst + j * kABlk, &p.tmX0, full_bar(s), ci_blk * CB + j * 64, w0 - 1, h0 + dy - 1, n_img);
           if (NPL == 2)
-            tma_load_4d(a_dst + p.a_plane + j * kABlk, &p.tmX1, full_bar(s), ci_blk * 128 + j * 64, w0 - 1, h0 + dy - 1,
+            tma_load_4d(a_dst + p.a_plane + j * kABlk, &p.tmX1, full_bar(s), ci_blk * CB + j * 64, w0 - 1, h0 + dy - 1,
                         n_img);
         }
         for (int j = 0; j < p.nb_b; ++j) {
@@ -150,7 +160,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
           for (int dx = 0; dx < 3; ++dx) {
             const uint32_t acc = tmem_base + (uint32_t)(dx * p.BN);
             const uint64_t ah = a_row + (uint64_t)(dx * 8);
-            if (NPL == 2) {
+            if (STACKM) {          // rows [x_hi | x_lo] (LBO = plane distance = kABlk) against dz_hi, then dz_lo
+              umma<false>(acc, ah, b_row, idesc, accum);
+              umma<false>(acc, ah, b_row + (uint64_t)b_plane16, idesc, 1u);
+            } else if (NPL == 2) {
               umma<false>(acc, ah + (uint64_t)a_plane16, b_row, idesc, accum);
               umma<false>(acc, ah, b_row + (uint64_t)b_plane16, idesc, 1u);
               umma<false>(acc, ah, b_row, idesc, 1u);
@@ -171,23 +184,58 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(const __grid_co
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM lane = input channel
     const int q = warp & 3;
-    const int ci = ci_blk * 128 + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tc_fence_after_sync();
     const bool any = t_end > t_begin;
-    for (int dx = 0; dx < 3; ++dx) {
-      const int tap = dy * 3 + dx;
-      float* out = p.ws + (size_t)blockIdx.z * 9 * p.cin * p.cout + ((size_t)tap * p.cin + ci) * p.cout + n0;
-      for (int ch = 0; ch < p.BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * p.BN + ch * 32), r);
-        tmem_ld_wait();
+    if constexpr (STACKM) {
+      // lanes [0,64) hold x_hi * dz, lanes [64,128) x_lo * dz of the same 64 channels: warps with q >= 2 hand their
+      // values over through shared memory, warps with q < 2 add and store
+      float* scratch = reinterpret_cast<float*>(sm + p.scratch_off);            // [64 channels][32 columns]
+      const int cl = (q & 1) * 32 + lane;
+      const int ci = ci_blk * 64 + cl;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int tap = dy * 3 + dx;
+        float* out = p.ws + (size_t)blockIdx.z * 9 * p.cin * p.cout + ((size_t)tap * p.cin + ci) * p.cout + n0;
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * p.BN + ch * 32), r);
+          tmem_ld_wait();
+          if (q >= 2) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          *reinterpret_cast<float4*>(out + ch * 32 + k) =
-              any ? make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]),
-                                __uint_as_float(r[k + 3]))
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 32; k += 4)
+              *reinterpret_cast<float4*>(scratch + cl * 32 + k) =
+                  make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+          }
+          named_bar_sync(1, 128);
+          if (q < 2) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 lo = *reinterpret_cast<const float4*>(scratch + cl * 32 + k);
+              *reinterpret_cast<float4*>(out + ch * 32 + k) =
+                  any ? make_float4(__uint_as_float(r[k]) + lo.x, __uint_as_float(r[k + 1]) + lo.y,
+                                    __uint_as_float(r[k + 2]) + lo.z, __uint_as_float(r[k + 3]) + lo.w)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          named_bar_sync(2, 128);                 // the exchange buffer is free again
+        }
+      }
+    } else {
+      const int ci = ci_blk * 128 + q * 32 + lane;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int tap = dy * 3 + dx;
+        float* out = p.ws + (size_t)blockIdx.z * 9 * p.cin * p.cout + ((size_t)tap * p.cin + ci) * p.cout + n0;
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * p.BN + ch * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            *reinterpret_cast<float4*>(out + ch * 32 + k) =
+                any ? make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]),
+                                  __uint_as_float(r[k + 3]))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
   }
@@ -215,17 +263,20 @@ int make_wplan(int fmt, int cin, int cout, int N, int H, int W, WPlan* o) {
   p.tiles_w = ceil_div(W, kTW);
   p.tiles_h = ceil_div(H, kTH);
   p.tiles_total = N * p.tiles_w * p.tiles_h;
-  p.a_plane = 2 * kABlk;
+  const bool stackm = cin % 128 != 0;            // 64-channel blocks: hi / lo planes stacked along the MMA's M
+  const int cb = stackm ? 64 : 128;
+  p.a_plane = (stackm ? 1 : 2) * kABlk;
   p.b_plane = p.nb_b * kBBlk;
   p.stage_bytes = npl * (p.a_plane + p.b_plane);
-  p.stages = (kSmemMax - 2048) / p.stage_bytes;
+  p.stages = (kSmemMax - 2048 - (stackm ? 8192 + 128 : 0)) / p.stage_bytes;
   if (p.stages > kStagesMax) p.stages = kStagesMax;
   if (p.stages < 2) return 1;
   p.bar_off = p.stages * p.stage_bytes;
-  o->smem = 1024 + p.bar_off + 8 * (2 * kStagesMax + 2);
+  p.scratch_off = p.bar_off + 128;
+  o->smem = 1024 + p.bar_off + 128 + (stackm ? 8192 : 0);
   p.tmem_cols = 3 * p.BN <= 256 ? 256 : 512;
   // split-K over pixel tiles: minimise (waves over 148 SMs) x (tiles per CTA); ties -> fewer splits
-  const long long base_ctas = (long long)(cin / 128) * 3 * (cout / p.BN);
+  const long long base_ctas = (long long)(cin / cb) * 3 * (cout / p.BN);
   long long best_cost = -1;
   int best_s = 1;
   const int max_s = p.tiles_total / 8 > 0 ? p.tiles_total / 8 : 1;
@@ -241,20 +292,20 @@ int make_wplan(int fmt, int cin, int cout, int N, int H, int W, WPlan* o) {
   }
   p.tiles_per_split = ceil_div(p.tiles_total, best_s);
   o->splits = ceil_div(p.tiles_total, p.tiles_per_split);
-  o->grid = dim3((cin / 128) * 3, cout / p.BN, o->splits);
+  o->grid = dim3((cin / cb) * 3, cout / p.BN, o->splits);
   return 0;
 }
 
-template <int NPL, bool F16>
+template <int NPL, bool F16, bool STACKM>
 int launch(const WPlan& pl, cudaStream_t st) {
   static thread_local bool done[16] = {false};
   int dev = 0;
   AIDE_CUDA(cudaGetDevice(&dev));
   if (dev >= 16 || !done[dev]) {
-    AIDE_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<NPL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    AIDE_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<NPL, F16, STACKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     if (dev < 16) done[dev] = true;
   }
-  wgrad_halo_kernel<NPL, F16><<<pl.grid, kThreads, pl.smem, st>>>(pl.p);
+  wgrad_halo_kernel<NPL, F16, STACKM><<<pl.grid, kThreads, pl.smem, st>>>(pl.p);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -269,7 +320,8 @@ int env_flag(const char* name, int dflt) {
 bool wgrad_halo_ok(int fmt, int cin, int cout, int N, int H, int W) {
   if (fmt != AIDE_FMT_F16X2 && fmt != AIDE_FMT_BF16) return false;
   if (env_flag("AIDE_WGRAD_HALO", 1) == 0) return false;
-  if (cin % 128 || cout % 64 || W < 8 || H < 2) return false;
+  if (cin % 64 || cout % 64 || W < 8 || H < 2) return false;
+  if (cin % 128 && (fmt != AIDE_FMT_F16X2 || env_flag("AIDE_WGRAD_STACKM", 1) == 0)) return false;   // 64-channel blocks: two-plane format only
   WPlan pl;
   return make_wplan(fmt, cin, cout, N, H, W, &pl) == 0;
 }
@@ -297,7 +349,9 @@ int wgrad_halo(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff, 
     if (act_tmap(&p.tmX1, dtype, x1, x_ctot, x_coff, cin, N, H, W, 64, kHW, kTH, 128)) return 1;
     if (act_tmap(&p.tmD1, dtype, dz1, cout, 0, cout, N, H, W, 64, kTW, kTH, 128)) return 1;
   }
-  int rc = fmt == AIDE_FMT_BF16 ? launch<1, false>(pl, st) : launch<2, true>(pl, st);
+  int rc = fmt == AIDE_FMT_BF16 ? launch<1, false, false>(pl, st)
+           : cin % 128         ? launch<2, true, true>(pl, st)
+                               : launch<2, true, false>(pl, st);
   if (rc) return rc;
   return launch_wgrad_reduce(p.ws, pl.splits, cout, cin, 1, dw, out_scale, out_scale_ptr, st);
 }

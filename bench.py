@@ -689,7 +689,7 @@ def main():
                   "fast": "bf16 operands, fp32 accumulate (NOT a parity mode)", "exact": "f32 CUDA cores"}[args.mode],
         "data": "synthetic",
         "config": workload_config(B, S, world, args.model),
-        "engine": {"mode": args.mode, "cuda_graph": bool(tr.cuda_graph), "stacked_aug_forward": bool(tr.group_augs),
+        "engine": {"mode": args.mode, "cuda_graph": bool(tr.cuda_graph), "stacked_aug_forward": bool(tr.group_augs), "stacked_train_forward": bool(tr.stack_train),
                    "resident_batches": n_pool, "global_select": bool(tr.global_select)},
         "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
@@ -709,7 +709,8 @@ def main():
         fmt_inf, fmt_train = E.mode_format(args.mode, False), E.mode_format(args.mode, True)
         # The dominant kernel launches of the step are the convolutions of the stacked pseudo-label forward (4 views x B
         # images per launch, 4/7 of the step's conv FLOPs); the train forward / dgrad run the same kernel at batch B.
-        Ba = 4 * B if tr.group_augs else B
+        # (with the train forward riding as a fifth statistics group: 5 x B images per launch)
+        Ba = (5 * B if (tr.stack_train and tr.flavour == "chaos") else 4 * B) if tr.group_augs else B
         rl = conv_roofline(fmt_inf, Ba, S, device, peaks)
         layers = {f"{FMT_NAMES[fmt_inf]}:B{Ba}": rl.pop("layers")}
         rl["batch_per_launch"] = Ba
