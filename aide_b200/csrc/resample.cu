@@ -102,19 +102,30 @@ __global__ void upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w
     src_index(sh, oy, h, y0, y1, ly0, ly1);
     const size_t r0 = ((size_t)n * h + y0) * w, r1 = ((size_t)n * h + y1) * w;
     const size_t drow = (size_t)row * W;
-    for (int ox = threadIdx.y; ox < W; ox += blockDim.y) {
-      int x0, x1;
-      float lx0, lx1;
+    // two output pixels per iteration (16 independent 128-bit plane loads in flight per thread: the one-pixel loop ran
+    // at ~0.5 of the copy peak, latency bound)
+    for (int ox = threadIdx.y; ox < W; ox += 2 * blockDim.y) {
+      const int oxb = ox + blockDim.y;
+      const bool two = oxb < W;
+      int x0, x1, u0, u1;
+      float lx0, lx1, mx0, mx1;
       src_index(sw, ox, w, x0, x1, lx0, lx1);
+      src_index(sw, two ? oxb : ox, w, u0, u1, mx0, mx1);
       const size_t s00 = (r0 + x0) * src.ctot + src.coff, s01 = (r0 + x1) * src.ctot + src.coff;
       const size_t s10 = (r1 + x0) * src.ctot + src.coff, s11 = (r1 + x1) * src.ctot + src.coff;
-      const size_t d0 = (drow + ox) * dst.ctot + dst.coff;
+      const size_t t00 = (r0 + u0) * src.ctot + src.coff, t01 = (r0 + u1) * src.ctot + src.coff;
+      const size_t t10 = (r1 + u0) * src.ctot + src.coff, t11 = (r1 + u1) * src.ctot + src.coff;
+      const size_t d0 = (drow + ox) * dst.ctot + dst.coff, d1 = (drow + oxb) * dst.ctot + dst.coff;
       for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
-        float a[8], b[8], d[8], e[8], o[8];
+        float a[8], b[8], d[8], e[8], o[8], a2[8], b2[8], d2[8], e2[8];
         ld8<FMT>(src.p0, src.p1, s00 + c, a);
         ld8<FMT>(src.p0, src.p1, s01 + c, b);
         ld8<FMT>(src.p0, src.p1, s10 + c, d);
         ld8<FMT>(src.p0, src.p1, s11 + c, e);
+        ld8<FMT>(src.p0, src.p1, t00 + c, a2);
+        ld8<FMT>(src.p0, src.p1, t01 + c, b2);
+        ld8<FMT>(src.p0, src.p1, t10 + c, d2);
+        ld8<FMT>(src.p0, src.p1, t11 + c, e2);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // same operation order as the 4-channel kernel: along W first, then along H
@@ -122,6 +133,14 @@ __global__ void upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w
           o[k] = ly0 * t0 + ly1 * t1;
         }
         st8<FMT>(dst.p0, dst.p1, d0 + c, o);
+        if (two) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float t0 = mx0 * a2[k] + mx1 * b2[k], t1 = mx0 * d2[k] + mx1 * e2[k];
+            o[k] = ly0 * t0 + ly1 * t1;
+          }
+          st8<FMT>(dst.p0, dst.p1, d1 + c, o);
+        }
       }
     }
   }
@@ -148,6 +167,20 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dhi, int ctot, i
       ox_lo = max(0, (int)floorf((float)(ix - 1) / sw) - 1);
       ox_hi = min(W - 1, (int)ceilf((float)(ix + 1) / sw) + 1);
     }
+    // horizontal weights of the candidate columns once per pixel (not once per candidate row)
+    constexpr int kMaxCand = 10;    // (ix +- 1) / scale spans <= ~4 output columns; the floor / ceil / +-1 margins widen the window to <= 9
+    float wxs[kMaxCand];
+    const int ncx = min(ox_hi - ox_lo + 1, kMaxCand);
+#pragma unroll
+    for (int j = 0; j < kMaxCand; ++j) {
+      wxs[j] = 0.f;
+      if (j < ncx) {
+        int x0, x1;
+        float lx0, lx1;
+        src_index(sw, ox_lo + j, w, x0, x1, lx0, lx1);
+        wxs[j] = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+      }
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       int y0, y1;
@@ -155,13 +188,12 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dhi, int ctot, i
       src_index(sh, oy, h, y0, y1, ly0, ly1);
       float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
       if (wy == 0.f) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        int x0, x1;
-        float lx0, lx1;
-        src_index(sw, ox, w, x0, x1, lx0, lx1);
-        float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
-        if (wx == 0.f) continue;
-        float4 v = *reinterpret_cast<const float4*>(dhi + (((size_t)n * H + oy) * W + ox) * ctot + coff + c);
+      const float* rowp = dhi + (((size_t)n * H + oy) * W + ox_lo) * ctot + coff + c;
+#pragma unroll
+      for (int j = 0; j < kMaxCand; ++j) {
+        const float wx = wxs[j];
+        if (j >= ncx || wx == 0.f) continue;
+        float4 v = *reinterpret_cast<const float4*>(rowp + (size_t)j * ctot);
         float ww = wy * wx;
         acc.x += ww * v.x;
         acc.y += ww * v.y;
