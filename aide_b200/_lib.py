@@ -22,6 +22,7 @@ SIGNATURES = {
     "aide_version": (_i, []),
     "aide_launch_count": (C.c_ulonglong, []),
     "aide_has_tma": (_i, []),
+    "aide_f16_saturated": (_i, [_i]),
     "aide_nchw_to_nhwc": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_nhwc_to_nchw": (_i, [_i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "aide_weight_prep": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),

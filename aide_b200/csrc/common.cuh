@@ -69,7 +69,32 @@ __device__ __forceinline__ float tf32_rn(float x) {
 // power of two chosen on the device.  Conversions saturate at +-65504 instead of producing inf.
 constexpr float kF16ActScale = 256.f;
 constexpr float kF16WScale = 4096.f;
+// Sticky saturation flag (one per translation unit, read through aide_f16_saturated()): set when a pre-scaled value
+// leaves the fp16 range, i.e. |activation| >= 255.87, |weight| >= 16 or a gradient beyond its dynamic scale's head-room.
+// The result is then clipped, which silently breaks the fp32-parity claim -- tests and users can check the flag.
+static __device__ unsigned int g_f16_sat_tu = 0;
+void register_f16_sat_reader(unsigned (*fn)(bool));
+namespace {
+struct F16SatRegistrar {
+  F16SatRegistrar() {
+    register_f16_sat_reader([](bool reset) -> unsigned {
+      unsigned v = 0;
+      if (cudaMemcpyFromSymbol(&v, g_f16_sat_tu, sizeof(v)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0u;
+      }
+      if (reset && v) {
+        const unsigned z = 0;
+        cudaMemcpyToSymbol(g_f16_sat_tu, &z, sizeof(z));
+      }
+      return v;
+    });
+  }
+};
+static F16SatRegistrar g_f16_sat_registrar;
+}  // namespace
 __device__ __forceinline__ void f16_split(float xs, __half& hi, __half& lo) {
+  if (fabsf(xs) > 65504.f) g_f16_sat_tu = 1u;          // sticky (benign race: every writer stores 1)
   const float c = fminf(fmaxf(xs, -65504.f), 65504.f);
   hi = __float2half_rn(c);
   lo = __float2half_rn(c - __half2float(hi));

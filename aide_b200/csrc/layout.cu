@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include <atomic>
+#include <vector>
 
 namespace aide {
 
@@ -11,6 +12,13 @@ namespace aide {
 static thread_local char g_err[1024] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ fp16 saturation flag (see common.cuh::f16_split)
+static std::vector<unsigned (*)(bool)>& f16_sat_readers() {
+  static std::vector<unsigned (*)(bool)> v;
+  return v;
+}
+void register_f16_sat_reader(unsigned (*fn)(bool)) { f16_sat_readers().push_back(fn); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -174,7 +182,12 @@ __global__ void __launch_bounds__(256) weight_prep_batch_kernel(const __grid_con
 using namespace aide;
 
 extern "C" const char* aide_last_error(void) { return g_err; }
-extern "C" int aide_version(void) { return 100; }
+extern "C" int aide_version(void) { return 200; }
+extern "C" int aide_f16_saturated(int reset) {
+  unsigned any = 0;
+  for (auto fn : f16_sat_readers()) any |= fn(reset != 0);
+  return any ? 1 : 0;
+}
 extern "C" unsigned long long aide_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int aide_nchw_to_nhwc(int fmt, const float* src, void* dst_p0, void* dst_p1, int dst_ctot, int dst_coff,

@@ -42,6 +42,11 @@ int aide_version(void);
 /* number of CUDA kernels this library has launched in this process (monotonic; bench.py reports the
  * per-step difference as "gpu_launches"). */
 unsigned long long aide_launch_count(void);
+/* AIDE_FMT_F16X2 stores tensors pre-scaled by a power of two in two fp16 planes; a value outside the fp16 range after
+ * scaling (|activation| >= 255.87, |weight| >= 16, a gradient beyond its dynamic scale's head-room) is CLIPPED.  Every
+ * conversion kernel sets a sticky device flag when that happens: returns 1 if any tensor saturated since the last
+ * reset (synchronising read of the current device; reset != 0 clears the flag). */
+int aide_f16_saturated(int reset);
 /* 1 if the tcgen05/TMA path can run (driver entry point for cuTensorMapEncodeTiled found). */
 int aide_has_tma(void);
 

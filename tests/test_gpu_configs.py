@@ -126,6 +126,8 @@ def test_config3_aide_step_b8_256_through_trainer(oracle, all_threads):
     assert abs(m["loss1"].item() - r["loss1"].item()) < 2e-5 * max(1.0, abs(r["loss1"].item()))
     assert abs(m["loss2"].item() - r["loss2"].item()) < 2e-5 * max(1.0, abs(r["loss2"].item()))
     assert dd < 1e-4, dd
+    from aide_b200 import lib
+    assert lib.aide_f16_saturated(1) == 0          # no operand left the fp16 range of the split-precision planes
     # the update that followed: Adam-amsgrad's first step is lr * sign(g) -> elements at rounding level differ by 2 lr
     oracle.adam_amsgrad_step(p1, r["grads1"], {}, 1)
     sd = tr.net1.state_dict()

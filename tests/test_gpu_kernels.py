@@ -590,3 +590,21 @@ def test_pixel_loss_maps_against_autograd(dev):
     got = maxpool_nchw(xd, 2, 4)
     (got * upp.to(dev)).sum().backward()
     assert torch.equal(got.detach().cpu(), ref.detach()) and torch.equal(xd.grad.cpu(), gx_ref)
+
+
+def test_f16_saturation_flag_is_sticky_and_resettable(dev):
+    """F16X2 planes hold x * 2^8 in fp16: |x| >= 255.87 is clipped.  The conversion kernels raise a sticky device flag
+    (aide_f16_saturated) so that a silent loss of fp32 parity cannot go unnoticed."""
+    from aide_b200 import ops
+    from aide_b200._lib import lib
+    lib.aide_f16_saturated(1)
+    x = torch.randn(1, 32, 8, 8).to(dev)
+    a = ops.from_nchw(x, 3)
+    torch.cuda.synchronize()
+    assert lib.aide_f16_saturated(0) == 0
+    x[0, 3, 2, 2] = 300.0
+    a = ops.from_nchw(x, 3)
+    torch.cuda.synchronize()
+    assert lib.aide_f16_saturated(0) == 1 and lib.aide_f16_saturated(1) == 1        # sticky until reset
+    assert lib.aide_f16_saturated(0) == 0
+    assert abs(ops.to_nchw(a)[0, 3, 2, 2].item() - 65504.0 / 256.0) < 1e-3           # clipped, not inf
