@@ -132,10 +132,10 @@ def test_conv_planner_returns_valid_tilings_for_every_layer():
                             rc = lib.aide_conv3x3_plan_info(fmt, cin, cout, B, h, h, out)
                             assert rc == 0, (plan.kind, S, B, u.name, fmt)
                             bn, mb, nacc, nbuf, rb, a_st, b_st, smem, flags = list(out)
-                            stack, resident = flags & 1, flags >> 1
+                            stack, resident, occ = flags & 1, (flags >> 1) & 1, 2 if flags & 4 else 1
                             assert cout % bn == 0 and bn in (32, 64, 128, 256) and mb in (1, 2, 4)
-                            assert nbuf * mb * nacc * bn * (1 + stack) <= 512
-                            assert smem <= 227 * 1024 and a_st >= 1 and b_st >= 2 and rb in (64, 128)
+                            assert nbuf * mb * nacc * bn * (1 + stack) <= 512 // occ        # two CTAs per SM share TMEM ...
+                            assert smem <= 227 * 1024 // occ and a_st >= 1 and b_st >= 2 and rb in (64, 128)   # ... and smem
                             assert not stack or (fmt != 2 and 2 * bn <= 256)
                             if resident:      # the whole weight matrix stays in shared memory: one cout tile, >= 2 halo stages
                                 es = 4 if fmt == 1 else 2
