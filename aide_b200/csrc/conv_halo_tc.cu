@@ -120,6 +120,81 @@ __device__ __forceinline__ void store_planes_32(void* p0, void* p1, size_t e, co
   }
 }
 
+// Epilogue of one 8x16-pixel tile for one warp (TMEM lane quadrant q): add up the accumulator column blocks, scale + bias,
+// then either fp32 z + BatchNorm partial sums (training) or BN(eval) + ReLU (+ 2x2 max-pool) into operand planes.
+template <int KIND>
+__device__ __forceinline__ void epilogue_tile(const HaloParams& p, uint32_t tmem_base, uint32_t buf, int m, int mt, int n0,
+                                              int q, int lane, float scale, int tiles_per_img) {
+  const int row = q * 32 + lane;
+  const int ty = row >> 3, tx = row & 7;
+  const int n_img = mt / tiles_per_img, r = mt - n_img * tiles_per_img;
+  const int hh = (r / p.tiles_w) * kTH + ty, ww = (r % p.tiles_w) * kTW + tx;
+  const bool valid = hh < p.H && ww < p.W;
+  float* zrow = p.z + (((size_t)n_img * p.H + hh) * p.W + ww) * p.z_ctot + p.z_coff + n0;
+  const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MB + m) * p.nacc * p.acc_w);
+  const int nparts = p.nacc * (p.stack ? 2 : 1);           // BN-wide column blocks to add up per accumulator set
+  for (int ch = 0; ch < p.BN / 32; ++ch) {
+    uint32_t rr[32];
+    tmem_ld_32x32(tbase + (uint32_t)(ch * 32), rr);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+    for (int a = 1; a < nparts; ++a) {
+      tmem_ld_32x32(tbase + (uint32_t)(a * p.BN + ch * 32), rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
+    }
+    const float* bp = p.bias ? p.bias + n0 + ch * 32 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = v[j] * scale;
+      if (bp) t += __ldg(bp + j);
+      v[j] = valid ? t : 0.f;
+    }
+    if (p.ep_ss) {
+      // ---- inference: BatchNorm (running statistics) + ReLU (+ max-pool) here, same operations in the same
+      // order as bn_relu_apply_kernel applies to the fp32 z of the unfused path -> bit-identical planes
+      const float* sc = p.ep_ss + n0 + ch * 32;
+      const float* sh = sc + p.cout;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
+      const size_t pix = ((size_t)n_img * p.H + hh) * p.W + ww;
+      if (valid && p.y0) store_planes_32<KIND>(p.y0, p.y1, pix * p.y_ctot + p.y_coff + n0 + ch * 32, v);
+      if (p.pa0 || p.pb0) {
+        // 2x2 max-pool: the window partners of pixel (ty, tx) are lanes ^1 (tx) and ^8 (ty) of this warp
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+          v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        }
+        if (valid && !(tx & 1) && !(ty & 1)) {
+          const size_t win = ((size_t)n_img * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1);
+          if (p.pa0) store_planes_32<KIND>(p.pa0, p.pa1, win * p.pa_ctot + p.pa_coff + n0 + ch * 32, v);
+          if (p.pb0) store_planes_32<KIND>(p.pb0, p.pb1, win * p.pb_ctot + p.pb_coff + n0 + ch * 32, v);
+        }
+      }
+      continue;
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(zrow + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    if (p.stat_partial) {
+      float sq[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+      const float s1 = column_sums_32(v, lane);
+      const float s2 = column_sums_32(sq, lane);
+      float* out = p.stat_partial + ((size_t)(mt * 4 + q) * 2) * p.cout + n0 + ch * 32 + lane;
+      out[0] = s1;
+      out[p.cout] = s2;
+    }
+  }
+}
+
 template <int KIND, int NKS>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -340,8 +415,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
   } else {
     // ------------------------------------------------------------------ epilogue (TMEM lane quadrant = warp % 4)
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ty = row >> 3, tx = row & 7;
     float scale = p.out_scale;
     if (p.out_scale_ptr) scale *= __ldg(p.out_scale_ptr);
     uint32_t tcount = 0;
@@ -353,73 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
       mbar_wait(tfull(buf), bph);
       tc_fence_after_sync();
       for (int m = 0; m < mbv; ++m) {
-        const int mt = m0 + m;
-        const int n_img = mt / tiles_per_img, r = mt - n_img * tiles_per_img;
-        const int hh = (r / p.tiles_w) * kTH + ty, ww = (r % p.tiles_w) * kTW + tx;
-        const bool valid = hh < p.H && ww < p.W;
-        float* zrow = p.z + (((size_t)n_img * p.H + hh) * p.W + ww) * p.z_ctot + p.z_coff + n0;
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MB + m) * p.nacc * p.acc_w);
-        const int nparts = p.nacc * (p.stack ? 2 : 1);           // BN-wide column blocks to add up per accumulator set
-        for (int ch = 0; ch < p.BN / 32; ++ch) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tbase + (uint32_t)(ch * 32), rr);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-          for (int a = 1; a < nparts; ++a) {
-            tmem_ld_32x32(tbase + (uint32_t)(a * p.BN + ch * 32), rr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
-          }
-          const float* bp = p.bias ? p.bias + n0 + ch * 32 : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = v[j] * scale;
-            if (bp) t += __ldg(bp + j);
-            v[j] = valid ? t : 0.f;
-          }
-          if (p.ep_ss) {
-            // ---- inference: BatchNorm (running statistics) + ReLU (+ max-pool) here, same operations in the same
-            // order as bn_relu_apply_kernel applies to the fp32 z of the unfused path -> bit-identical planes
-            const float* sc = p.ep_ss + n0 + ch * 32;
-            const float* sh = sc + p.cout;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
-            const size_t pix = ((size_t)n_img * p.H + hh) * p.W + ww;
-            if (valid && p.y0) store_planes_32<KIND>(p.y0, p.y1, pix * p.y_ctot + p.y_coff + n0 + ch * 32, v);
-            if (p.pa0 || p.pb0) {
-              // 2x2 max-pool: the window partners of pixel (ty, tx) are lanes ^1 (tx) and ^8 (ty) of this warp
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-              }
-              if (valid && !(tx & 1) && !(ty & 1)) {
-                const size_t win = ((size_t)n_img * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1);
-                if (p.pa0) store_planes_32<KIND>(p.pa0, p.pa1, win * p.pa_ctot + p.pa_coff + n0 + ch * 32, v);
-                if (p.pb0) store_planes_32<KIND>(p.pb0, p.pb1, win * p.pb_ctot + p.pb_coff + n0 + ch * 32, v);
-              }
-            }
-            continue;
-          }
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(zrow + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.stat_partial) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-            const float s1 = column_sums_32(v, lane);
-            const float s2 = column_sums_32(sq, lane);
-            float* out = p.stat_partial + ((size_t)(mt * 4 + q) * 2) * p.cout + n0 + ch * 32 + lane;
-            out[0] = s1;
-            out[p.cout] = s2;
-          }
-        }
+        epilogue_tile<KIND>(p, tmem_base, buf, m, m0 + m, n0, q, lane, scale, tiles_per_img);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -434,6 +441,241 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_tc_kernel(const __gr
   }
 }
 
+// ================================================================================================ CTA-pair kernel
+// conv3x3_halo2_tc_kernel: the same algorithm on cta_group::2 -- two CTAs on the two SMs of a TPC (cluster of 2) issue ONE
+// MMA of M = 256: each CTA owns MB pixel tiles (its 128 rows of A, its own halo ring, its own TMEM accumulators) and
+// holds only HALF of the weight operand's N rows, which the tensor cores of the two SMs exchange.  Per SM the weight
+// stage shrinks from 2*BN to 1.5*BN rows (stacked split precision) and the shared-memory operand reads per MMA from
+// 128 + N to 128 + N/2 rows -- the bound of the BN <= 128 layers.
+//
+//   stacked F16X2 stage of a CTA:   Y (BN rows): rank 0 = W_hi[n0, n0+BN), rank 1 = W_lo[n0, n0+BN)
+//                                    X (BN/2 rows): rank r = W_hi[n0 + r*BN/2, +BN/2)
+//   MMA 1: A_hi x Y  (N = 2*BN: columns [0,BN) = hi*hi, [BN,2BN) = hi*lo)     MMA 2: A_lo x X (N = BN) -> columns lo_col
+//   BF16 (one plane): Y only, BN/2 rows per CTA, one MMA of N = BN.
+//
+// Barriers: "full" barriers live in the LEADER's shared memory and count the TMA bytes of both CTAs; "empty" / "TMEM full"
+// barriers exist in both CTAs and are signalled by one multicast tcgen05.commit; "TMEM empty" is the leader's, with the
+// epilogue warps of both CTAs arriving on it.  Only the leader's warp 1 issues MMAs.
+struct Halo2Params {
+  HaloParams h;
+  CUtensorMap tmBh;                // hi-plane weights with a box of BN/2 rows (the X region)
+  int pair_items, yx_bytes;        // work items of a pair; bytes of region Y (= offset of X inside a weight stage)
+};
+
+template <int KIND, int NKS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_halo2_tc_kernel(const __grid_constant__ Halo2Params pp) {
+  static_assert(KIND == K_F16X2 || KIND == K_BF16, "the pair kernel issues kind::f16 MMAs");
+  const HaloParams& p = pp.h;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int NPL = KIND == K_BF16 ? 1 : 2;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const int SA = p.a_stages, SB = p.b_stages;
+  const uint32_t bar_base = base + p.bar_off;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (kMaxAStages + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * kMaxAStages + kMaxBStages + s); };
+  auto tfull = [&](int b) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + b); };
+  auto tempty = [&](int b) { return bar_base + 8u * (2 * kMaxAStages + 2 * kMaxBStages + 2 + b); };
+  constexpr int kSlotIdx = 2 * kMaxAStages + 2 * kMaxBStages + 4;
+  const uint32_t slot_addr = bar_base + 8u * kSlotIdx;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 8 * kSlotIdx);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB0);
+    if (NPL == 2) {
+      tma_prefetch_desc(&p.tmA1);
+      tma_prefetch_desc(&p.tmB1);
+      tma_prefetch_desc(&pp.tmBh);
+    }
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 8);                   // 4 epilogue warps of each CTA of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(slot_addr, (uint32_t)p.tmem_cols);
+    tmem_relinquish2();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                            // the peer's barriers are initialised before anyone signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    const bool leader = elect_one();
+    const uint32_t halo_bytes = kHaloPix * p.row_bytes;
+    const uint32_t a_tx = 2u * NPL * p.MB * halo_bytes;                         // both CTAs
+    const uint32_t b_tx = 2u * (uint32_t)p.b_stage_bytes;
+    const int half = p.BN / 2;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int item = pair; item < pp.pair_items; item += n_pairs) {
+      const int n_tile = item % p.n_tiles, m0 = ((item / p.n_tiles) * 2 + (int)rank) * p.MB;
+      const int n0 = n_tile * p.BN;
+      int th0[4], tw0[4], tn[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int mt = m0 + (m < p.MB ? m : 0);
+        tn[m] = mt / tiles_per_img;              // >= N for tiles past the end: the whole box is out of bounds -> zeros
+        const int r = mt - tn[m] * tiles_per_img;
+        th0[m] = (r / p.tiles_w) * kTH - 1;
+        tw0[m] = (r % p.tiles_w) * kTW - 1;
+      }
+      int c0 = 0;
+      for (int c = 0; c < p.n_cchunks; ++c, c0 += p.kc) {
+        mbar_wait(aempty(sa), pha ^ 1);
+        if (leader) {
+          if (rank == 0) mbar_arrive_expect_tx(afull(sa), a_tx);
+          const uint32_t a_dst = base + sa * p.a_stage_bytes;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m < p.MB) {
+              tma2_load_4d(a_dst + m * p.a_slot_bytes, &p.tmA0, afull(sa), c0, tw0[m], th0[m], tn[m]);
+              if (NPL == 2)
+                tma2_load_4d(a_dst + (p.MB + m) * p.a_slot_bytes, &p.tmA1, afull(sa), c0, tw0[m], th0[m], tn[m]);
+            }
+          }
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+        int kcol = c0;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, kcol += p.cin) {
+          mbar_wait(bempty(sb), phb ^ 1);
+          if (leader) {
+            if (rank == 0) mbar_arrive_expect_tx(bfull(sb), b_tx);
+            const uint32_t b_dst = base + p.b_off + sb * p.b_stage_bytes;
+            if (NPL == 2) {
+              // Y: the full-height plane of this rank (hi on the leader, lo on the peer); X: this rank's half of hi
+              tma2_load_2d(b_dst, rank == 0 ? &p.tmB0 : &p.tmB1, bfull(sb), kcol, n0);
+              tma2_load_2d(b_dst + pp.yx_bytes, &pp.tmBh, bfull(sb), kcol, n0 + (int)rank * half);
+            } else {
+              tma2_load_2d(b_dst, &pp.tmBh, bfull(sb), kcol, n0 + (int)rank * half);
+            }
+          }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t fmtc = KIND == K_BF16 ? 1u : 0u;
+      const uint32_t idesc1 = make_idesc(fmtc, 0u, 0u, 256u, (uint32_t)(NPL == 2 ? 2 * p.BN : p.BN));
+      const uint32_t idesc2 = make_idesc(fmtc, 0u, 0u, 256u, (uint32_t)p.BN);
+      const uint32_t layout = NKS == 4 ? 2u : 4u;
+      const uint64_t a_desc0 = make_smem_desc(base, 16, kHW * p.row_bytes, layout);
+      const uint64_t b_desc0 = make_smem_desc(base + p.b_off, 16, 8 * p.row_bytes, layout);
+      const uint32_t a_plane16 = (uint32_t)(p.MB * p.a_slot_bytes) >> 4;
+      const uint32_t x16 = (uint32_t)pp.yx_bytes >> 4;
+      const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
+      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t row16 = (uint32_t)p.row_bytes >> 4;
+      const uint32_t acc_tile = (uint32_t)(p.nacc * p.acc_w);
+      const bool leader = elect_one();
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, tcount = 0;
+      for (int item = pair; item < pp.pair_items; item += n_pairs, ++tcount) {
+        const uint32_t buf = tcount % p.nbuf, bph = (tcount / p.nbuf) & 1;
+        mbar_wait(tempty(buf), bph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t acc_item = tmem_base + buf * p.MB * acc_tile;
+        int ai = 0;
+        uint32_t first = 0;
+        for (int c = 0; c < p.n_cchunks; ++c) {
+          mbar_wait(afull(sa), pha);
+          tc_fence_after_sync();
+          uint64_t a_row = a_desc0 + (uint64_t)(sa * a_stage16);
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy, a_row += (uint64_t)(kHW * row16)) {
+            uint64_t a_tap = a_row;
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx, a_tap += (uint64_t)row16) {
+              mbar_wait(bfull(sb), phb);
+              tc_fence_after_sync();
+              if (leader) {
+                const uint64_t b_y = b_desc0 + (uint64_t)(sb * b_stage16);
+                const uint32_t flag0 = (first >> ai) & 1u;
+                uint64_t a_hi = a_tap;
+                uint32_t acc = acc_item + (uint32_t)ai * p.acc_w;
+                for (int m = 0; m < p.MB; ++m, a_hi += (uint64_t)a_slot16, acc += acc_tile) {
+#pragma unroll
+                  for (int ks = 0; ks < NKS; ++ks) {
+                    const uint32_t flag = ks == 0 ? flag0 : 1u;
+                    umma_pair_f16(acc, a_hi + (uint64_t)(2 * ks), b_y + (uint64_t)(2 * ks), idesc1, flag);
+                    if (NPL == 2)
+                      umma_pair_f16(acc + (uint32_t)p.lo_col, a_hi + (uint64_t)(a_plane16 + 2 * ks),
+                                    b_y + (uint64_t)(x16 + 2 * ks), idesc2, 1u);
+                  }
+                }
+                umma_commit_pair(bempty(sb));
+              }
+              __syncwarp();
+              first |= 1u << ai;
+              ai = ai + 1 == p.nacc ? 0 : ai + 1;
+              if (++sb == SB) { sb = 0; phb ^= 1; }
+            }
+          }
+          if (leader) umma_commit_pair(aempty(sa));
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+        }
+        if (leader) umma_commit_pair(tfull(buf));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, each its own tiles)
+    const int q = warp & 3;
+    float scale = p.out_scale;
+    if (p.out_scale_ptr) scale *= __ldg(p.out_scale_ptr);
+    uint32_t tcount = 0;
+    for (int item = pair; item < pp.pair_items; item += n_pairs, ++tcount) {
+      const int n_tile = item % p.n_tiles, m0 = ((item / p.n_tiles) * 2 + (int)rank) * p.MB;
+      const int n0 = n_tile * p.BN;
+      const uint32_t buf = tcount % p.nbuf, bph = (tcount / p.nbuf) & 1;
+      mbar_wait(tfull(buf), bph);
+      tc_fence_after_sync();
+      for (int m = 0; m < p.MB; ++m) {
+        if (m0 + m >= p.m_tiles) break;                          // padding tile of the last pair
+        epilogue_tile<KIND>(p, tmem_base, buf, m, m0 + m, n0, q, lane, scale, tiles_per_img);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty(buf));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                            // nobody leaves while the peer may still read this CTA's memory
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 // ================================================================================================ host side
 inline int kind_of(int fmt) { return fmt == AIDE_FMT_BF16 ? K_BF16 : fmt == AIDE_FMT_F16X2 ? K_F16X2 : K_TF32X2; }
 
@@ -443,7 +685,8 @@ int env_int(const char* name, int dflt) {
 }
 
 struct HaloPlan {
-  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack, resident, occ;   // occ: CTAs per SM (1 or 2)
+  int BN, MB, nacc, nbuf, row_bytes, a_stages, b_stages, stack, resident, occ;   // occ: CTAs per SM (1 or 2); 4 = CTA pair
+  int yx;                                                                        // pair: bytes of weight region Y
   int a_slot, a_stage, b_plane, b_stage, smem;
   double cost;
 };
@@ -519,13 +762,15 @@ constexpr PlanEntry kPlanTable[] = {
 #include "conv_plan_table.inc"
 };
 
-const PlanEntry* lookup_plan(int fmt, int cin, int cout, long long m_tiles) {
+const PlanEntry* lookup_plan(int fmt, int cin, int cout, long long m_tiles, bool allow_pair) {
   const PlanEntry* hit = nullptr;
   double best_ratio = 1.26;                       // same layer, tile count within 25 %: the same tiling regime
   for (const PlanEntry& e : kPlanTable) {
     if (e.fmt != fmt || e.cin != cin || e.cout != cout) continue;
+    if (e.occ == 4 && !allow_pair) continue;
     const double r = (double)m_tiles > e.m_tiles ? (double)m_tiles / e.m_tiles : (double)e.m_tiles / (double)m_tiles;
-    if (r < best_ratio) {
+    // same distance: a pair entry (listed next to the best single-CTA tiling of the shape) wins
+    if (r < best_ratio || (hit && r == best_ratio && e.occ == 4)) {
       best_ratio = r;
       hit = &e;
     }
@@ -533,7 +778,7 @@ const PlanEntry* lookup_plan(int fmt, int cin, int cout, long long m_tiles) {
   return hit;
 }
 
-bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bool use_table = true) {
+bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bool use_table = true, bool allow_pair = true) {
   const int es = fmt_elem_bytes(fmt), npl = fmt_planes(fmt);
   int force_bn = env_int("AIDE_CONV_BN", 0), force_mb = env_int("AIDE_CONV_MB", 0);
   int force_stack = env_int("AIDE_CONV_STACK", -1), force_rb = env_int("AIDE_CONV_RB", 0);
@@ -543,10 +788,13 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
   const int force_res = env_int("AIDE_CONV_WRES", 0);
   // Two CTAs per SM (half the shared memory, <= 256 TMEM columns each): a second resident CTA issues MMAs while the
   // first waits on its barriers -- pays on the narrow layers whose tensor pipe idles between short MMAs.  1 / 2 force it.
+  // 4: the CTA-pair kernel (cta_group::2, conv3x3_halo2_tc_kernel) -- table / env only, like 2.
   int force_occ = env_int("AIDE_CONV_OCC", 0);
+  if (force_occ == 4 && (!allow_pair || fmt == AIDE_FMT_TF32X2)) force_occ = 0;
+  if (!env_int("AIDE_CONV_PAIR", 1)) allow_pair = false;
   if (use_table && !force_bn && !force_mb && force_stack < 0 && !force_rb && force_res == 0 && !force_occ &&
       env_int("AIDE_CONV_TABLE", 1)) {
-    if (const PlanEntry* e = lookup_plan(fmt, cin, cout, m_tiles)) {
+    if (const PlanEntry* e = lookup_plan(fmt, cin, cout, m_tiles, allow_pair)) {
       // build exactly the measured tiling through the same enumeration (forced parameters); fall back to the model
       // if it does not fit (cannot happen for the shapes it was measured on)
       force_bn = e->BN; force_mb = e->MB; force_stack = e->stack; force_rb = e->rb; force_occ = e->occ;
@@ -566,10 +814,11 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
         if (force_rb && rb != force_rb) continue;
         const int n_cchunks = cin / kc;
         const int nks = rb / 32;
-       for (int occ = 1; occ <= 2; ++occ) {
+       for (int occ = 1; occ <= 4; occ <<= 1) {
        if ((force_occ ? force_occ : 1) != occ) continue;          // the cost model never picks 2 by itself: table / env only
        for (int stack = 0; stack <= 1; ++stack) {
         if (stack && (npl != 2 || 2 * bn > 256)) continue;
+        if (occ == 4 && stack != (npl == 2)) continue;            // the pair kernel: stacked planes only
         if (force_stack >= 0 && stack != force_stack && !(stack == 0 && (npl != 2 || 2 * bn > 256))) continue;
         // accumulation chain per TMEM column of the LARGE partial sum: 3 MMAs per 32-byte K step, 2 when the weight
         // planes are stacked, 1 when both cross terms go to the small accumulator (lo_col; measured on the 256x256
@@ -587,6 +836,10 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
         c.a_stage = npl * mb * c.a_slot;
         c.b_plane = bn * rb;
         c.b_stage = npl * c.b_plane;
+        if (occ == 4) {                                            // per CTA: Y = one full plane (or half of the only one), X = half
+          c.yx = npl == 2 ? c.b_plane : 0;
+          c.b_stage = c.yx + c.b_plane / 2;
+        }
         const int avail = (occ == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 1024 - kBarBytes;   // 1 KB per CTA is reserved by the system
         c.a_stages = 2;
         int rest = avail - c.a_stages * c.a_stage;
@@ -613,7 +866,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
         }
         // resident-weight variant: the whole weight matrix of the layer next to >= 2 halo stages
         const int wbytes = 9 * n_cchunks * c.b_stage;
-        if (force_res != 0 && bn == cout && wbytes + 2 * c.a_stage <= avail) {
+        if (force_res != 0 && occ != 4 && bn == cout && wbytes + 2 * c.a_stage <= avail) {
           HaloPlan r = c;
           r.resident = 1;
           r.a_stages = (avail - wbytes) / c.a_stage;
@@ -634,7 +887,7 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
       if (best->cost < 0 || pick.cost < best->cost * 0.999) *best = pick;
     }
   }
-  if (best->cost < 0 && use_table) return make_plan(fmt, cin, cout, m_tiles, best, false);
+  if (best->cost < 0 && use_table) return make_plan(fmt, cin, cout, m_tiles, best, false, allow_pair);
   return best->cost >= 0;
 }
 
@@ -654,6 +907,24 @@ int launch2(const HaloParams& p, int grid, int smem, cudaStream_t st) {
 template <int KIND>
 int launch(const HaloParams& p, int grid, int smem, cudaStream_t st) {
   return p.row_bytes == 128 ? launch2<KIND, 4>(p, grid, smem, st) : launch2<KIND, 2>(p, grid, smem, st);
+}
+
+template <int KIND, int NKS>
+int launch_pair2(const Halo2Params& p, int grid, int smem, cudaStream_t st) {
+  static thread_local bool done[16] = {false};
+  int dev = 0;
+  AIDE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 16 || !done[dev]) {
+    AIDE_CUDA(cudaFuncSetAttribute(conv3x3_halo2_tc_kernel<KIND, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    if (dev < 16) done[dev] = true;
+  }
+  conv3x3_halo2_tc_kernel<KIND, NKS><<<grid, kThreads, smem, st>>>(p);      // __cluster_dims__(2,1,1): grid is even
+  AIDE_CHECK_LAUNCH();
+  return 0;
+}
+template <int KIND>
+int launch_pair(const Halo2Params& p, int grid, int smem, cudaStream_t st) {
+  return p.h.row_bytes == 128 ? launch_pair2<KIND, 4>(p, grid, smem, st) : launch_pair2<KIND, 2>(p, grid, smem, st);
 }
 
 }  // namespace
@@ -721,6 +992,16 @@ int halo_conv3x3(int fmt, const void* x0, const void* x1, int x_ctot, int x_coff
     if (act_tmap(&p.tmA1, dtype, x1, x_ctot, x_coff, cin, N, H, W, p.kc, kHW, kHH, p.row_bytes)) return 1;
     if (mat_tmap(&p.tmB1, dtype, w1, cout, 9 * cin, p.kc, p.BN, p.row_bytes)) return 1;
   }
+  if (pl.occ == 4) {
+    Halo2Params pp{};
+    pp.h = p;
+    pp.yx_bytes = pl.yx;
+    pp.pair_items = ceil_div(p.m_tiles, 2 * p.MB) * p.n_tiles;
+    if (mat_tmap(&pp.tmBh, dtype, w0, cout, 9 * cin, p.kc, p.BN / 2, p.row_bytes)) return 1;
+    const int pairs = pp.pair_items < kNumSMs / 2 ? pp.pair_items : kNumSMs / 2;
+    if (kind == K_BF16) return launch_pair<K_BF16>(pp, 2 * pairs, pl.smem, st);
+    return launch_pair<K_F16X2>(pp, 2 * pairs, pl.smem, st);
+  }
   const int max_ctas = kNumSMs * (pl.occ == 2 ? 2 : 1);
   const int grid = p.total_items < max_ctas ? p.total_items : max_ctas;
   if (kind == K_BF16) return launch<K_BF16>(p, grid, pl.smem, st);
@@ -734,7 +1015,7 @@ extern "C" int aide_conv3x3_plan_info(int fmt, int cin, int cout, int N, int H, 
   HaloPlan pl;
   make_plan(fmt, cin, cout, (long long)N * ceil_div(W, kTW) * ceil_div(H, kTH), &pl);
   out[0] = pl.BN; out[1] = pl.MB; out[2] = pl.nacc; out[3] = pl.nbuf; out[4] = pl.row_bytes; out[5] = pl.a_stages;
-  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack + 2 * pl.resident + 4 * (pl.occ == 2);
+  out[6] = pl.b_stages; out[7] = pl.smem; out[8] = pl.stack + 2 * pl.resident + 4 * (pl.occ == 2) + 8 * (pl.occ == 4);
   return 0;
 }
 

@@ -133,6 +133,8 @@ def test_conv_planner_returns_valid_tilings_for_every_layer():
                             assert rc == 0, (plan.kind, S, B, u.name, fmt)
                             bn, mb, nacc, nbuf, rb, a_st, b_st, smem, flags = list(out)
                             stack, resident, occ = flags & 1, (flags >> 1) & 1, 2 if flags & 4 else 1
+                            if flags & 8:        # CTA pair (cta_group::2): one CTA per SM, stacked planes, kind::f16 only
+                                assert fmt != 1 and stack == (fmt == 3) and not resident and bn * (1 + stack) <= 256
                             assert cout % bn == 0 and bn in (32, 64, 128, 256) and mb in (1, 2, 4)
                             assert nbuf * mb * nacc * bn * (1 + stack) <= 512 // occ        # two CTAs per SM share TMEM ...
                             assert smem <= 227 * 1024 // occ and a_st >= 1 and b_st >= 2 and rb in (64, 128)   # ... and smem

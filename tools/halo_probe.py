@@ -53,7 +53,7 @@ def plan(fmt, cin, cout, N, H, W):
     if A.lib.aide_conv3x3_plan_info(fmt, cin, cout, N, H, W, out):
         return None
     return dict(BN=out[0], MB=out[1], nacc=out[2], nbuf=out[3], rb=out[4], aS=out[5], bS=out[6], stack=out[8] & 1,
-                res=(out[8] >> 1) & 1, occ=2 if out[8] & 4 else 1)
+                res=(out[8] >> 1) & 1, occ=4 if out[8] & 8 else 2 if out[8] & 4 else 1)
 
 
 def check(fmt, N, H, W, cin, cout):
@@ -206,7 +206,7 @@ if args.sweep_full:
                 for mb in (1, 2, 4):
                     for stack in (0, 1):
                         for rb in (64, 128):
-                            for occ in (1, 2):
+                            for occ in (1, 2, 4):
                                 wres = 0
                                 os.environ.update(AIDE_CONV_BN=str(bn), AIDE_CONV_MB=str(mb), AIDE_CONV_STACK=str(stack),
                                                   AIDE_CONV_RB=str(rb), AIDE_CONV_WRES="0", AIDE_CONV_OCC=str(occ))
