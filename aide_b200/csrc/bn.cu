@@ -12,26 +12,31 @@ namespace aide {
 
 // ------------------------------------------------------------------ column reduction of partial rows
 // out[j] = sum_r partial[r*ld + j]  for j < cols, accumulated in fp64 in fixed order.
-// block = (32 columns, 8 row lanes)
+// block = (32 columns, kRedLanes row lanes).  These launches walk ~1200 partial rows of a few hundred columns: with 8 row
+// lanes every thread chained ~150 dependent loads (19-26 us per launch, 130 launches per step); 32 lanes and four loads
+// in flight cut the chain to ~10 round trips.
+constexpr int kRedLanes = 32;
 __global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int ld, int cols,
                                    float* __restrict__ out) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kRedLanes][33];
   int j = blockIdx.x * 32 + threadIdx.x;
   double acc = 0.0;
-  if (j < cols)
-    for (int r = threadIdx.y; r < rows; r += 8) acc += (double)partial[(size_t)r * ld + j];
+  if (j < cols) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < rows; r += kRedLanes) acc += (double)partial[(size_t)r * ld + j];
+  }
   sm[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && j < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    for (int k = 0; k < kRedLanes; ++k) t += sm[k][threadIdx.x];
     out[j] = (float)t;
   }
 }
 
 int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* out, cudaStream_t st) {
-  reduce_rows_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, st>>>(partial, rows, ld, cols, out);
+  reduce_rows_kernel<<<ceil_div(cols, 32), dim3(32, kRedLanes), 0, st>>>(partial, rows, ld, cols, out);
   AIDE_CHECK_LAUNCH();
   return 0;
 }
@@ -41,19 +46,28 @@ int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* 
 // chunk of kStatChunk rows into an fp64 sum with many blocks and stores it IN PLACE as a (hi, lo) float pair in
 // the first two rows of its own chunk (no other block touches those cells); stage 2 -- the finalize kernel --
 // then walks only the folded rows.  Fixed order throughout: bit-reproducible run to run.
-constexpr int kStatChunk = 64;
+// The chunk length depends on the rows of ONE statistics group only (a stacked-batch forward folds every view exactly
+// like a separate forward would): 64 rows up to 4096, then rows/64 -- at 16384 rows (8 slices of 256x256) 64 chunks of
+// 256 rows per channel group instead of 256 chunks of 64, whose 5120 blocks of 2 loads per thread were pure
+// block-scheduling latency (92 us for 42 MB).
+constexpr int kStatChunkMin = 64;
+__host__ __device__ inline int stat_chunk(int rows) {
+  const int c = (rows / 64) & ~31;
+  return c < kStatChunkMin ? kStatChunkMin : c > 1024 ? 1024 : c;
+}
 
-constexpr int kStatLanes = 32;   // row lanes per block: these kernels are latency bound (a handful of dependent loads)
+constexpr int kStatLanes = 8;    // row lanes per block: 256-thread blocks, 8 independent loads per thread on a 64-row chunk
+                                 // (1024-thread blocks with 2 loads per thread were bound by block scheduling)
 
-__global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int cols /* = 2*C */) {
+__global__ void bn_stat_fold_kernel(float* __restrict__ partial, int rows, int cols /* = 2*C */, int chunk) {
   partial += (size_t)blockIdx.z * rows * cols;          // statistics group (stacked-batch forward): its own row block
   __shared__ double sm[kStatLanes][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
-  const int r0 = blockIdx.y * kStatChunk;
-  const int r1 = min(rows, r0 + kStatChunk);
+  const int r0 = blockIdx.y * chunk;
+  const int r1 = min(rows, r0 + chunk);
   double acc = 0.0;
   if (j < cols) {
-#pragma unroll 2
+#pragma unroll 8
     for (int r = r0 + threadIdx.y; r < r1; r += kStatLanes) acc += (double)partial[(size_t)r * cols + j];
   }
   sm[threadIdx.y][threadIdx.x] = acc;
@@ -148,7 +162,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int groups
 // LAST block of a channel group to arrive finalises those 16 channels for all statistics groups, reading the folded
 // (hi, lo) pairs of every chunk in fixed order (bit-reproducible whichever block happens to be last).  tickets: one
 // zero-initialised counter per channel group, left at zero again.
-__global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int rows, int C, int n_chunks, int sgroups,
+__global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int rows, int C, int chunk, int n_chunks, int sgroups,
                                              double count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                              float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
                                              float* __restrict__ scale_shift, float* __restrict__ mean_rstd,
@@ -162,11 +176,11 @@ __global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int ro
   const int j = stat * C + c;                                 // column of this thread in a partial row
   {
     float* part = partial + (size_t)blockIdx.z * rows * cols;
-    const int r0 = blockIdx.y * kStatChunk;
-    const int r1 = min(rows, r0 + kStatChunk);
+    const int r0 = blockIdx.y * chunk;
+    const int r1 = min(rows, r0 + chunk);
     double acc = 0.0;
     if (cvalid) {
-#pragma unroll 2
+#pragma unroll 8
       for (int r = r0 + threadIdx.y; r < r1; r += kStatLanes) acc += (double)part[(size_t)r * cols + j];
     }
     sm[threadIdx.y][threadIdx.x] = acc;
@@ -200,8 +214,9 @@ __global__ void bn_stat_fold_finalize_kernel(float* __restrict__ partial, int ro
     const float* part = partial + (size_t)sg * rows * cols;
     double a = 0.0;
     if (cvalid) {
+#pragma unroll 4
       for (int g = threadIdx.y; g < n_chunks; g += kStatLanes) {
-        const int r = g * kStatChunk;
+        const int r = g * chunk;
         a += (double)__ldcg(part + (size_t)r * cols + j);
         if (r + 1 < rows) a += (double)__ldcg(part + (size_t)(r + 1) * cols + j);
       }
@@ -506,25 +521,27 @@ __global__ void dz_scale_kernel(unsigned int* __restrict__ gmax_bits, const floa
 }
 
 // Column reduction of the backward partial rows (reduce_rows_kernel) whose LAST block (ticket) also derives the dZ scale:
-// one launch instead of two per unit.  block = (32, 8); ticket: zero on entry, left zero.
+// one launch instead of two per unit.  block = (32, kRedLanes); ticket: zero on entry, left zero.
 __global__ void bn_bwd_sums_scale_kernel(const float* __restrict__ partial, int rows, int C, float* __restrict__ sums,
                                          unsigned int* __restrict__ gmax_bits, const float* __restrict__ mean_rstd,
                                          const float* __restrict__ gamma, float inv_count, float* __restrict__ scale_out,
                                          unsigned int* __restrict__ ticket) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kRedLanes][33];
   __shared__ float red[32];
   __shared__ unsigned int s_last;
   const int cols = 2 * C;
   const int j = blockIdx.x * 32 + threadIdx.x;
   double acc = 0.0;
-  if (j < cols)
-    for (int r = threadIdx.y; r < rows; r += 8) acc += (double)partial[(size_t)r * cols + j];
+  if (j < cols) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < rows; r += kRedLanes) acc += (double)partial[(size_t)r * cols + j];
+  }
   sm[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && j < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    for (int k = 0; k < kRedLanes; ++k) t += sm[k][threadIdx.x];
     sums[j] = (float)t;
     __threadfence();
   }
@@ -680,19 +697,20 @@ extern "C" int aide_bn_finalize_grouped(float* stat_partial, int rows, int sgrou
                "bn_finalize: missing statistics input");
   dim3 block(32, kStatLanes), grid(ceil_div(C, 32));
   int groups = rows, row_stride = 1, sub = 1;
-  if (training && rows > 2 * kStatChunk) {   // many tiles: fold chunks in parallel first (in place)
-    groups = ceil_div(rows, kStatChunk);
+  const int chunk = stat_chunk(rows);
+  if (training && rows > 2 * kStatChunkMin) {   // many tiles: fold chunks in parallel first (in place)
+    groups = ceil_div(rows, chunk);
     if (tickets) {                           // ... and let the last block of each channel group finalize: one launch
       bn_stat_fold_finalize_kernel<<<dim3(ceil_div(C, 16), groups, sgroups), block, 0, as_stream(stream)>>>(
-          stat_partial, rows, C, groups, sgroups, count, gamma, beta, running_mean, running_var, momentum, eps,
+          stat_partial, rows, C, chunk, groups, sgroups, count, gamma, beta, running_mean, running_var, momentum, eps,
           scale_shift, mean_rstd, tickets);
       AIDE_CHECK_LAUNCH();
       return 0;
     }
     bn_stat_fold_kernel<<<dim3(ceil_div(2 * C, 32), groups, sgroups), block, 0, as_stream(stream)>>>(stat_partial, rows,
-                                                                                                      2 * C);
+                                                                                                      2 * C, chunk);
     AIDE_CHECK_LAUNCH();
-    row_stride = kStatChunk;
+    row_stride = chunk;
     sub = 2;
   }
   bn_finalize_kernel<<<grid, block, 0, as_stream(stream)>>>(stat_partial, groups, row_stride, sub, rows, C, count,
@@ -804,17 +822,17 @@ extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, c
   if (fmt == AIDE_FMT_F16X2) {
     AIDE_REQUIRE(gmax && dz_scale, "bn_relu_bwd_apply: F16X2 needs gmax (from bn_relu_bwd_reduce) and dz_scale[2]");
     if (tickets) {
-      bn_bwd_sums_scale_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, C, dbeta, gbits, mean_rstd, gamma,
+      bn_bwd_sums_scale_kernel<<<ceil_div(2 * C, 32), dim3(32, kRedLanes), 0, st>>>(partial, rows, C, dbeta, gbits, mean_rstd, gamma,
                                                                             inv, dz_scale, tickets);
       AIDE_CHECK_LAUNCH();
     } else {
-      reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
+      reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, kRedLanes), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
       AIDE_CHECK_LAUNCH();
       dz_scale_kernel<<<1, 256, 0, st>>>(gbits, mean_rstd, gamma, dbeta, inv, C, dz_scale);
       AIDE_CHECK_LAUNCH();
     }
   } else {
-    reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
+    reduce_rows_kernel<<<ceil_div(2 * C, 32), dim3(32, kRedLanes), 0, st>>>(partial, rows, 2 * C, 2 * C, dbeta);
     AIDE_CHECK_LAUNCH();
   }
   dim3 block(gm.cx, gm.ty), grid(gm.rows, gm.cgroups);
@@ -829,7 +847,7 @@ extern "C" int aide_bn_relu_bwd_apply(int fmt, const float* g, const float* z, c
                              fuse_dbias ? tickets + 1 : nullptr, dbias_conv)));
   AIDE_CHECK_LAUNCH();
   if (dbias_conv && !fuse_dbias) {
-    reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(partial2, rows, C, C, dbias_conv);
+    reduce_rows_kernel<<<ceil_div(C, 32), dim3(32, kRedLanes), 0, st>>>(partial2, rows, C, C, dbias_conv);
     AIDE_CHECK_LAUNCH();
   }
   return 0;

@@ -116,42 +116,63 @@ __global__ void conv1x1_fwd16_kernel(CView x, const float* __restrict__ w, const
 }
 
 // blockDim = (cx, ty), grid = (rows, cgroups); each thread owns 4 channels.
-template <int FMT>
-__global__ void conv1x1_bwd_kernel(CView x, int C, const float* __restrict__ w, const float* __restrict__ dl, int K,
+template <int FMT, int KB>            // KB: compile-time bound of the class count (2 for every AIDE head, else KB)
+__global__ void __launch_bounds__(256, 2) conv1x1_bwd_kernel(CView x, int C, const float* __restrict__ w, const float* __restrict__ dl, int K,
                                    size_t npix, int HW, float* __restrict__ dx, float* __restrict__ partial) {
   extern __shared__ float smem[];  // [ty][cx][K*4 + K]
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const bool cvalid = c < C;
   const int stride = K * 4 + K;
-  float aw[kMaxK][4], ab[kMaxK];
-  float4 wv[kMaxK];
+  float aw[KB][4], ab[KB];
+  float4 wv[KB];
 #pragma unroll
-  for (int k = 0; k < kMaxK; ++k) {
+  for (int k = 0; k < KB; ++k) {
     aw[k][0] = aw[k][1] = aw[k][2] = aw[k][3] = 0.f;
     ab[k] = 0.f;
     wv[k] = (cvalid && k < K) ? *reinterpret_cast<const float4*>(w + (size_t)k * C + c) : make_float4(0, 0, 0, 0);
   }
   if (cvalid) {
-    for (size_t p = (size_t)blockIdx.x * blockDim.y + threadIdx.y; p < npix; p += (size_t)gridDim.x * blockDim.y) {
-      size_t n = p / HW, hw = p % HW;
-      float4 xv = ld4<FMT>(x.p0, x.p1, p * x.ctot + x.coff + c);
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    // two pixels per iteration (independent loads in flight; 32-bit index arithmetic -- the 64-bit division per pixel
+    // and the single pixel in flight held this kernel at 0.19 of the copy peak); same accumulation order
+    const unsigned int np = (unsigned int)npix, step = gridDim.x * blockDim.y;
+    for (unsigned int p = blockIdx.x * blockDim.y + threadIdx.y; p < np; p += 2 * step) {
+      const unsigned int q = p + step;
+      const bool two = q < np;
+      const unsigned int n0 = p / (unsigned int)HW, hw0 = p - n0 * (unsigned int)HW;
+      const unsigned int n1 = two ? q / (unsigned int)HW : n0, hw1 = two ? q - n1 * (unsigned int)HW : hw0;
+      const float4 xv0 = ld4<FMT>(x.p0, x.p1, (size_t)p * x.ctot + x.coff + c);
+      const float4 xv1 = two ? ld4<FMT>(x.p0, x.p1, (size_t)q * x.ctot + x.coff + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float g0[KB], g1[KB];
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k) {
-        if (k < K) {
-          float g = __ldg(dl + (n * K + k) * HW + hw);
-          d.x += g * wv[k].x; d.y += g * wv[k].y; d.z += g * wv[k].z; d.w += g * wv[k].w;
-          aw[k][0] += g * xv.x; aw[k][1] += g * xv.y; aw[k][2] += g * xv.z; aw[k][3] += g * xv.w;
-          ab[k] += g;
-        }
+      for (int k = 0; k < KB; ++k) {
+        g0[k] = k < K ? __ldg(dl + ((size_t)n0 * K + k) * HW + hw0) : 0.f;
+        g1[k] = (k < K && two) ? __ldg(dl + ((size_t)n1 * K + k) * HW + hw1) : 0.f;
       }
-      *reinterpret_cast<float4*>(dx + p * C + c) = d;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const float4 xv = u ? xv1 : xv0;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          if (k < K) {
+            const float g = u ? g1[k] : g0[k];
+            d.x += g * wv[k].x; d.y += g * wv[k].y; d.z += g * wv[k].z; d.w += g * wv[k].w;
+            aw[k][0] += g * xv.x; aw[k][1] += g * xv.y; aw[k][2] += g * xv.z; aw[k][3] += g * xv.w;
+            ab[k] += g;
+          }
+        }
+        *reinterpret_cast<float4*>(dx + (size_t)(u ? q : p) * C + c) = d;
+      }
     }
   }
   float* row = smem + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * stride;
-  for (int k = 0; k < K; ++k) {
-    row[k * 4 + 0] = aw[k][0]; row[k * 4 + 1] = aw[k][1]; row[k * 4 + 2] = aw[k][2]; row[k * 4 + 3] = aw[k][3];
-    row[K * 4 + k] = ab[k];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) {
+    if (k < K) {
+      row[k * 4 + 0] = aw[k][0]; row[k * 4 + 1] = aw[k][1]; row[k * 4 + 2] = aw[k][2]; row[k * 4 + 3] = aw[k][3];
+      row[K * 4 + k] = ab[k];
+    }
   }
   __syncthreads();
   if (threadIdx.y == 0 && cvalid) {
@@ -174,7 +195,7 @@ static HeadGeom head_geom(int N, int H, int W, int C) {
   g.cgroups = ceil_div(c4, g.cx);
   long long npix = (long long)N * H * W;
   long long want = (npix + g.ty * 8 - 1) / (g.ty * 8);
-  long long cap = (long long)kNumSMs * 4 / g.cgroups;
+  long long cap = (long long)kNumSMs * 8 / g.cgroups;
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -229,8 +250,14 @@ extern "C" int aide_conv1x1_bwd(int fmt, const void* x_p0, const void* x_p1, int
   dim3 block(g.cx, g.ty), grid(g.rows, g.cgroups);
   size_t smem = (size_t)g.cx * g.ty * (K * 5) * sizeof(float);
   size_t npix = (size_t)N * H * W;
-  AIDE_DISPATCH_FMT(fmt, (conv1x1_bwd_kernel<FMT><<<grid, block, smem, as_stream(stream)>>>(
-                             x, C, w, dlogits_nchw, K, npix, H * W, dx, partial)));
+  AIDE_REQUIRE(npix < (1ull << 31), "conv1x1_bwd: more than 2^31 pixels");
+  if (K <= 2) {
+    AIDE_DISPATCH_FMT(fmt, (conv1x1_bwd_kernel<FMT, 2><<<grid, block, smem, as_stream(stream)>>>(
+                               x, C, w, dlogits_nchw, K, npix, H * W, dx, partial)));
+  } else {
+    AIDE_DISPATCH_FMT(fmt, (conv1x1_bwd_kernel<FMT, kMaxK><<<grid, block, smem, as_stream(stream)>>>(
+                               x, C, w, dlogits_nchw, K, npix, H * W, dx, partial)));
+  }
   AIDE_CHECK_LAUNCH();
   int ld = K * C + K;
   return launch_reduce_rows(partial, g.rows, ld, ld, dw_db, as_stream(stream));

@@ -7,6 +7,8 @@
 // first, then along H.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace aide {
 
 __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
@@ -88,59 +90,64 @@ __device__ __forceinline__ void st8(void* p0, void* p1, size_t e, const float (&
   }
 }
 
-// blockDim = (cx, ty): threadIdx.x walks the channels of a pixel in 8-channel (128-bit) vectors, whole OUTPUT rows are
-// dealt to blocks and threadIdx.y walks along the row -- the vertical source rows / weights are block-uniform and the
-// inner loop has no integer division.
+// blockDim = (cx, ty): threadIdx.x walks the channels of a pixel in 8-channel (128-bit) vectors; a block owns a PAIR of
+// output rows (2i, 2i+1) and threadIdx.y walks the output column pairs (2j, 2j+1).  With align_corners the four outputs
+// of such a 2x2 block read only 3 x 3 distinct source pixels (rows {y0, y1} of the upper output and y1 of the lower one;
+// the lower output's first row is one of the upper one's two) -- 18 plane loads per 4 outputs instead of 32, which is
+// what bounds this kernel (L1 / L2 request rate, not HBM: 0.50 of the copy peak before).  Per output the operations and
+// their order are those of the 4-channel kernel: along W first, then along H.
 template <int FMT>
-__global__ void upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w, int C, float sh, float sw) {
+__global__ void __launch_bounds__(256, 2) upsample2x_fwd16_kernel(CView src, View dst, int N, int h, int w, int C, float sh, float sw) {
   const int H = 2 * h, W = 2 * w;
-  const int total_rows = N * H;
-  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
-    const int n = row / H, oy = row - n * H;
-    int y0, y1;
-    float ly0, ly1;
-    src_index(sh, oy, h, y0, y1, ly0, ly1);
-    const size_t r0 = ((size_t)n * h + y0) * w, r1 = ((size_t)n * h + y1) * w;
-    const size_t drow = (size_t)row * W;
-    // two output pixels per iteration (16 independent 128-bit plane loads in flight per thread: the one-pixel loop ran
-    // at ~0.5 of the copy peak, latency bound)
-    for (int ox = threadIdx.y; ox < W; ox += 2 * blockDim.y) {
-      const int oxb = ox + blockDim.y;
-      const bool two = oxb < W;
-      int x0, x1, u0, u1;
-      float lx0, lx1, mx0, mx1;
-      src_index(sw, ox, w, x0, x1, lx0, lx1);
-      src_index(sw, two ? oxb : ox, w, u0, u1, mx0, mx1);
-      const size_t s00 = (r0 + x0) * src.ctot + src.coff, s01 = (r0 + x1) * src.ctot + src.coff;
-      const size_t s10 = (r1 + x0) * src.ctot + src.coff, s11 = (r1 + x1) * src.ctot + src.coff;
-      const size_t t00 = (r0 + u0) * src.ctot + src.coff, t01 = (r0 + u1) * src.ctot + src.coff;
-      const size_t t10 = (r1 + u0) * src.ctot + src.coff, t11 = (r1 + u1) * src.ctot + src.coff;
-      const size_t d0 = (drow + ox) * dst.ctot + dst.coff, d1 = (drow + oxb) * dst.ctot + dst.coff;
+  const int total_pairs = N * h;
+  for (int rp = blockIdx.x; rp < total_pairs; rp += gridDim.x) {
+    const int n = rp / h, oya = 2 * (rp - n * h);
+    int ya0, ya1, yb0, yb1;
+    float lya0, lya1, lyb0, lyb1;
+    src_index(sh, oya, h, ya0, ya1, lya0, lya1);
+    src_index(sh, oya + 1, h, yb0, yb1, lyb0, lyb1);
+    const bool ib0 = yb0 != ya0;                               // the lower output's first source row is ya1 (else ya0)
+    const size_t r0 = ((size_t)n * h + ya0) * w, r1 = ((size_t)n * h + ya1) * w, r2 = ((size_t)n * h + yb1) * w;
+    const size_t drow_a = ((size_t)n * H + oya) * W, drow_b = drow_a + W;
+    for (int j = threadIdx.y; j < w; j += blockDim.y) {
+      const int oxa = 2 * j;
+      int xa0, xa1, xb0, xb1;
+      float lxa0, lxa1, lxb0, lxb1;
+      src_index(sw, oxa, w, xa0, xa1, lxa0, lxa1);
+      src_index(sw, oxa + 1, w, xb0, xb1, lxb0, lxb1);
+      const bool jb0 = xb0 != xa0;
+      const size_t c0 = (size_t)xa0 * src.ctot + src.coff, c1 = (size_t)xa1 * src.ctot + src.coff,
+                   c2 = (size_t)xb1 * src.ctot + src.coff;
+      const size_t da = (drow_a + oxa) * dst.ctot + dst.coff, db = (drow_b + oxa) * dst.ctot + dst.coff;
       for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
-        float a[8], b[8], d[8], e[8], o[8], a2[8], b2[8], d2[8], e2[8];
-        ld8<FMT>(src.p0, src.p1, s00 + c, a);
-        ld8<FMT>(src.p0, src.p1, s01 + c, b);
-        ld8<FMT>(src.p0, src.p1, s10 + c, d);
-        ld8<FMT>(src.p0, src.p1, s11 + c, e);
-        ld8<FMT>(src.p0, src.p1, t00 + c, a2);
-        ld8<FMT>(src.p0, src.p1, t01 + c, b2);
-        ld8<FMT>(src.p0, src.p1, t10 + c, d2);
-        ld8<FMT>(src.p0, src.p1, t11 + c, e2);
+        float v[3][3][8];
+        ld8<FMT>(src.p0, src.p1, r0 * src.ctot + c0 + c, v[0][0]);
+        ld8<FMT>(src.p0, src.p1, r0 * src.ctot + c1 + c, v[0][1]);
+        ld8<FMT>(src.p0, src.p1, r0 * src.ctot + c2 + c, v[0][2]);
+        ld8<FMT>(src.p0, src.p1, r1 * src.ctot + c0 + c, v[1][0]);
+        ld8<FMT>(src.p0, src.p1, r1 * src.ctot + c1 + c, v[1][1]);
+        ld8<FMT>(src.p0, src.p1, r1 * src.ctot + c2 + c, v[1][2]);
+        ld8<FMT>(src.p0, src.p1, r2 * src.ctot + c0 + c, v[2][0]);
+        ld8<FMT>(src.p0, src.p1, r2 * src.ctot + c1 + c, v[2][1]);
+        ld8<FMT>(src.p0, src.p1, r2 * src.ctot + c2 + c, v[2][2]);
+        float oaa[8], oab[8], oba[8], obb[8];                  // [output row a/b][output column a/b]
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          // same operation order as the 4-channel kernel: along W first, then along H
-          const float t0 = lx0 * a[k] + lx1 * b[k], t1 = lx0 * d[k] + lx1 * e[k];
-          o[k] = ly0 * t0 + ly1 * t1;
-        }
-        st8<FMT>(dst.p0, dst.p1, d0 + c, o);
-        if (two) {
+          float ha[3], hb[3];                                  // the three source rows, interpolated along W
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float t0 = mx0 * a2[k] + mx1 * b2[k], t1 = mx0 * d2[k] + mx1 * e2[k];
-            o[k] = ly0 * t0 + ly1 * t1;
+          for (int r = 0; r < 3; ++r) {
+            ha[r] = lxa0 * v[r][0][k] + lxa1 * v[r][1][k];
+            hb[r] = lxb0 * (jb0 ? v[r][1][k] : v[r][0][k]) + lxb1 * v[r][2][k];
           }
-          st8<FMT>(dst.p0, dst.p1, d1 + c, o);
+          oaa[k] = lya0 * ha[0] + lya1 * ha[1];
+          oab[k] = lya0 * hb[0] + lya1 * hb[1];
+          oba[k] = lyb0 * (ib0 ? ha[1] : ha[0]) + lyb1 * ha[2];
+          obb[k] = lyb0 * (ib0 ? hb[1] : hb[0]) + lyb1 * hb[2];
         }
+        st8<FMT>(dst.p0, dst.p1, da + c, oaa);
+        st8<FMT>(dst.p0, dst.p1, da + dst.ctot + c, oab);
+        st8<FMT>(dst.p0, dst.p1, db + c, oba);
+        st8<FMT>(dst.p0, dst.p1, db + dst.ctot + c, obb);
       }
     }
   }
@@ -202,6 +209,85 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dhi, int ctot, i
       }
     }
     *reinterpret_cast<float4*>(dlo + pix * C + c) = acc;
+  }
+}
+
+// Row form of the same gather (the fast path): a block owns one low-res row, so the <= 4 contributing output rows and
+// their vertical weights are block-uniform; threadIdx.y walks the pixels of the row, threadIdx.x the channels in 128-bit
+// vectors; the <= 4 x 4 taps are independent loads.  Same candidates, same weights and the same summation order (output
+// rows ascending, columns ascending inside a row) as upsample2x_bwd_kernel: bit-identical results, ~3x its bandwidth.
+__global__ void __launch_bounds__(256, 2) upsample2x_bwd_rows_kernel(const float* __restrict__ dhi, int ctot, int coff, float* __restrict__ dlo,
+                                           int N, int h, int w, int C, float sh, float sw) {
+  const int H = 2 * h, W = 2 * w;
+  const int total_rows = N * h;
+  for (int row = blockIdx.x; row < total_rows; row += gridDim.x) {
+    const int n = row / h, iy = row - n * h;
+    int oy_lo = 0, oy_hi = H - 1;
+    if (sh > 0.f) {
+      oy_lo = max(0, (int)floorf((float)(iy - 1) / sh) - 1);
+      oy_hi = min(H - 1, (int)ceilf((float)(iy + 1) / sh) + 1);
+    }
+    int oys[4] = {0, 0, 0, 0};
+    float wys[4] = {0.f, 0.f, 0.f, 0.f};
+    int nr = 0;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(sh, oy, h, y0, y1, ly0, ly1);
+      const float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+      if (wy != 0.f && nr < 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k == nr) { oys[k] = oy; wys[k] = wy; }
+        ++nr;
+      }
+    }
+    for (int ix = threadIdx.y; ix < w; ix += blockDim.y) {
+      int ox_lo = 0, ox_hi = W - 1;
+      if (sw > 0.f) {
+        ox_lo = max(0, (int)floorf((float)(ix - 1) / sw) - 1);
+        ox_hi = min(W - 1, (int)ceilf((float)(ix + 1) / sw) + 1);
+      }
+      int oxs[4] = {0, 0, 0, 0};
+      float wxs[4] = {0.f, 0.f, 0.f, 0.f};
+      int nc = 0;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1;
+        float lx0, lx1;
+        src_index(sw, ox, w, x0, x1, lx0, lx1);
+        const float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+        if (wx != 0.f && nc < 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k == nc) { oxs[k] = ox; wxs[k] = wx; }
+          ++nc;
+        }
+      }
+      const size_t opix = ((size_t)n * h + iy) * w + ix;
+      for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        float4 v[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[r][j] = (r < nr && j < nc)
+                          ? __ldg(reinterpret_cast<const float4*>(dhi + (((size_t)n * H + oys[r]) * W + oxs[j]) * ctot + coff + c))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (r < nr && j < nc) {
+              const float ww = wys[r] * wxs[j];
+              acc.x += ww * v[r][j].x;
+              acc.y += ww * v[r][j].y;
+              acc.z += ww * v[r][j].z;
+              acc.w += ww * v[r][j].w;
+            }
+        *reinterpret_cast<float4*>(dlo + opix * C + c) = acc;
+      }
+    }
   }
 }
 
@@ -294,7 +380,7 @@ extern "C" int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_
     int cx = C / 8 < 32 ? C / 8 : 32;                   // threads across the channels of one pixel
     while (cx & (cx - 1)) cx &= cx - 1;                 // power of two
     const dim3 block(cx, 256 / cx);
-    long long blocks = (long long)N * 2 * h;            // one output row per block iteration
+    long long blocks = (long long)N * h;                // one pair of output rows per block iteration
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     const float sh = ac_scale(h, 2 * h), sw = ac_scale(w, 2 * w);
     if (fmt == AIDE_FMT_F16X2)
@@ -316,6 +402,17 @@ extern "C" int aide_upsample2x_fwd(int fmt, const void* src_p0, const void* src_
 extern "C" int aide_upsample2x_bwd(const float* dhi, int dhi_ctot, int dhi_coff, float* dlo, int N, int h, int w,
                                    int C, void* stream) {
   AIDE_REQUIRE(dhi && dlo && C % 4 == 0 && dhi_coff % 4 == 0 && dhi_ctot % 4 == 0, "upsample2x_bwd: bad arguments");
+  static const bool rows_form = !(std::getenv("AIDE_UPSAMPLE_BWD_ROWS") && std::atoi(std::getenv("AIDE_UPSAMPLE_BWD_ROWS")) == 0);
+  if (rows_form && h >= 2 && w >= 2) {        // (a 1-pixel map has > 4 taps per direction: every output reads it)
+    int cx = C / 4 < 32 ? C / 4 : 32;
+    while (cx & (cx - 1)) cx &= cx - 1;
+    long long blocks = (long long)N * h;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    upsample2x_bwd_rows_kernel<<<(int)blocks, dim3(cx, 256 / cx), 0, as_stream(stream)>>>(
+        dhi, dhi_ctot, dhi_coff, dlo, N, h, w, C, ac_scale(h, 2 * h), ac_scale(w, 2 * w));
+    AIDE_CHECK_LAUNCH();
+    return 0;
+  }
   size_t total = (size_t)N * h * w * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

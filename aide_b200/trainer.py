@@ -99,6 +99,9 @@ class AideTrainer:
         # gradient all-reduce in buckets launched while the backward pass is still running (decoder first); 0 / 1 = one
         # all-reduce per net after its backward
         self.n_buckets = int(os.environ.get("AIDE_B200_BUCKETS", "4"))
+        # diagnostic only (tools/gpu_session19.sh): skip the gradient all-reduce to time the slowest rank's compute alone --
+        # the replicas diverge, never use it for training
+        self._comm = os.environ.get("AIDE_B200_NO_COMM", "0") != "1"
         self._buckets = {id(n): {t: r for t, r in E.gradient_buckets(n._plan, n._glayout, self.n_buckets)}
                          for n in (self.net1, self.net2)}
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
@@ -261,7 +264,7 @@ class AideTrainer:
             d = L.loss_backward(lg, t_other, me["sums"], coef[0], coef[1], coef[2] if has_q else None,
                                 other["q"], other["w"])
             works = []
-            bucketed = self.world > 1 and self.n_buckets > 1
+            bucketed = self.world > 1 and self.n_buckets > 1 and self._comm
             if bucketed:
                 ranges = self._buckets[id(net)]
 
@@ -271,7 +274,7 @@ class AideTrainer:
                                                                   async_op=True))
             net._engine_backward(me["tape"], d, on_done if bucketed else None)
             flat = net.last_grad_flat
-            if self.world > 1:
+            if self.world > 1 and self._comm:
                 if not bucketed:
                     torch.distributed.all_reduce(flat, group=self.group)
                 for w_ in works:

@@ -174,7 +174,11 @@ def timed_steps(fn, steps, world, device):
     e1.record()
     torch.cuda.synchronize(device)
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    timed_steps.rank_ms = [round(ms.item() / max(steps, 1), 3)]
     if world > 1:
+        allms = torch.empty(world, device=device)
+        torch.distributed.all_gather_into_tensor(allms, ms)
+        timed_steps.rank_ms = [round(v / max(steps, 1), 3) for v in allms.tolist()]      # per-rank skew, for the record
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.barrier()
     return ms.item()
@@ -662,6 +666,7 @@ def main():
     ms = timed_steps(dev_step, K, world, device)
     launches = A.lib.aide_launch_count() + tr.graph_launches - l0
     host_enqueue_ms = timed_steps.host_ms
+    rank_ms = timed_steps.rank_ms
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 
@@ -692,7 +697,7 @@ def main():
         "engine": {"mode": args.mode, "cuda_graph": bool(tr.cuda_graph), "stacked_aug_forward": bool(tr.group_augs), "stacked_train_forward": bool(tr.stack_train),
                    "resident_batches": n_pool, "global_select": bool(tr.global_select)},
         "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
-        "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 2), "rank_ms_per_step": rank_ms,
         "clocks": clocks, "e2e": e2e,
     }
     out["algorithmic_tflops"] = round(value * out["config"]["algorithmic_gflop_per_slice"] / 1e3, 1)

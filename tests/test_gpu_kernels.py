@@ -50,6 +50,33 @@ def test_conv3x3_forward_and_stats(dev, fmt, shape):
     assert relmax(s[1], (got.cpu() ** 2).sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("fmt", [2, 3])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32, 32), (1, 32, 32, 64, 64), (2, 8, 8, 128, 256), (1, 20, 12, 64, 32),
+                                   (3, 24, 40, 96, 96), (1, 8, 8, 1024, 512), (1, 16, 8, 64, 128), (5, 8, 16, 32, 64)])
+def test_conv3x3_cta_pair_kernel_equals_single_cta_kernel(dev, fmt, shape, monkeypatch):
+    """The cta_group::2 kernel (two CTAs, one MMA of 256 pixels, half of the weight rows in each CTA) forced on small and
+    ragged maps -- odd tile counts exercise the zero-filled padding tile of the last pair: same tolerance against fp32
+    as every conv kernel, and the SAME BITS as the single-CTA kernel on the same tiling (identical accumulation chains:
+    the pair only changes which SM holds which rows)."""
+    from aide_b200 import ops
+    N, H, W, cin, cout = shape
+    x, w, b = rnd(N, cin, H, W, seed=1), rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5), rnd(cout, seed=3)
+    ref = F.conv2d(x, w, b, padding=1)
+    a = ops.from_nchw(x.to(dev), fmt)
+    out = {}
+    monkeypatch.setenv("AIDE_CONV_TABLE", "0")
+    monkeypatch.setenv("AIDE_CONV_BN", "32" if cout % 64 else "64")
+    monkeypatch.setenv("AIDE_CONV_MB", "1")
+    monkeypatch.setenv("AIDE_CONV_STACK", "1")
+    for occ in (4, 1):
+        monkeypatch.setenv("AIDE_CONV_OCC", str(occ))
+        z, part = ops.conv3x3(a, w.to(dev), b.to(dev), stats=True)
+        torch.cuda.synchronize()
+        out[occ] = (ops.nhwc_to_nchw(z).cpu(), part.cpu())
+    assert relmax(out[4][0], ref) < TOL[fmt]
+    assert torch.equal(out[4][0], out[1][0]) and torch.equal(out[4][1], out[1][1])
+
+
 def test_conv3x3_first_layer_cin3(dev):
     from aide_b200 import ops
     x, w, b = rnd(2, 3, 32, 48, seed=1), rnd(32, 3, 3, 3, seed=2, scale=0.2), rnd(32, seed=3)
@@ -259,7 +286,7 @@ def test_bn_relu_pool_backward(dev, fmt, gscale, fused):
 
 
 @pytest.mark.parametrize("fmt", [0, 1, 2, 3])
-@pytest.mark.parametrize("hw", [(16, 16), (1, 1), (6, 10)])
+@pytest.mark.parametrize("hw", [(16, 16), (1, 1), (6, 10), (2, 2), (3, 5), (5, 2), (64, 48), (1, 7)])
 def test_upsample_bilinear(dev, fmt, hw):
     from aide_b200 import ops
     h, w = hw

@@ -1,0 +1,32 @@
+#!/bin/bash
+# N GPUs (N = number visible): weak point, UNet-320 (BASELINE config 5), strong point (global batch 64), and at N = 8 the
+# all-reduce bucket count / NCCL CTA cap / global small-loss selection variants
+set +e
+N=$(nvidia-smi -L | wc -l)
+O=gpurun_out/s17
+mkdir -p $O
+run() {
+  name=$1; shift
+  envs=()
+  while [[ "$1" == *=* ]]; do envs+=("$1"); shift; done
+  if [ "$N" -gt 1 ]; then
+    env "${envs[@]}" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-cpu-baseline "$@" > $O/${name}_n$N.json 2> $O/${name}_n$N.err
+  else
+    env "${envs[@]}" timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --no-extras --no-cpu-baseline "$@" > $O/${name}_n$N.json 2> $O/${name}_n$N.err
+  fi
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/s17/${name}_n$N.json') if l.startswith('{')][-1])
+    print('$name N=$N', {k:d[k] for k in ('value','ms_per_step','n_gpus','scaling')}, 'B/gpu', d['config']['per_gpu_batch'], 'e2e', d['e2e']['value'], d.get('clocks',{}).get('sm_mhz'))
+except Exception as e: print('$name parse fail', e); print(open('gpurun_out/s17/${name}_n$N.err').read()[-1500:])
+PY
+}
+run weak
+run unet320 --model unet --size 320
+run strong --scaling strong --global-batch 64
+if [ "$N" -eq 8 ]; then
+  run buckets1 AIDE_B200_BUCKETS=1
+  run ctas16 NCCL_MAX_CTAS=16
+  run globalsel --global-select
+fi

@@ -131,5 +131,23 @@ stepc, bc = torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(2, device
 report("adam_amsgrad (26.7 M parameters)", n * 4 * 9,
        lambda: call("aide_adam_amsgrad_dev", p.data_ptr(), g_.data_ptr(), m.data_ptr(), v.abs_().data_ptr(), vm.abs_().data_ptr(), n,
                     1e-4, 0.9, 0.999, 1e-8, stepc.data_ptr(), bc.data_ptr(), 1.0, None, st))
+# BatchNorm statistics fold + finalize over the conv kernel's partial rows (4 rows per 8x16-pixel tile), stacked forward
+# of 5 groups of `batch` slices
+for (hw, Cc) in ((256, 64), (128, 128), (64, 256)):
+    rows = 4 * args.batch * ((hw + 7) // 8) * ((hw + 15) // 16)
+    G = 5
+    parts0 = torch.randn(G, rows, 2, Cc, device=dev)
+    parts = parts0.clone()
+    gam, bet = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+    rm, rv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    tk = torch.zeros(lib.aide_bn_ticket_slots(Cc), dtype=torch.int32, device=dev)
+    ss = torch.empty(G, 2, Cc, device=dev)
+    mr = torch.empty(G, 2, Cc, device=dev)
+
+    def fold():
+        call("aide_bn_finalize_grouped", parts.data_ptr(), rows, G, Cc, float(args.batch * hw * hw), gam.data_ptr(),
+             bet.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5, 1, ss.data_ptr(), mr.data_ptr(), tk.data_ptr(), st)
+    report(f"bn_stat_fold_finalize [5 x {rows} rows x 2 x {Cc}]", parts.numel() * 4, fold)
+
 if args.json:
     json.dump(dict(peak_gbs=PEAK, rows=rows_out), open(args.json, "w"), indent=1)

@@ -34,7 +34,8 @@ def rel(a, b):
 bad = 0
 for fmt in args.fmts:
     for (N, H, W, cin, cout) in [(2, 8, 8, 128, 256), (1, 16, 16, 128, 64), (2, 20, 24, 256, 128), (1, 4, 40, 128, 128),
-                                 (3, 32, 32, 128, 64), (1, 16, 16, 1024, 512)]:
+                                 (3, 32, 32, 128, 64), (1, 16, 16, 1024, 512), (2, 16, 24, 32, 32), (1, 20, 12, 64, 32),
+                                 (2, 16, 40, 32, 64), (3, 24, 40, 96, 96)]:
         g = torch.Generator().manual_seed(cin + H)
         x = torch.randn(N, cin, H, W, generator=g).to(dev)
         dz = torch.randn(N, cout, H, W, generator=g).to(dev)
