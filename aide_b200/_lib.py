@@ -69,6 +69,12 @@ SIGNATURES = {
     "aide_conv1x1_fwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "aide_conv1x1_bwd_rows": (_i, [_i, _i, _i, _i]),
     "aide_conv1x1_bwd": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "aide_comm_alloc": (_i, [_sz, C.POINTER(_vp), C.c_char_p]),
+    "aide_comm_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "aide_comm_close": (_i, [_vp]),
+    "aide_comm_free": (_i, [_vp]),
+    "aide_comm_pad_words": (_i, [_i, _i]),
+    "aide_allreduce_p2p": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _i, _sz, _sz, _i, _vp]),
     "aide_loss_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _f, _vp, _vp, _vp]),
     "aide_loss_blocks": (_i, [_i, _i]),
     "aide_loss_image_finalize": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),

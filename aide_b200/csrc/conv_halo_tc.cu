@@ -840,7 +840,9 @@ bool make_plan(int fmt, int cin, int cout, long long m_tiles, HaloPlan* best, bo
           c.yx = npl == 2 ? c.b_plane : 0;
           c.b_stage = c.yx + c.b_plane / 2;
         }
-        const int avail = (occ == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 1024 - kBarBytes;   // 1 KB per CTA is reserved by the system
+        // 1 KB per CTA is reserved by the system; single-CTA plans stop at 226 KB so that one more CTA without shared
+        // memory of its own -- the peer-memory all-reduce (comm.cu) -- can share the SM with a persistent conv CTA
+        const int avail = (occ == 2 ? (kSmemMax - 2048) / 2 : kSmemMax - 1024) - 1024 - kBarBytes;
         c.a_stages = 2;
         int rest = avail - c.a_stages * c.a_stage;
         if (rest < 2 * c.b_stage) {                                // try a single halo stage before giving up

@@ -107,6 +107,7 @@ class _EngineNet(nn.Module):
         self._tensors: Optional[Dict[str, torch.Tensor]] = None
         self._scratch: Optional[torch.Tensor] = None
         self.last_grad_flat: Optional[torch.Tensor] = None
+        self._grad_flat_static: Optional[torch.Tensor] = None
         self._ticket_off, self._ticket_total = E.ticket_offsets(plan)
         self._tickets: Optional[torch.Tensor] = None          # zero-initialised once per device, self-resetting
 
@@ -218,7 +219,11 @@ class _EngineNet(nn.Module):
                                       "supported; the reference never does this")
         named = self._named()
         # zeros, not empty: the 4-element alignment gaps between tensors are part of the flat Adam / all-reduce buffer
-        flat = torch.zeros(self._glayout.total, dtype=torch.float32, device=dlogits.device)
+        if self._grad_flat_static is not None:       # a persistent (peer-mapped) buffer supplied by AideTrainer
+            flat = self._grad_flat_static
+            flat.zero_()
+        else:
+            flat = torch.zeros(self._glayout.total, dtype=torch.float32, device=dlogits.device)
         self.last_grad_flat = flat
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
                        dlogits.contiguous(), flat, tape.group, on_done)

@@ -62,7 +62,8 @@ class AideTrainer:
     def __init__(self, kind: str = "fuseunet", mode: Optional[str] = None, device="cuda:0", seed: int = 2,
                  lr: float = 1e-4, n_clean: int = 2, segcor_weight=(1.0, 10.0), temperature: float = 1.0,
                  flavour: str = "chaos", two_streams: bool = True, process_group=None,
-                 cuda_graph: Optional[bool] = None, global_select: bool = False, max_graphs: int = 4):
+                 cuda_graph: Optional[bool] = None, global_select: bool = False, max_graphs: int = 4,
+                 data_parallel: bool = True, comm: Optional[str] = None):
         self.device = torch.device(device)
         self.kind, self.flavour, self.temperature = kind, flavour, temperature
         self.n_clean, self.segcor_weight = n_clean, segcor_weight
@@ -84,7 +85,8 @@ class AideTrainer:
             net._prep_dgrad_always = True             # one weight preparation per step serves all 5 forwards + dgrad
         self.group = process_group
         self.world, self.rank = 1, 0
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if data_parallel and (process_group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
             self.rank = torch.distributed.get_rank(process_group)
         # Data-parallel selection semantics.  False (default): every rank selects n_clean "clean" images inside its
@@ -102,8 +104,23 @@ class AideTrainer:
         # diagnostic only (tools/gpu_session19.sh): skip the gradient all-reduce to time the slowest rank's compute alone --
         # the replicas diverge, never use it for training
         self._comm = os.environ.get("AIDE_B200_NO_COMM", "0") != "1"
+        self._sync_only = os.environ.get("AIDE_B200_COMM_SYNC_ONLY", "0") == "1"    # diagnostic, like NO_COMM
         self._buckets = {id(n): {t: r for t, r in E.gradient_buckets(n._plan, n._glayout, self.n_buckets)}
                          for n in (self.net1, self.net2)}
+        # Gradient all-reduce: "p2p" = aide_allreduce_p2p over NVLink peer memory (csrc/comm.cu; its CTAs share the SMs
+        # with the tensor-core kernels), "nccl" = torch.distributed.all_reduce.  p2p needs the flat gradient buffers in
+        # IPC-exported allocations: they are created here, once, and the backward pass writes into them.
+        self.comm_kind = (comm or os.environ.get("AIDE_B200_COMM", "p2p")) if self.world > 1 else "none"
+        self._peer = None
+        if self.comm_kind not in ("p2p", "nccl", "none"):
+            raise ValueError("comm must be 'p2p' or 'nccl'")
+        if self.world > 1 and self.comm_kind == "p2p" and self._comm:
+            from .comm import PeerBuffers
+            self._peer = PeerBuffers(self.group, self.device, [self.net1._glayout.total, self.net2._glayout.total],
+                                     blocks=int(os.environ.get("AIDE_B200_COMM_BLOCKS", "32")))
+            for i, net in enumerate((self.net1, self.net2)):
+                net._grad_flat_static = self._peer.tensors[i][:net._glayout.total]
+            self._comm_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
         self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
         # ... and the train forward as one more group of that stacked forward (train-mode views only, i.e. the chaos flavour)
@@ -265,20 +282,37 @@ class AideTrainer:
                                 other["q"], other["w"])
             works = []
             bucketed = self.world > 1 and self.n_buckets > 1 and self._comm
+            peer = self._peer
+            if peer is not None:
+                ci = 0 if net is self.net1 else 1
+                cs = self._comm_streams[ci]
+
+                def reduce_range(lo, hi):          # on the net's communication stream, behind everything enqueued so far
+                    cs.wait_stream(torch.cuda.current_stream())
+                    if self._sync_only:            # diagnostic: the cross-GPU barriers without the data
+                        hi = lo + 4
+                    peer.all_reduce(ci, lo, hi, cs.cuda_stream)
+            else:
+                def reduce_range(lo, hi):
+                    works.append(torch.distributed.all_reduce(net.last_grad_flat[lo:hi], group=self.group, async_op=True))
             if bucketed:
                 ranges = self._buckets[id(net)]
 
                 def on_done(name):                 # these float ranges of the flat gradient are final: reduce them now
                     for lo, hi in ranges.get(name, ()):
-                        works.append(torch.distributed.all_reduce(net.last_grad_flat[lo:hi], group=self.group,
-                                                                  async_op=True))
+                        reduce_range(lo, hi)
             net._engine_backward(me["tape"], d, on_done if bucketed else None)
             flat = net.last_grad_flat
             if self.world > 1 and self._comm:
                 if not bucketed:
-                    torch.distributed.all_reduce(flat, group=self.group)
+                    if peer is not None:
+                        reduce_range(0, flat.numel())
+                    else:
+                        torch.distributed.all_reduce(flat, group=self.group)
                 for w_ in works:
                     w_.wait()
+                if peer is not None:
+                    torch.cuda.current_stream().wait_stream(cs)
                 if self.global_select:             # the scalar was this rank's share of the global loss
                     torch.distributed.all_reduce(loss, group=self.group)
             # local selection: mean of the per-rank gradients; global selection: the coefficients already carry the

@@ -337,6 +337,22 @@ int aide_adam_amsgrad_dev(float* p, const float* g, float* m, float* v, float* v
                           float lr, float beta1, float beta2, float eps, int* step_counter, float* bc_scratch,
                           float grad_scale, const float* lr_dev, void* stream);
 
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (csrc/comm.cu) ------------------------------------------------
+ * Replaces the gradient reduction of nn.DataParallel (train_files/trainchaos_proposed_30cases1labeled.py:188-189; SURVEY.md
+ * 8e) for the one-process-per-GPU layout.  Buffers that take part are allocated with aide_comm_alloc (plain cudaMalloc +
+ * a 64-byte CUDA IPC handle), the handles travel through the host-side process group once, every rank maps its peers'
+ * allocations with aide_comm_open.  aide_allreduce_p2p sums the float range [lo, lo + count) of the `world` buffers in place
+ * (two-shot: reduce-scatter by peer loads in rank order, then all-gather; bit-identical on every rank).  pads: one flag pad
+ * of aide_comm_pad_words(world, channels) zeroed 32-bit words per rank.  All ranks must issue the calls of a channel in the
+ * same order with the same (lo, count, blocks); calls that can be in flight together use different channels. */
+int aide_comm_alloc(size_t bytes, void** ptr, unsigned char* handle /*[64]*/);
+int aide_comm_open(const unsigned char* handle /*[64]*/, void** ptr);
+int aide_comm_close(void* ptr);
+int aide_comm_free(void* ptr);
+int aide_comm_pad_words(int world, int channels);
+int aide_allreduce_p2p(float* const* bufs, unsigned int* const* pads, int rank, int world, int channel, int channels,
+                       size_t lo, size_t count, int blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -222,6 +222,8 @@ def test_gradient_buckets_cover_the_flat_buffer_in_completion_order():
         cov = sorted(r for _, rs in buckets for r in rs)
         assert cov[0][0] == 0 and cov[-1][1] == gl.total
         assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
+        # the peer-memory all-reduce kernel moves 128-bit vectors: every cut is a multiple of 4 floats (the tail is padded)
+        assert all(lo % 4 == 0 for lo, _ in cov) and all(hi % 4 == 0 for _, hi in cov[:-1])
         order = [u.name for u in reversed(plan.units)]                     # backward visiting order of the units
         done_at = {name: i for i, name in enumerate(order)}
         owner = {}                                                          # parameter -> unit / gate that finishes it

@@ -26,8 +26,68 @@ def shard(r):
     return (d(x1), d(x2)), d(t1), d(t2), [(d(a), d(b)) for a, b in augs]
 
 
-for graph in (False, True):
-    tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+# (0) the peer-memory all-reduce kernel alone: random data, ragged ranges, against the fixed-order sum it promises
+from aide_b200.comm import PeerBuffers  # noqa: E402
+
+pb = PeerBuffers(None, dev, [1 << 20, 4099 * 4], blocks=8)
+g = torch.Generator().manual_seed(5)
+data = [torch.randn(world, n, generator=g) for n in pb.sizes]
+for rep in range(3):
+    for i, (lo, hi) in ((0, (0, 1 << 20)), (1, (0, 4099 * 4)), (0, (1024, 70000)), (1, (8, 40))):
+        pb.tensors[i].copy_(data[i][rank] * (rep + 1))
+        torch.cuda.synchronize()
+        dist.barrier()
+        pb.all_reduce(i, lo, hi, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = data[i][rank].clone() * (rep + 1)
+        acc = data[i][0][lo:hi] * (rep + 1)
+        for r in range(1, world):
+            acc = acc + data[i][r][lo:hi] * (rep + 1)
+        want[lo:hi] = acc
+        assert torch.equal(pb.tensors[i].cpu(), want), (rep, i, lo, hi, (pb.tensors[i].cpu() - want).abs().max())
+        dist.barrier()
+print(f"[rank {rank}] aide_allreduce_p2p ok (bit-exact, rank-order sums)", flush=True)
+pb.close()
+# bandwidth of the collective alone at the size of one network's gradient (26.7 M floats), against NCCL
+n_grad = 26675076 + (-26675076) % 4
+for blocks in (8, 16, 32, 64):
+    pb = PeerBuffers(None, dev, [n_grad], blocks=blocks)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        pb.all_reduce(0, 0, n_grad, st)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        pb.all_reduce(0, 0, n_grad, st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    if rank == 0:
+        print(f"aide_allreduce_p2p {n_grad * 4 / 1e6:.0f} MB, {blocks} CTAs: {ms:.3f} ms  algbw {n_grad * 4 / ms / 1e6:.0f} GB/s  "
+              f"busbw {n_grad * 4 / ms / 1e6 * 2 * (world - 1) / world:.0f} GB/s", flush=True)
+    pb.close()
+t = torch.zeros(n_grad, device=dev)
+for _ in range(3):
+    dist.all_reduce(t)
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    dist.all_reduce(t)
+e1.record(); torch.cuda.synchronize()
+if rank == 0:
+    ms = e0.elapsed_time(e1) / 10
+    print(f"nccl all_reduce {n_grad * 4 / 1e6:.0f} MB: {ms:.3f} ms  algbw {n_grad * 4 / ms / 1e6:.0f} GB/s", flush=True)
+del t
+if os.environ.get("DDP_CHECK_KERNEL_ONLY", "0") == "1":       # any world size: the collective alone
+    dist.barrier()
+    if rank == 0:
+        print("DDP_CHECK_KERNEL_OK", flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+for graph, comm in ((False, "p2p"), (True, "p2p"), (False, "nccl"), (True, "nccl")):
+    tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph, comm=comm)
     tr.broadcast_parameters(0)
     p0 = tr.opt1.flat.clone()
     x, t1, t2, augs = shard(rank)
@@ -43,14 +103,12 @@ for graph in (False, True):
     if rank == 0 and not graph:
         grads = []
         for r in range(world):
-            ref = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=False, process_group=None)
-            ref.world = 1
+            ref = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=False, data_parallel=False)
             xs, a, b, au = shard(r)
             ref._step_eager(xs, a, b, au, 0.25)
             grads.append(ref.net1.last_grad_flat.clone())
         gmean = (grads[0] + grads[1]) / 2
-        upd = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=False)
-        upd.world = 1
+        upd = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=False, data_parallel=False)
         upd.opt1.step(gmean)
         diff = (upd.opt1.flat - mine).abs().max().item()
         assert diff <= 2.1e-4, diff        # identical up to the all-reduce summation order on sign-like first updates
@@ -58,7 +116,7 @@ for graph in (False, True):
         assert frac_same > 0.99, frac_same
         assert not torch.equal(mine, p0)
     dist.barrier()
-    print(f"[rank {rank}] graph={graph} ok", flush=True)
+    print(f"[rank {rank}] graph={graph} comm={comm} ok", flush=True)
 # (3) nn.DataParallel semantics (global_select=True): the per-image losses of all ranks are gathered, the small-loss
 # sort and the clean / rest split are global, gradients add up.  Reference emulation with the oracle: every shard runs
 # its own forward (replica-local BatchNorm statistics, as DataParallel does), outputs are concatenated and the loss of
