@@ -23,7 +23,7 @@ except Exception as e: print('$name parse fail', e); print(open('gpurun_out/s19/
 PY
 }
 run weak
-if [ "$N" -gt 1 ]; then run nocomm AIDE_B200_NO_COMM=1; fi
+if [ "$N" -eq 2 ]; then run nocomm AIDE_B200_NO_COMM=1; fi
 if [ "$N" -lt 8 ]; then
   run strong --scaling strong --global-batch 64
   run unet320 --model unet --size 320
