@@ -149,5 +149,21 @@ for (hw, Cc) in ((256, 64), (128, 128), (64, 256)):
              bet.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5, 1, ss.data_ptr(), mr.data_ptr(), tk.data_ptr(), st)
     report(f"bn_stat_fold_finalize [5 x {rows} rows x 2 x {Cc}]", parts.numel() * 4, fold)
 
+# first layer (Cin = 3, fp32 CUDA cores): 27 FMAs per output element, 12 B in + 4*Cout B out per pixel
+import aide_b200 as A  # noqa: E402
+for N in (5 * args.batch, args.batch):
+    hw, cout = 256, 32
+    x = ops.Act(N, hw, hw, 3, 0, dev)
+    x.planes.normal_()
+    w = torch.randn(cout, 3, 3, 3, device=dev) * 0.2
+    bias = torch.zeros(cout, device=dev)
+    w0, w1, keep = ops.weight_prep(w, 0)
+    z = torch.empty((N, hw, hw, cout), dtype=torch.float32, device=dev)
+    rows = A.lib.aide_conv3x3_stat_rows(0, 3, cout, N, hw, hw)
+    part = torch.empty((rows, 2, cout), dtype=torch.float32, device=dev)
+    report(f"conv3x3 first layer 3->32 [{N}x256x256]", N * hw * hw * (12 + 4 * cout),
+           lambda: call("aide_conv3x3_fwd", 0, x.p0, x.p1, x.C, 0, 3, w0, w1, bias.data_ptr(), z.data_ptr(), cout, 0, cout,
+                        N, hw, hw, part.data_ptr(), st))
+
 if args.json:
     json.dump(dict(peak_gbs=PEAK, rows=rows_out), open(args.json, "w"), indent=1)
