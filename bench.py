@@ -241,8 +241,9 @@ def conv_roofline(fmt, B, S, device, peaks):
     passes = {1: 3, 2: 1, 3: 3}.get(fmt, 0)
     ceiling = {1: peak / 6.0, 2: peak, 3: peak / 3.0}.get(fmt, peak)
     sustained = peaks.get("bf16_tflops_sustained")
-    return dict(bound="tensor", kernel=f"conv3x3_halo_tc_kernel<{FMT_NAMES[fmt]}> (persistent tcgen05 implicit GEMM, TMA halo "
-                                       "tiles; dgrad is the same kernel; maps below 8x8 run conv3x3_fwd_tc_kernel)",
+    return dict(bound="tensor", kernel=f"conv3x3_halo2_tc_kernel / conv3x3_halo_tc_kernel<{FMT_NAMES[fmt]}> (persistent tcgen05 "
+                                       "implicit GEMM on TMA halo tiles: CTA pairs (cta_group::2, M = 256) or single CTAs per the "
+                                       "measured plan table; dgrad is the same kernel; maps below 8x8 run conv3x3_fwd_tc_kernel)",
                 achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4),
                 frac_sustained=round(achieved / sustained, 4) if sustained else None, traffic=traffic,
                 traffic_note=traffic_note, launches=int(sum(r["launches_per_fwd"] for r in rows)),
@@ -293,7 +294,7 @@ def _time_launch(fn, flush, device, reps=5):
 
 
 def wgrad_roofline(fmt, B, S, device, peaks):
-    """conv3x3 weight-gradient kernels (conv_wgrad_halo.cu; Cin in {32, 64}: conv_tc.cu), every fuseunet layer shape
+    """conv3x3 weight-gradient kernel (conv_wgrad_halo.cu), every fuseunet layer shape
     at the train batch, incl. the split-K reduce.  FLOPs = 2*B*H*W*Cout*Cin*9 per launch."""
     import aide_b200 as A
     from aide_b200 import engine as E, ops
@@ -324,7 +325,7 @@ def wgrad_roofline(fmt, B, S, device, peaks):
     achieved = tot_flop / tot_ms / 1e9
     peak = peaks.get("bf16_tflops") or 1590.0
     ceiling = {1: peak / 6.0, 2: peak, 3: peak / 3.0}.get(fmt, peak)
-    return dict(bound="tensor", kernel="wgrad_halo_kernel (Cin >= 128) / wgrad_tc_kernel (Cin 32, 64) + split-K reduce",
+    return dict(bound="tensor", kernel="wgrad_halo_kernel (three dx taps per CTA on one halo box; Cin = 64: hi/lo planes stacked along M; 32-channel layers on zero-padded 64-channel boxes) + split-K reduce",
                 achieved=round(achieved, 1), peak=peak, unit="TFLOP/s", frac=round(achieved / peak, 4),
                 frac_of_format_ceiling=round(achieved / ceiling, 4), batch_per_launch=B, operand_format=FMT_NAMES[fmt],
                 layers=rows)
