@@ -213,7 +213,7 @@ class _EngineNet(nn.Module):
             tape.group = groups - 1          # a stacked forward with a tape: the backward runs through the LAST group
         return logits, tape
 
-    def _engine_backward(self, tape, dlogits, on_done=None):
+    def _engine_backward(self, tape, dlogits, on_done=None, sync_names=None):
         if not tape.training:
             raise NotImplementedError("backward through an eval-mode (running-statistics) BatchNorm forward is not "
                                       "supported; the reference never does this")
@@ -226,7 +226,7 @@ class _EngineNet(nn.Module):
             flat = torch.zeros(self._glayout.total, dtype=torch.float32, device=dlogits.device)
         self.last_grad_flat = flat
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
-                       dlogits.contiguous(), flat, tape.group, on_done)
+                       dlogits.contiguous(), flat, tape.group, on_done, sync_names)
         tw = {u.conv + ".weight" for u in self._plan.units if u.transposed}
         return [E.transposed_weight_grad(self._glayout.view(flat, n)) if n in tw else self._glayout.view(flat, n)
                 for n, _ in self.named_parameters()]

@@ -301,7 +301,8 @@ class AideTrainer:
                 def on_done(name):                 # these float ranges of the flat gradient are final: reduce them now
                     for lo, hi in ranges.get(name, ()):
                         reduce_range(lo, hi)
-            net._engine_backward(me["tape"], d, on_done if bucketed else None)
+            net._engine_backward(me["tape"], d, on_done if bucketed else None,
+                                 set(self._buckets[id(net)]) if bucketed else None)
             flat = net.last_grad_flat
             if self.world > 1 and self._comm:
                 if not bucketed:
