@@ -696,7 +696,9 @@ def main():
         "data": "synthetic",
         "config": workload_config(B, S, world, args.model),
         "engine": {"mode": args.mode, "cuda_graph": bool(tr.cuda_graph), "stacked_aug_forward": bool(tr.group_augs), "stacked_train_forward": bool(tr.stack_train),
-                   "resident_batches": n_pool, "global_select": bool(tr.global_select)},
+                   "resident_batches": n_pool, "global_select": bool(tr.global_select),
+                   "gradient_all_reduce": {"p2p": "aide_allreduce_p2p (NVLink peer memory, csrc/comm.cu)", "nccl": "torch.distributed.all_reduce (NCCL)",
+                                           "none": None}[tr.comm_kind] if tr._comm else "disabled (AIDE_B200_NO_COMM diagnostic)"},
         "gpu_launches": int(launches), "gpu_launches_per_step": round(launches / K, 1),
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 2), "rank_ms_per_step": rank_ms,
         "clocks": clocks, "e2e": e2e,

@@ -293,7 +293,7 @@ def test_teacher_forced_training_steps(oracle):
     dev = torch.device("cuda:0")
     steps = int(os.environ.get("AIDE_TF_STEPS", "10"))
     size = int(os.environ.get("AIDE_TF_SIZE", "256"))
-    B = 4
+    B = int(os.environ.get("AIDE_TF_BATCH", "4"))
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(2)
     p1 = oracle.clone_params(oracle.init_fuseunet(2), requires_grad=True)
