@@ -9,6 +9,7 @@ their storage to the CUDA engine (aide_b200.engine) through one autograd.Functio
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -108,6 +109,9 @@ class _EngineNet(nn.Module):
         self._scratch: Optional[torch.Tensor] = None
         self.last_grad_flat: Optional[torch.Tensor] = None
         self._grad_flat_static: Optional[torch.Tensor] = None
+        self._auto_graph = os.environ.get("AIDE_B200_AUTOGRAPH", "1") != "0" and os.environ.get("AIDE_B200_GRAPH", "1") != "0"
+        self._auto_graph_max = int(os.environ.get("AIDE_B200_AUTOGRAPH_MAX", "4"))
+        self._auto_graphs: Dict[tuple, object] = {}       # key -> False (seen once, eager) | _GraphedForward
         self._ticket_off, self._ticket_total = E.ticket_offsets(plan)
         self._tickets: Optional[torch.Tensor] = None          # zero-initialised once per device, self-resetting
 
@@ -115,6 +119,7 @@ class _EngineNet(nn.Module):
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._tensors, self._weights, self._scratch, self._tickets = None, {}, None, None
+        self._auto_graphs = {}
         return out
 
     def _named(self) -> Dict[str, torch.Tensor]:
@@ -236,8 +241,63 @@ class _EngineNet(nn.Module):
         params = self._param_order()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _NetFunction.apply(self, len(inputs), *inputs, *params)
+        if self._auto_graph and not torch.cuda.is_current_stream_capturing():
+            return self._nograd_forward_graphed(inputs)
         logits, _ = self._engine_forward(inputs, keep_tape=False)
         return logits
+
+    def _nograd_forward_graphed(self, inputs):
+        """No-grad forwards of an unmodified reference script -- the 8 pseudo-label forwards of every training step
+        (trainchaos_proposed_30cases1labeled.py:263-272, train-mode BatchNorm) and the thousands of single-slice
+        evaluation forwards per epoch (:373-496) -- are ~100-170 launches of ~30 us host time each when issued eagerly.
+        The second call with the same input shape / BatchNorm mode captures the forward INCLUDING its weight preparation
+        into a CUDA graph; later calls copy the inputs into the graph's static buffers, replay, and return a copy of the
+        logits.  In-place parameter updates (torch.optim) need no re-capture: the replay re-derives the operand planes
+        from the parameters' current values.  AIDE_B200_AUTOGRAPH=0 disables it."""
+        named = self._named()
+        w0 = named[self._plan.units[0].conv + ".weight"]
+        key = (tuple(inputs[0].shape), len(inputs), self.training, id(named), w0.data_ptr(), inputs[0].device.index)
+        ent = self._auto_graphs.get(key)
+        if ent is None:                                   # first sight: eager (this is also the capture's warm-up)
+            self._auto_graphs[key] = False
+            while len(self._auto_graphs) > self._auto_graph_max:
+                self._auto_graphs.pop(next(iter(self._auto_graphs)))
+            logits, _ = self._engine_forward(inputs, keep_tape=False)
+            return logits
+        if ent is False:
+            ent = self._auto_graphs[key] = _GraphedForward(self, inputs)
+        else:
+            self._auto_graphs[key] = self._auto_graphs.pop(key)     # most recently used last
+        return ent(*inputs)
+
+
+class _GraphedForward:
+    """Captured no-grad forward of one network for one input shape and BatchNorm mode, weight preparation included
+    (see _EngineNet._nograd_forward_graphed).  Must be constructed right after an eager forward of the same shape."""
+
+    def __init__(self, net: "_EngineNet", inputs):
+        self.static_in = [torch.empty_like(x) for x in inputs]
+        N, _, H, W = inputs[0].shape
+        fmt = E.mode_format(net.engine_mode, False)
+        total = net._layouts[(N, H, W, fmt, 1)].total
+        self._arena = torch.empty(total, dtype=torch.uint8, device=inputs[0].device)      # owned by the graph
+        saved = net._weights
+        net._weights = {}                                 # force the weight preparation INTO the graph ...
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = E.lib.aide_launch_count()
+        try:
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.out, _ = net._engine_forward(self.static_in, keep_tape=False, arena=self._arena)
+            self._planes = net._weights                   # ... whose operand planes belong to the graph's memory pool
+        finally:
+            net._weights = saved                          # eager paths never alias graph-owned planes
+        self.n_kernels = E.lib.aide_launch_count() - n0
+
+    def __call__(self, *inputs):
+        for d, s_ in zip(self.static_in, inputs):
+            d.copy_(s_, non_blocking=True)
+        self.graph.replay()
+        return self.out.clone()
 
 
 class _GraphedEval:

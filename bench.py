@@ -392,6 +392,39 @@ def eval_single_slice(args, S, device, n_slices=200):
                 api="net.graphed_eval(modal1, modal2) + predict_mask, one 256x256 slice per call (pinned host in / out)")
 
 
+def eval_module_single_slice(args, S, device, n_slices=200):
+    """The same loop written like the unmodified script (trainchaos_proposed_30cases1labeled.py:403-411): net.eval(),
+    `with torch.no_grad(): output = net(inphase, outphase)`, torch.argmax(softmax(output), 1), .cpu() -- no engine-specific
+    call.  The module captures its no-grad forward into a CUDA graph on the second call (nets._nograd_forward_graphed)."""
+    import aide_b200 as A
+    import torch.nn.functional as F
+    torch.manual_seed(2)
+    net = A.fuseunet(num_classes=2, mode=args.mode).to(device).eval()
+    g = torch.Generator().manual_seed(99)
+    host = [tuple(torch.randn(1, 3, S, S, generator=g) for _ in range(2)) for _ in range(4)]
+    keep = {}
+
+    def one(i):
+        a, b = (t.to(device) for t in host[i % 4])
+        with torch.no_grad():
+            out = net(a, b)
+        keep["mask"] = torch.argmax(F.softmax(out, dim=1), dim=1).cpu()
+
+    for i in range(5):
+        one(i)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_slices):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / n_slices
+    return dict(value=round(1e3 / ms, 1), unit="slices/s", ms_per_slice=round(ms, 4), slices=n_slices,
+                api="unmodified-script pattern: net.eval(); with torch.no_grad(): net(modal1, modal2); argmax(softmax).cpu() "
+                    "(pageable host tensors, one 256x256 slice per call)")
+
+
 def module_e2e(args, B, S, device, K):
     """The call pattern of an UNMODIFIED training script (train_files/trainchaos_proposed_30cases1labeled.py:263-325)
     on the drop-in modules: 8 detached augmented forwards, F.softmax / sharpen in torch, 2 train forwards through
@@ -753,6 +786,10 @@ def main():
                 out["eval_single_slice"] = eval_single_slice(args, S, device)
             except Exception as e:  # noqa: BLE001
                 out["eval_single_slice"] = dict(value=None, error=f"{type(e).__name__}: {e}")
+            try:
+                out["eval_module_single_slice"] = eval_module_single_slice(args, S, device)
+            except Exception as e:  # noqa: BLE001
+                out["eval_module_single_slice"] = dict(value=None, error=f"{type(e).__name__}: {e}")
             try:
                 out["e2e_module"] = module_e2e(args, B, S, device, max(2, min(K, 5)))
             except Exception as e:  # noqa: BLE001

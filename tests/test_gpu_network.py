@@ -548,3 +548,48 @@ def test_fused_eval_forward_is_bit_identical_to_unfused(oracle, kind, monkeypatc
     assert torch.equal(y, y_ref)
     print(f"{kind}: eval forward launches {n_unfused} -> {n_fused}")
     assert n_fused < 0.7 * n_unfused
+
+
+def test_nograd_module_forward_replays_a_graph_and_follows_weight_updates():
+    """The no-grad forwards of an unmodified reference script (8 pseudo-label forwards per step in train mode,
+    trainchaos_proposed_30cases1labeled.py:263-272; single-slice evaluation, :373-496) are captured into a CUDA graph on
+    their second call.  The replay must be indistinguishable from the eager forward: same logits bit for bit, same
+    running statistics / num_batches_tracked, it must follow in-place parameter updates without re-capture, and every
+    returned tensor must stay valid when the next forward runs."""
+    import aide_b200 as A
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    a = A.fuseunet(num_classes=2, mode="parity").to(dev).train()
+    b = A.fuseunet(num_classes=2, mode="parity").to(dev).train()
+    b.load_state_dict(a.state_dict())
+    b._auto_graph = False
+    g = torch.Generator().manual_seed(3)
+    xs = [(torch.randn(2, 3, 64, 64, generator=g).to(dev), torch.randn(2, 3, 64, 64, generator=g).to(dev)) for _ in range(6)]
+    outs = []
+    with torch.no_grad():
+        for i, x in enumerate(xs):
+            if i == 4:                                     # an optimiser-style in-place update between forwards
+                for pa, pb in zip(a.parameters(), b.parameters()):
+                    d = 0.01 * torch.randn(pa.shape, generator=g).to(dev)
+                    pa.add_(d)
+                    pb.add_(d)
+            ya, yb = a(*x), b(*x)
+            assert torch.equal(ya, yb), i
+            outs.append((ya, yb.clone()))
+        graphs = [v for v in a._auto_graphs.values() if v]
+        assert len(graphs) == 1 and graphs[0].n_kernels > 50           # calls 2.. were replays of one captured forward
+        for ya, yb in outs:
+            assert torch.equal(ya, yb)                                  # earlier results were not overwritten
+        for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert torch.equal(va, vb), ka                              # running statistics, num_batches_tracked
+        a.eval(), b.eval()
+        for i, x in enumerate(xs[:3]):
+            assert torch.equal(a(x[0][:1], x[1][:1]), b(x[0][:1], x[1][:1])), i
+        assert len([v for v in a._auto_graphs.values() if v]) == 2
+    # a forward WITH grad in between uses the eager path and its own weight planes
+    x = xs[0]
+    la = a.train()(*x).sum()
+    lb = b.train()(*x).sum()
+    la.backward(), lb.backward()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa.grad, pb.grad)
