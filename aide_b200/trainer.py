@@ -101,7 +101,7 @@ class AideTrainer:
         # gradient all-reduce in buckets launched while the backward pass is still running (decoder first); 0 / 1 = one
         # all-reduce per net after its backward
         self.n_buckets = int(os.environ.get("AIDE_B200_BUCKETS", "4"))
-        # diagnostic only (tools/gpu_session19.sh): skip the gradient all-reduce to time the slowest rank's compute alone --
+        # diagnostic only (tools/sessions/s19.sh): skip the gradient all-reduce to time the slowest rank's compute alone --
         # the replicas diverge, never use it for training
         self._comm = os.environ.get("AIDE_B200_NO_COMM", "0") != "1"
         self._sync_only = os.environ.get("AIDE_B200_COMM_SYNC_ONLY", "0") == "1"    # diagnostic, like NO_COMM
