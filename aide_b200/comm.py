@@ -37,31 +37,46 @@ class PeerBuffers:
         self.channels = len(sizes)
         self.sizes = [int(n + (-n) % 4) for n in sizes]
         pad_words = lib.aide_comm_pad_words(self.world, self.channels)
-        mine, handles = [], []
+        # Every rank walks through the same collectives whether or not its own CUDA calls succeed; the verdict is agreed
+        # on at the end, so a rank whose IPC mapping fails cannot leave the others waiting in a different collective.
+        mine, handles, err = [], [], None
+        self._opened, self.ptrs = [], []
         with torch.cuda.device(device):
-            for n in self.sizes + [pad_words]:
-                ptr, h = C.c_void_p(), C.create_string_buffer(64)
-                call("aide_comm_alloc", n * 4, C.byref(ptr), h)
-                mine.append(ptr.value)
-                handles.append(h.raw)
-            torch.cuda.synchronize(device)
+            try:
+                for n in self.sizes + [pad_words]:
+                    ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                    call("aide_comm_alloc", n * 4, C.byref(ptr), h)
+                    mine.append(ptr.value)
+                    handles.append(h.raw)
+                torch.cuda.synchronize(device)
+            except Exception as e:  # noqa: BLE001
+                err, handles = e, None
             everyone: List = [None] * self.world
             dist.all_gather_object(everyone, handles, group=group)
-            # ptrs[k][r]: allocation k (buffers, then the pad) of rank r, mapped into this process
-            self._opened = []
-            self.ptrs = []
-            for k in range(len(mine)):
-                row = []
-                for r in range(self.world):
-                    if r == self.rank:
-                        row.append(mine[k])
-                    else:
-                        p = C.c_void_p()
-                        call("aide_comm_open", everyone[r][k], C.byref(p))
-                        self._opened.append(p.value)
-                        row.append(p.value)
-                self.ptrs.append(row)
+            if err is None and any(h is None for h in everyone):
+                err = RuntimeError("a peer could not allocate its buffers")
+            if err is None:
+                try:
+                    # ptrs[k][r]: allocation k (buffers, then the pad) of rank r, mapped into this process
+                    for k in range(len(mine)):
+                        row = []
+                        for r in range(self.world):
+                            if r == self.rank:
+                                row.append(mine[k])
+                            else:
+                                p = C.c_void_p()
+                                call("aide_comm_open", everyone[r][k], C.byref(p))
+                                self._opened.append(p.value)
+                                row.append(p.value)
+                        self.ptrs.append(row)
+                except Exception as e:  # noqa: BLE001 -- e.g. CUDA IPC not permitted between these processes
+                    err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # also: everybody has mapped everything
         self._mine = mine
+        if int(ok.item()) == 0:
+            self._release()
+            raise RuntimeError(f"peer-memory buffers unavailable on rank {self.rank} or one of its peers: {err!r}")
         self._raw = [_RawCuda(mine[i], self.sizes[i]) for i in range(self.channels)]
         self.tensors = [torch.as_tensor(r, device=device) for r in self._raw]
         for t, p in zip(self.tensors, mine):
@@ -69,7 +84,6 @@ class PeerBuffers:
                 raise RuntimeError("torch copied the peer buffer instead of viewing it")
         self._pad_arr = (C.c_void_p * self.world)(*self.ptrs[-1])
         self._buf_arr = [(C.c_void_p * self.world)(*self.ptrs[i]) for i in range(self.channels)]
-        dist.barrier(group=group)                    # every rank has mapped everything before the first kernel runs
 
     def all_reduce(self, i: int, lo: int, hi: int, stream: int) -> None:
         """Sum floats [lo, hi) of buffer i over the ranks, in place, on CUDA stream `stream` (raw handle)."""
@@ -78,9 +92,7 @@ class PeerBuffers:
         call("aide_allreduce_p2p", self._buf_arr[i], self._pad_arr, self.rank, self.world, i, self.channels, lo4, hi4 - lo4,
              self.blocks, stream)
 
-    def close(self) -> None:
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+    def _release(self) -> None:
         for p in self._opened:
             call("aide_comm_close", p)
         self._opened = []
@@ -88,3 +100,8 @@ class PeerBuffers:
         for p in self._mine:
             call("aide_comm_free", p)
         self._mine = []
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self._release()

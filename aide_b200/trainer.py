@@ -116,11 +116,18 @@ class AideTrainer:
             raise ValueError("comm must be 'p2p' or 'nccl'")
         if self.world > 1 and self.comm_kind == "p2p" and self._comm:
             from .comm import PeerBuffers
-            self._peer = PeerBuffers(self.group, self.device, [self.net1._glayout.total, self.net2._glayout.total],
-                                     blocks=int(os.environ.get("AIDE_B200_COMM_BLOCKS", "32")))
-            for i, net in enumerate((self.net1, self.net2)):
-                net._grad_flat_static = self._peer.tensors[i][:net._glayout.total]
-            self._comm_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            try:            # PeerBuffers raises on EVERY rank if any rank could not allocate / map (it agrees on the verdict)
+                self._peer = PeerBuffers(self.group, self.device, [self.net1._glayout.total, self.net2._glayout.total],
+                                         blocks=int(os.environ.get("AIDE_B200_COMM_BLOCKS", "32")))
+            except RuntimeError as e:
+                # NCCL is a GPU collective too: a choice between two device paths, announced loudly, never a CPU path
+                import warnings
+                warnings.warn(f"peer-memory all-reduce unavailable ({e}); using NCCL")
+                self._peer, self.comm_kind = None, "nccl"
+            else:
+                for i, net in enumerate((self.net1, self.net2)):
+                    net._grad_flat_static = self._peer.tensors[i][:net._glayout.total]
+                self._comm_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
         # run the 4 augmented forwards of a net as ONE stacked-batch forward with per-view BatchNorm statistics
         self.group_augs = os.environ.get("AIDE_B200_GROUP_AUGS", "1") != "0"
         # ... and the train forward as one more group of that stacked forward (train-mode views only, i.e. the chaos flavour)
