@@ -544,7 +544,9 @@ class GradLayout:
             cur += (n + 3) // 4 * 4
 
         for u in plan.units:
-            add(u.conv + ".weight", (u.cout, u.cin, 3, 3))
+            # a ConvTranspose2d(k=2, s=2) parameter keeps ITS shape [Cin,Cout,2,2]: the slot is the parameter's gradient
+            # (the 3x3 stand-in's gradient lives in a scratch buffer of the backward pass and is re-indexed into it)
+            add(u.conv + ".weight", (u.cin, u.cout, 2, 2) if u.transposed else (u.cout, u.cin, 3, 3))
             add(u.conv + ".bias", (u.cout,))
             add(u.bn + ".bias", (u.cout,))       # dbeta  } adjacent: written as one [2][C] vector
             add(u.bn + ".weight", (u.cout,))     # dgamma }
@@ -618,6 +620,8 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
         ufmt = FMT_F32 if u.first else fmt
         if not u.first:
             reserve("dx:" + u.name, N * h * w * u.cin * 4)
+        if u.transposed:
+            reserve("dk:" + u.name, u.cout * u.cin * 9 * 4)
         max_g = max(max_g, N * h * w * u.cout * 4)
         max_dz = max(max_dz, _align(N * h * w * u.cout * _esize(ufmt)) * _planes(ufmt))
         max_part = max(max_part, lib.aide_bn_bwd_rows(N, h, w, u.cout) * 2 * u.cout * 4)
@@ -741,14 +745,21 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
                  part2, gmax, dz_scale, bb + off["gscale"] + 64, st)
             x0, x1, xct, xco = aview(u.src[0], u.src[1])
             wst = st
-            if side is not None:
+            dw_dst = bb + off["dk:" + u.name] if u.transposed else gptr(u.conv + ".weight")
+            if side is not None and u.transposed and last_wgrad is not None:
+                main.wait_event(last_wgrad)          # this wgrad runs on the main stream: the shared workspace must be free
+            if side is not None and not u.transposed:
                 ready = torch.cuda.Event()
                 ready.record(main)
                 side.wait_event(ready)
                 wst = side.cuda_stream
             call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
-                 bb + off["ws"], max_ws, gptr(u.conv + ".weight"), wst)
-            if side is not None:
+                 bb + off["ws"], max_ws, dw_dst, wst)
+            if u.transposed:                        # dW[ci,co,a,b] = dK[co,ci,1-a,1-b]: tensor re-indexing into the slot
+                o0 = off["dk:" + u.name]
+                dk = barena[o0:o0 + u.cout * u.cin * 36].view(torch.float32).view(u.cout, u.cin, 3, 3)
+                glayout.view(grad_flat, u.conv + ".weight").copy_(transposed_weight_grad(dk))
+            elif side is not None:
                 busy[k] = last_wgrad = torch.cuda.Event()
                 last_wgrad.record(side)
             if not u.first:

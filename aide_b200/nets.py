@@ -232,9 +232,7 @@ class _EngineNet(nn.Module):
         self.last_grad_flat = flat
         E.run_backward(self._plan, self._bplan, self._glayout, tape.layout, named, tape.weights, tape.arena,
                        dlogits.contiguous(), flat, tape.group, on_done, sync_names)
-        tw = {u.conv + ".weight" for u in self._plan.units if u.transposed}
-        return [E.transposed_weight_grad(self._glayout.view(flat, n)) if n in tw else self._glayout.view(flat, n)
-                for n, _ in self.named_parameters()]
+        return [self._glayout.view(flat, n) for n, _ in self.named_parameters()]
 
     def _run(self, *inputs):
         self._check_inputs(inputs)

@@ -63,7 +63,7 @@ class AideTrainer:
                  lr: float = 1e-4, n_clean: int = 2, segcor_weight=(1.0, 10.0), temperature: float = 1.0,
                  flavour: str = "chaos", two_streams: bool = True, process_group=None,
                  cuda_graph: Optional[bool] = None, global_select: bool = False, max_graphs: int = 4,
-                 data_parallel: bool = True, comm: Optional[str] = None):
+                 data_parallel: bool = True, comm: Optional[str] = None, net_kwargs: Optional[Dict] = None):
         self.device = torch.device(device)
         self.kind, self.flavour, self.temperature = kind, flavour, temperature
         self.n_clean, self.segcor_weight = n_clean, segcor_weight
@@ -71,11 +71,9 @@ class AideTrainer:
         if kind not in NET_KINDS:
             raise ValueError(f"kind must be one of {sorted(NET_KINDS)}")          # cf. 'Model not implemented', :78
         ctor = NET_KINDS[kind]
-        self.net1 = ctor(num_classes=2, mode=mode).to(self.device).train()
-        self.net2 = ctor(num_classes=2, mode=mode).to(self.device).train()
-        if any(u.transposed for u in self.net1._plan.units):
-            raise NotImplementedError("AideTrainer keeps parameters in the flat gradient layout; ConvTranspose2d decoders "
-                                      "(learned_bilinear=True) run through the nn.Module / torch.optim path")
+        kw = dict(net_kwargs or {})                  # e.g. learned_bilinear=True (netblocks.py:11-14), reduction / dilation
+        self.net1 = ctor(num_classes=2, mode=mode, **kw).to(self.device).train()
+        self.net2 = ctor(num_classes=2, mode=mode, **kw).to(self.device).train()
         self.opt1 = flat_adam_for(self.net1, lr)
         self.opt2 = flat_adam_for(self.net2, lr)
         for net, opt in ((self.net1, self.opt1), (self.net2, self.opt2)):

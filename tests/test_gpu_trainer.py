@@ -167,3 +167,40 @@ def test_trainer_step_attention_variants(oracle, kind, flavour):
     key = "sa3.conv2.weight" if unet else "modal2_sa3.conv2.weight"
     diff = (sd[key].cpu() - p1[key].detach()).abs()
     assert diff.max().item() <= 2.1e-4 and diff.median().item() < 2e-5, (diff.max().item(), diff.median().item())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_step_learned_bilinear_decoder(oracle, graph):
+    """learned_bilinear=True (ConvTranspose2d(k=2,s=2) up path, netblocks.py:11-14) inside the fused step: the transposed
+    weights keep their [Cin,Cout,2,2] slots in the flat parameter / gradient buffers (the 3x3 stand-in's gradient is
+    re-indexed into them), so flat Adam, the bucket plan and the all-reduce need no special case.  One step against the
+    oracle: losses, index sets, the transposed-weight gradient, the weights after Adam."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    tr = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph, net_kwargs=dict(learned_bilinear=True))
+    torch.manual_seed(2)
+    p1 = oracle.clone_params(oracle.init_fuseunet(2, learned_bilinear=True), requires_grad=True)
+    p2 = oracle.clone_params(oracle.init_fuseunet(2, learned_bilinear=True), requires_grad=True)
+    assert list(tr.net1.state_dict().keys()) == list(p1.keys())
+    d = lambda t: t.to(dev)
+    x, t1, t2, augs = batch(oracle, B, S, 640)
+    r = oracle.aide_step(oracle.fuseunet_forward, p1, p2, x, augs, t1, t2, 0.25)
+    m = tr.step(tuple(d(t) for t in x), d(t1), d(t2), [tuple(d(t) for t in a) for a in augs], 0.25)
+    assert abs(m["loss1"].item() - r["loss1"].item()) < 2e-5 * max(1, abs(r["loss1"].item()))
+    assert abs(m["loss2"].item() - r["loss2"].item()) < 2e-5 * max(1, abs(r["loss2"].item()))
+    assert torch.equal(m["indx1"].cpu(), r["indx1"]) and torch.equal(m["indx2"].cpu(), r["indx2"])
+    name = "up_block1.bilinear_up.0.weight"
+    g_ref = r["grads1"][name]
+    g = tr.net1._glayout.view(tr.net1.last_grad_flat, name).cpu()
+    assert g.shape == g_ref.shape == (1024, 512, 2, 2)
+    # the deepest decoder level of a 64x64 input is a 4x4 map under train-mode BatchNorm: its gradient is the most
+    # rounding-sensitive of the net (cf. oracle_sensitivity_band); a wrong re-indexing would not correlate at all
+    assert ((g - g_ref).abs().max() / g_ref.abs().max()).item() < 1e-2
+    cos = torch.nn.functional.cosine_similarity(g.double().flatten(), g_ref.double().flatten(), dim=0).item()
+    assert 1.0 - cos < 1e-4, cos
+    st1 = {}
+    oracle.adam_amsgrad_step(p1, r["grads1"], st1, 1)
+    w = tr.net1.state_dict()[name].cpu()
+    diff = (w - p1[name].detach()).abs()
+    assert diff.max().item() <= 2.1e-4 and diff.median().item() < 2e-5, (diff.max().item(), diff.median().item())

@@ -239,3 +239,24 @@ def test_gradient_buckets_cover_the_flat_buffer_in_completion_order():
                     if lo <= off < hi and name not in owner:               # gates / head: only in the last bucket
                         assert trig == last_trigger, (plan.kind, trig, name)
         assert [t for t, _ in buckets] == sorted([t for t, _ in buckets], key=lambda t: done_at[t])
+
+
+def test_flat_gradient_slots_have_the_parameter_shapes():
+    """The fused trainer keeps parameters, Adam state and gradients in ONE flat layout (engine.GradLayout): every slot must
+    have exactly the shape of the module parameter it belongs to -- including the ConvTranspose2d weights [Cin,Cout,2,2] of
+    learned_bilinear=True (netblocks.py:11-14), whose 3x3 stand-in gradient is re-indexed into the slot -- and the slots
+    must tile the buffer without overlap (4-float alignment gaps only)."""
+    import aide_b200
+    from aide_b200 import engine as E
+    for ctor, plan in ((aide_b200.fuseunet, E.plan_fuseunet), (aide_b200.UNet, E.plan_unet)):
+        for lb in (False, True):
+            net = ctor(num_classes=2, learned_bilinear=lb)
+            gl = E.GradLayout(plan(2, learned_bilinear=lb))
+            named = dict(net.named_parameters())
+            assert set(named) == set(gl.off)
+            end = 0
+            for name, (off, shape) in sorted(gl.off.items(), key=lambda kv: kv[1][0]):
+                assert tuple(named[name].shape) == shape, (name, lb)
+                assert off >= end and off - end < 4 and (off % 4 == 0 or name.endswith((".bias", "bn.weight")))
+                end = off + named[name].numel()
+            assert gl.total - end < 4
