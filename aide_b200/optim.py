@@ -108,6 +108,45 @@ class FlatAdamAMSGrad(torch.optim.Optimizer):
     def bump_versions(self) -> None:
         torch.autograd.graph.increment_version(self.params)
 
+    # ---- checkpoint / resume: the entries of torch.optim.Adam(amsgrad=True).state_dict() (the reference's optimiser,
+    # trainchaos_proposed_30cases1labeled.py:231-232), parameters numbered in this optimiser's (flat-buffer) order
+    def state_dict(self):
+        step = float(int(self.step_dev.item()))
+        state = {}
+        if step > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                sl = slice(o, o + p.numel())
+                state[i] = dict(step=torch.tensor(step), exp_avg=self.m[sl].view_as(p).clone(),
+                                exp_avg_sq=self.v[sl].view_as(p).clone(), max_exp_avg_sq=self.vmax[sl].view_as(p).clone())
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=0, amsgrad=True,
+                     params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd) -> None:
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(self.params):
+            raise ValueError("optimiser state has a different number of parameters")
+        if not group.get("amsgrad", True) or group.get("weight_decay", 0) != 0:
+            raise ValueError("FlatAdamAMSGrad is Adam(amsgrad=True, weight_decay=0)")
+        self.betas, self.eps = tuple(group["betas"]), float(group["eps"])
+        self.param_groups[0]["betas"], self.param_groups[0]["eps"] = self.betas, self.eps
+        self.set_lr(float(group["lr"]))
+        for buf in (self.m, self.v, self.vmax):
+            buf.zero_()
+        step = 0
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                continue
+            sl = slice(o, o + p.numel())
+            self.m[sl].copy_(st["exp_avg"].reshape(-1))
+            self.v[sl].copy_(st["exp_avg_sq"].reshape(-1))
+            self.vmax[sl].copy_(st["max_exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        self.step_dev.fill_(step)
+        self.t = step
+
 
 class PolyLR(_LRScheduler):
     def __init__(self, optimizer, max_epoch, power=0.9, last_epoch=-1):

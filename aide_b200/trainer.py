@@ -144,6 +144,30 @@ class AideTrainer:
         self.graph_launches = 0          # kernels launched through graph replays (aide_launch_count() sees eager ones)
 
     # ------------------------------------------------------------------------------------------
+    # checkpoint / resume.  The reference saves {'net': state_dict, 'loss', 'epoch'} per network
+    # (trainchaos_proposed_30cases1labeled.py:504-526) and never the optimiser; state_dict() holds both so that a resumed
+    # run continues bit for bit.
+    def state_dict(self) -> Dict:
+        return {"net1": self.net1.state_dict(), "net2": self.net2.state_dict(), "opt1": self.opt1.state_dict(),
+                "opt2": self.opt2.state_dict(), "steps": self.steps}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        torch.cuda.synchronize(self.device)
+        self.net1.load_state_dict(sd["net1"])        # in place: the parameters stay views of the flat buffers
+        self.net2.load_state_dict(sd["net2"])
+        self.opt1.load_state_dict(sd["opt1"])
+        self.opt2.load_state_dict(sd["opt2"])
+        self.steps = int(sd.get("steps", 0))
+        for net, opt in ((self.net1, self.opt1), (self.net2, self.opt2)):
+            net._weights = None                       # operand-format weight planes follow the new values
+            opt.bump_versions()
+
+    def save_reference_checkpoints(self, path1: str, path2: str, epoch: int, loss1=None, loss2=None) -> None:
+        """The two files the reference writes for its best epoch (:507-526); loadable by the unmodified scripts."""
+        for net, path, loss in ((self.net1, path1, loss1), (self.net2, path2, loss2)):
+            torch.save({"net": net.state_dict(), "loss": loss, "epoch": epoch}, path)
+
+    # ------------------------------------------------------------------------------------------
     def _state_tensors(self) -> List[torch.Tensor]:
         out = []
         for opt in (self.opt1, self.opt2):

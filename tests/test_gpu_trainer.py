@@ -204,3 +204,48 @@ def test_trainer_step_learned_bilinear_decoder(oracle, graph):
     w = tr.net1.state_dict()[name].cpu()
     diff = (w - p1[name].detach()).abs()
     assert diff.max().item() <= 2.1e-4 and diff.median().item() < 2e-5, (diff.max().item(), diff.median().item())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_checkpoint_resume_is_bit_exact(oracle, graph, tmp_path):
+    """Checkpoint / resume: two steps, state_dict() through torch.save / torch.load, a third step -- a fresh trainer that
+    loads the checkpoint and runs the same third step must land on the same bits (weights, BatchNorm buffers, Adam state,
+    losses).  The optimiser part has the entries of torch.optim.Adam(amsgrad=True).state_dict(); the per-network files of
+    the reference (trainchaos_proposed_30cases1labeled.py:504-526) load into the modules."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    d = lambda t: t.to(dev)
+    dev_batch = lambda b: (tuple(d(t) for t in b[0]), d(b[1]), d(b[2]), [tuple(d(t) for t in a) for a in b[3]])
+    batches = [dev_batch(batch(oracle, B, S, 900 + i)) for i in range(3)]
+    a = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+    for i in range(2):
+        a.step(*batches[i], 0.25)
+    path = str(tmp_path / "trainer.pt")
+    torch.save(a.state_dict(), path)
+    a.save_reference_checkpoints(str(tmp_path / "n1.pkl"), str(tmp_path / "n2.pkl"), epoch=3, loss1=0.5, loss2=0.6)
+    ma = a.step(*batches[2], 0.25)
+    la = (ma["loss1"].item(), ma["loss2"].item())
+    b = AideTrainer("fuseunet", mode="parity", device=dev, seed=7, cuda_graph=graph)      # different initial weights
+    b.load_state_dict(torch.load(path, map_location=dev))
+    mb = b.step(*batches[2], 0.25)
+    assert (mb["loss1"].item(), mb["loss2"].item()) == la
+    for (ka, va), (kb, vb) in zip(a.net1.state_dict().items(), b.net1.state_dict().items()):
+        assert torch.equal(va, vb), ka
+    for x, y in ((a.opt2.m, b.opt2.m), (a.opt2.v, b.opt2.v), (a.opt2.vmax, b.opt2.vmax), (a.opt2.flat, b.opt2.flat)):
+        assert torch.equal(x, y)
+    assert int(b.opt1.step_dev.item()) == 3 and b.steps == 3
+    # the optimiser part has torch.optim.Adam's per-parameter entries (step, exp_avg, exp_avg_sq, max_exp_avg_sq), numbered
+    # in the flat buffer's parameter order
+    import aide_b200 as A
+    ref_net = A.fuseunet(num_classes=2, mode="parity").to(dev)
+    ck = torch.load(path, map_location=dev)
+    order = sorted(a.net1._glayout.off.items(), key=lambda kv: kv[1][0])
+    assert len(ck["opt1"]["state"]) == len(order) == len(list(ref_net.parameters()))
+    assert set(ck["opt1"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"}
+    named = dict(ref_net.named_parameters())
+    for i, (name, _) in enumerate(order):
+        assert ck["opt1"]["state"][i]["exp_avg"].shape == named[name].shape
+    # the reference-format file loads into a module and reproduces net1 after two steps
+    ref_net.load_state_dict(torch.load(str(tmp_path / "n1.pkl"), map_location=dev)["net"])
+    assert torch.equal(ref_net.state_dict()["last_conv1.weight"], ck["net1"]["last_conv1.weight"])
