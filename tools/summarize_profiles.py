@@ -120,5 +120,48 @@ def traffic(src: str, out: str) -> None:
     print(f"wrote {out}: {key} ({len(per)} layers, {sum(per) / 1e6:.1f} MB total)")
 
 
+def hbm(src: str, out: str) -> None:
+    """`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` log of
+    tools/profile_step.py -> <out>.md: per kernel launches, time, DRAM bytes, GB/s against the measured copy peak."""
+    import json
+    import os
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        peak = 6544.0
+    per = {}
+    with open(src) as f:
+        for line in f:
+            if line.startswith('"ID"'):
+                break
+        for r in csv.reader(f):
+            if len(r) < 15:
+                continue
+            e = per.setdefault(int(r[0]), dict(name=short(r[4]), ns=0.0, bytes=0.0))
+            v = float(r[14].replace(",", ""))
+            unit = r[13].lower()
+            if "time_duration" in r[12]:
+                e["ns"] += v * {"ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(unit, 1)
+            else:
+                e["bytes"] += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for e in per.values():
+        a = agg[e["name"]]
+        a[0] += 1
+        a[1] += e["ns"]
+        a[2] += e["bytes"]
+    with open(out + ".md", "w") as f:
+        f.write("# Memory-side kernels of one stacked pseudo-label forward (4 views x 8) + one train forward / backward "
+                "(fuseunet, 256x256, F16X2)\n\n")
+        f.write("ncu `gpu__time_duration.sum`, `dram__bytes_read.sum + dram__bytes_write.sum` per kernel (`tools/profile_step.py`, "
+                f"eager launches, cold caches, serialised); peak = measured copy bandwidth {peak:.0f} GB/s.  Kernels that move "
+                "little data (statistics folds, column reductions) are listed for their time.\n\n")
+        f.write("| kernel | launches | total ms | DRAM GB | GB/s | of measured peak |\n|---|---:|---:|---:|---:|---:|\n")
+        for name, (n, ns, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            gbs = b / ns if ns else 0.0
+            f.write(f"| `{name}` | {n} | {ns / 1e6:.3f} | {b / 1e9:.3f} | {gbs:.0f} | {gbs / peak:.2f} |\n")
+    print(f"wrote {out}.md ({len(per)} launches)")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "hbm": hbm}[sys.argv[1]](sys.argv[2], sys.argv[3])
