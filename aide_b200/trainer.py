@@ -141,6 +141,10 @@ class AideTrainer:
         self.cuda_graph = bool(cuda_graph)
         self._graphs: Dict[tuple, tuple] = {}
         self._aug_dev = None             # (matrices, modes, flips) of the current step's reverse augmentation, or None
+        self._staging: Dict[tuple, list] = {}        # device staging buffers of step_from_host(prefetch=...)
+        self._staged = None                          # (host batch, its device copy, event) started by the previous call
+        self._copy_stream = None
+        self._consumed = None
         self.graph_launches = 0          # kernels launched through graph replays (aide_launch_count() sees eager ones)
 
     # ------------------------------------------------------------------------------------------
@@ -393,6 +397,8 @@ class AideTrainer:
                 self._aug_dev = None
         graph, static, out, n_kernels = entry
         self._fill_static(static, xs, t1, t2, augs)            # D2D, or H2D straight into the graph's inputs
+        self._consumed = torch.cuda.Event()                     # the step's inputs have left their source buffers
+        self._consumed.record()
         if host_aug is not None:
             for d, s_ in zip(static["aug"], host_aug):
                 d.copy_(s_, non_blocking=True)
@@ -453,15 +459,55 @@ class AideTrainer:
                     out1=m1["logits"], out2=m2["logits"])
 
     # ------------------------------------------------------------------------------------------
-    def step_from_host(self, host_batch: Dict, rate: float, device_batch: Optional[Dict] = None):
+    def _stage(self, host_batch: Dict) -> None:
+        """Start the H2D copy of the NEXT step's inputs on the copy stream, into staging buffers on the device: it runs
+        while the current step computes (the loader-side prefetch of a training loop)."""
+        flat = list(self._inputs(host_batch["x"])) + [host_batch["t1"], host_batch["t2"]] + \
+            [t for a in host_batch["augs"] for t in self._inputs(a)]
+        key = tuple((tuple(t.shape), t.dtype) for t in flat)
+        st = self._staging.get(key)
+        if st is None:
+            st = self._staging[key] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in flat]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)          # the previous contents of the staging buffers were copied onwards
+        else:
+            cs.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(cs):
+            for d, s_ in zip(st, flat):
+                d.copy_(s_, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        nx, na = len(self._inputs(host_batch["x"])), len(host_batch["augs"])
+        per = len(self._inputs(host_batch["augs"][0])) if na else 0
+        dev = dict(x=tuple(st[:nx]), t1=st[nx], t2=st[nx + 1],
+                   augs=[tuple(st[nx + 2 + v * per: nx + 2 + (v + 1) * per]) for v in range(na)])
+        self._staged = (host_batch, dev, ready)
+
+    def step_from_host(self, host_batch: Dict, rate: float, device_batch: Optional[Dict] = None,
+                       prefetch: Optional[Dict] = None):
         """End-to-end form: `host_batch` holds pinned CPU tensors (x: tuple, t1, t2, augs: list of tuples).
-        Copies them to the device (async, current stream), runs the step and reads the two losses and Dice sums
-        back to the host.  Returns (dict of python floats, h2d bytes, d2h bytes)."""
+        Copies them to the device (async), runs the step and reads the two losses and Dice sums back to the host.
+        `prefetch`: the batch of the NEXT call -- its H2D copy is started on a copy stream right after this step's launch
+        and overlaps the step's compute; the next call (given the same dict) then finds its inputs on the device.
+        Returns (dict of python floats, h2d bytes, d2h bytes)."""
         h2d = 0
         for t in list(self._inputs(host_batch["x"])) + [host_batch["t1"], host_batch["t2"]] + \
                 [t for a in host_batch["augs"] for t in self._inputs(a)]:
             h2d += t.numel() * t.element_size()
-        out = self.step(host_batch["x"], host_batch["t1"], host_batch["t2"], host_batch["augs"], rate)
+        src = host_batch
+        if self._staged is not None and self._staged[0] is host_batch:          # prefetched by the previous call
+            _, src, ready = self._staged
+            torch.cuda.current_stream(self.device).wait_event(ready)
+        self._staged = None
+        out = self.step(src["x"], src["t1"], src["t2"], src["augs"], rate)
+        if not self.cuda_graph:                    # eager steps read their inputs until they finish
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        if prefetch is not None:
+            self._stage(prefetch)
         res = torch.stack([out["loss1"], out["loss2"], out["dice1"], out["dice2"]]).to("cpu")   # synchronising D2H
         vals = res.tolist()
         return dict(loss1=vals[0], loss2=vals[1], dice1=vals[2], dice2=vals[3]), h2d, res.numel() * 4

@@ -249,3 +249,26 @@ def test_trainer_checkpoint_resume_is_bit_exact(oracle, graph, tmp_path):
     # the reference-format file loads into a module and reproduces net1 after two steps
     ref_net.load_state_dict(torch.load(str(tmp_path / "n1.pkl"), map_location=dev)["net"])
     assert torch.equal(ref_net.state_dict()["last_conv1.weight"], ck["net1"]["last_conv1.weight"])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_step_from_host_prefetch_gives_the_same_steps(oracle, graph):
+    """step_from_host(batch, prefetch=next) starts the next batch's H2D copy on a copy stream while the step computes; the
+    results must be those of the plain call sequence, also when the following call does NOT use the prefetched batch."""
+    from aide_b200.trainer import AideTrainer
+    dev = torch.device("cuda:0")
+    B, S = 4, 64
+    hosts = []
+    for i in range(4):
+        x, t1, t2, augs = batch(oracle, B, S, 950 + i)
+        hosts.append(dict(x=tuple(t.pin_memory() for t in x), t1=t1.pin_memory(), t2=t2.pin_memory(),
+                          augs=[tuple(t.pin_memory() for t in a) for a in augs]))
+    a = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+    b = AideTrainer("fuseunet", mode="parity", device=dev, seed=2, cuda_graph=graph)
+    order = [0, 1, 2, 0, 3]
+    nxt = [1, 2, 3, 3, None]                      # call 2 prefetches batch 3 but call 3 then runs batch 0: staged copy unused
+    for i, k in enumerate(order):
+        va, _, _ = a.step_from_host(hosts[k], 0.25)
+        vb, h2d, d2h = b.step_from_host(hosts[k], 0.25, prefetch=None if nxt[i] is None else hosts[nxt[i]])
+        assert va == vb, (i, va, vb)
+    assert torch.equal(a.opt1.flat, b.opt1.flat) and torch.equal(a.opt2.flat, b.opt2.flat)
