@@ -39,6 +39,7 @@ SIGNATURES = {
     "aide_conv3x3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "aide_conv3x3_dgrad": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "aide_conv3x3_wgrad": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "aide_conv3x3_wgrad_ex": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _i, _i, _vp, _vp]),
     "aide_bn_finalize": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp]),
     "aide_bn_finalize_grouped": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "aide_bn_ticket_slots": (_i, [_i]),

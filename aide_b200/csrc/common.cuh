@@ -12,6 +12,18 @@
 
 namespace aide {
 
+// A column sum out[j] = sum_r src[r * ld + j] that rides along with the split-K reduction of a weight gradient (the conv
+// bias gradient of the same unit: one launch less per unit).  aide_conv3x3_wgrad_ex posts it for the calling thread,
+// the next launch_wgrad_reduce() on that thread takes it.
+struct ColSumJob {
+  const float* src;
+  int rows, ld, cols;
+  float* dst;
+};
+void wgrad_reduce_post_job(const ColSumJob& job);
+bool wgrad_reduce_take_job(ColSumJob* job);
+
+
 // ------------------------------------------------------------------ error plumbing
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

@@ -38,6 +38,7 @@ int c3_stat_rows(int N, int H, int W);
 int c3_conv3x3(const float* x, int x_ctot, int x_coff, const float* w, const float* bias, float* z, int z_ctot,
                int z_coff, int cout, int N, int H, int W, float* stat_partial, cudaStream_t st);
 size_t c3_wgrad_workspace_bytes(int cout, int N, int H, int W);
+int launch_reduce_rows(const float* partial, int rows, int ld, int cols, float* out, cudaStream_t st);
 int c3_wgrad(const float* x, int x_ctot, int x_coff, const float* dz, int cout, int N, int H, int W, float* ws,
              size_t ws_bytes, float* dw, cudaStream_t st);
 }  // namespace aide
@@ -131,6 +132,24 @@ extern "C" int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, i
   return tc_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, cout, N, H, W, workspace, workspace_bytes, dw_oihw,
                   fmt == AIDE_FMT_F16X2 ? 1.0f / kF16ActScale : 1.0f, fmt == AIDE_FMT_F16X2 ? dz_inv_scale : nullptr,
                   as_stream(stream));
+}
+
+// Same, plus a column sum out[j] = sum_r src[r * cols + j] (rows x cols fp32, e.g. the conv-bias gradient from the partial
+// rows of aide_bn_relu_bwd_apply) folded into the split-K reduction launch of the weight gradient.
+extern "C" int aide_conv3x3_wgrad_ex(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                                     const void* dz_p0, const void* dz_p1, const float* dz_inv_scale, int cout, int N, int H,
+                                     int W, void* workspace, size_t workspace_bytes, float* dw_oihw, const float* colsum_src,
+                                     int colsum_rows, int colsum_cols, float* colsum_dst, void* stream) {
+  const bool want = colsum_src && colsum_dst && colsum_rows > 0 && colsum_cols > 0;
+  if (want) wgrad_reduce_post_job(ColSumJob{colsum_src, colsum_rows, colsum_cols, colsum_cols, colsum_dst});
+  const int rc = aide_conv3x3_wgrad(fmt, x_p0, x_p1, x_ctot, x_coff, cin, dz_p0, dz_p1, dz_inv_scale, cout, N, H, W, workspace,
+                                    workspace_bytes, dw_oihw, stream);
+  ColSumJob left;
+  if (want && wgrad_reduce_take_job(&left)) {       // a path without the shared reduction kernel (first layer), or an error
+    if (rc) return rc;
+    return launch_reduce_rows(left.src, left.rows, left.ld, left.cols, left.dst, as_stream(stream));
+  }
+  return rc;
 }
 
 // ---- inference: conv3x3 + eval-mode BatchNorm + ReLU (+ MaxPool2d) in ONE launch ---------------------------------------

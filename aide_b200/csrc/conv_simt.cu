@@ -176,12 +176,34 @@ wgrad_simt_kernel(const float* __restrict__ x, int x_ctot, int x_coff, int cin, 
   }
 }
 
-// dw_oihw[co][ci][tap] = sum_split ws[split][...]; layout 0: [co][tap][ci], layout 1: [tap][ci][co]
+// dw_oihw[co][ci][tap] = sum_split ws[split][...]; layout 0: [co][tap][ci], layout 1: [tap][ci][co].
+// The last `job_blocks` blocks of the grid do a posted column sum instead (32 columns x 8 row lanes each, fp64, fixed order).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int layout,
-                                    float* __restrict__ dw, float scale, const float* __restrict__ scale_ptr) {
+                                    float* __restrict__ dw, float scale, const float* __restrict__ scale_ptr,
+                                    ColSumJob job, int job_blocks) {
+  const int main_blocks = gridDim.x - job_blocks;
+  if ((int)blockIdx.x >= main_blocks) {
+    __shared__ double sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = (blockIdx.x - main_blocks) * 32 + tx;
+    double acc = 0.0;
+    if (j < job.cols) {
+#pragma unroll 4
+      for (int r = ty; r < job.rows; r += 8) acc += (double)job.src[(size_t)r * job.ld + j];
+    }
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < job.cols) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[k][tx];
+      job.dst[j] = (float)t;
+    }
+    return;
+  }
   size_t total = (size_t)cout * cin * 9;
   if (scale_ptr) scale *= __ldg(scale_ptr);      // descale of the operand formats (static) x gradient scale (dynamic)
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)main_blocks * blockDim.x) {
     // i indexes the workspace layout (coalesced reads)
     int co, ci, tap;
     if (layout == 0) {
@@ -199,12 +221,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
   }
 }
 
+namespace {
+thread_local ColSumJob t_job{nullptr, 0, 0, 0, nullptr};
+}
+void wgrad_reduce_post_job(const ColSumJob& job) { t_job = job; }
+bool wgrad_reduce_take_job(ColSumJob* job) {
+  if (!t_job.src) return false;
+  *job = t_job;
+  t_job.src = nullptr;
+  return true;
+}
+
 int launch_wgrad_reduce(const float* ws, int splits, int cout, int cin, int layout, float* dw, float scale,
                         const float* scale_ptr, cudaStream_t st) {
   size_t total = (size_t)cout * cin * 9;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splits, cout, cin, layout, dw, scale, scale_ptr);
+  ColSumJob job{nullptr, 0, 0, 0, nullptr};
+  const int job_blocks = wgrad_reduce_take_job(&job) ? ceil_div(job.cols, 32) : 0;
+  wgrad_reduce_kernel<<<blocks + job_blocks, 256, 0, st>>>(ws, splits, cout, cin, layout, dw, scale, scale_ptr, job,
+                                                           job_blocks);
   AIDE_CHECK_LAUNCH();
   return 0;
 }

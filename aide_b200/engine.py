@@ -740,9 +740,12 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
             rows = lib.aide_bn_bwd_rows(N, h, w, u.cout)
             dz0 = bb + off["dz%d" % k]
             dz1 = dz0 + _align(N * h * w * u.cout * _esize(ufmt)) if _planes(ufmt) == 2 else None
+            # the conv-bias gradient (column sums of part2) rides in the wgrad's split-K reduction launch -- unless the
+            # wgrad runs on the side stream, where part2 could be overwritten by the next unit before it is read
+            fuse_db = side is None or u.transposed
             call("aide_bn_relu_bwd_apply", ufmt, g, z, mr, params[u.bn + ".weight"].data_ptr(), part, rows,
-                 N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"), gptr(u.conv + ".bias"),
-                 part2, gmax, dz_scale, bb + off["gscale"] + 64, st)
+                 N, h, w, u.cout, dz0, dz1, gptr(u.bn + ".weight"), gptr(u.bn + ".bias"),
+                 None if fuse_db else gptr(u.conv + ".bias"), part2, gmax, dz_scale, bb + off["gscale"] + 64, st)
             x0, x1, xct, xco = aview(u.src[0], u.src[1])
             wst = st
             dw_dst = bb + off["dk:" + u.name] if u.transposed else gptr(u.conv + ".weight")
@@ -753,8 +756,12 @@ def run_backward(plan: Plan, bplan: BackwardPlan, glayout: GradLayout, layout: L
                 ready.record(main)
                 side.wait_event(ready)
                 wst = side.cuda_stream
-            call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
-                 bb + off["ws"], max_ws, dw_dst, wst)
+            if fuse_db:
+                call("aide_conv3x3_wgrad_ex", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
+                     bb + off["ws"], max_ws, dw_dst, part2, rows, u.cout, gptr(u.conv + ".bias"), wst)
+            else:
+                call("aide_conv3x3_wgrad", ufmt, x0, x1, xct, xco, u.cin, dz0, dz1, dz_inv, u.cout, N, h, w,
+                     bb + off["ws"], max_ws, dw_dst, wst)
             if u.transposed:                        # dW[ci,co,a,b] = dK[co,ci,1-a,1-b]: tensor re-indexing into the slot
                 o0 = off["dk:" + u.name]
                 dk = barena[o0:o0 + u.cout * u.cin * 36].view(torch.float32).view(u.cout, u.cin, 3, 3)

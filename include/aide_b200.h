@@ -112,6 +112,13 @@ size_t aide_conv3x3_wgrad_workspace_bytes(int fmt, int cin, int cout, int N, int
 int aide_conv3x3_wgrad(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
                        const void* dz_p0, const void* dz_p1, const float* dz_inv_scale, int cout, int N, int H, int W,
                        void* workspace, size_t workspace_bytes, float* dw_oihw, void* stream);
+/* aide_conv3x3_wgrad plus a column sum colsum_dst[j] = sum_r colsum_src[r * colsum_cols + j] folded into the weight gradient's
+ * split-K reduction launch -- the conv-bias gradient of the same unit from the partial rows aide_bn_relu_bwd_apply leaves in
+ * partial2 (pass dbias_conv = NULL there): one launch less per unit (nn.Conv2d bias gradient, netblocks.py:24,26). */
+int aide_conv3x3_wgrad_ex(int fmt, const void* x_p0, const void* x_p1, int x_ctot, int x_coff, int cin,
+                          const void* dz_p0, const void* dz_p1, const float* dz_inv_scale, int cout, int N, int H, int W,
+                          void* workspace, size_t workspace_bytes, float* dw_oihw, const float* colsum_src,
+                          int colsum_rows, int colsum_cols, float* colsum_dst, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +MaxPool2d(2,2), +concat slot) (netblocks.py:25,27,28; fuseunet.py:13-31) */
 /* Reduce the conv's partial statistics in fixed order (fp64), then
