@@ -117,10 +117,10 @@ def test_conv_planner_returns_valid_tilings_for_every_layer():
     import ctypes as C
     from aide_b200 import engine as E, lib
     out = (C.c_int * 9)()
-    checked = 0
+    checked = pairs = 0
     for plan in (E.plan_fuseunet(2), E.plan_unet(2)):
         for S in (256, 320):
-            for B in (4, 8, 32):
+            for B in (1, 4, 8, 32, 40):
                 for u in plan.units:
                     if u.first:
                         continue
@@ -147,7 +147,9 @@ def test_conv_planner_returns_valid_tilings_for_every_layer():
                             lib.aide_conv3x3_plan_info(fmt, cin, cout, B, h, h, again)
                             assert list(again) == list(out)
                             checked += 1
+                            pairs += bool(flags & 8)
     assert checked > 1000
+    assert pairs > checked // 4          # the measured plan table is wired in: most >= 64-channel layers run as CTA pairs
 
 
 def test_stat_rows_scale_with_batch_groups():
